@@ -134,6 +134,11 @@ struct lcbo {
     std::vector<Block> blocks; // blocksInstance_
     int64_t blocks_found = 0;
     uint64_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef LCBO_EPOCH
+    std::vector<uint32_t> epoch;
+    uint32_t thresh = 0;
+    mutable std::vector<int64_t> *readlog = nullptr;
+#endif
 
     // ----- iterator helpers: JunctionSequentialIterator, junctionstorage.h:158-396 -----
     int64_t Vertex(int64_t g, bool pos) const { return pos ? pos_id[g] : -(int64_t)pos_id[g]; }   // :171-174
@@ -141,9 +146,16 @@ struct lcbo {
     bool Valid(int64_t g, int32_t chr) const { return g >= chr_off[chr] && g < chr_off[chr + 1]; }  // :265-268
     bool IsUsed(int64_t g, bool pos) const                                                          // :270-283
     {
+#ifdef LCBO_EPOCH /* experiments/jacobi_proto.cpp: `used` seen through an epoch threshold, reads logged */
+        if (!pos && g <= chr_off[pos_chr[g]]) return false;
+        int64_t f = pos ? g : g - 1;
+        if (readlog) readlog->push_back(f);
+        return epoch[f] < thresh;
+#else
         if (pos) return used[g] != 0;
         if (g > chr_off[pos_chr[g]]) return used[g - 1] != 0;
         return false;
+#endif
     }
     void MarkUsed(int64_t g, bool pos) // :285-295
     {
@@ -241,6 +253,18 @@ struct lcbo {
     bool Compatible(int64_t sg, bool spos, int64_t eg, bool epos, const PEdge &e) // path.h:380-428
     {
         if (spos != epos) return false;
+#ifdef LCBO_EPOCH /* experiment: the pure distance tests first, so the flag scan is bounded by max_branch bp */
+        {
+            int64_t rd = Position(eg, epos) - Position(sg, spos);
+            if (!spos) rd = -rd;
+            if (rd < 0) return false;
+            int64_t ad = (int64_t)DistGet(Vertex(eg, epos)) - (int64_t)DistGet(Vertex(sg, spos));
+            int64_t n1 = Step(sg, spos);
+            if ((rd > max_branch || ad > max_branch) &&
+                (!Valid(n1, (int32_t)pos_chr[sg]) || GetChar(sg, spos) != e.ch || eg != n1 || Vertex(n1, spos) != e.ev))
+                return false;
+        }
+#endif
         for (int64_t it = sg; it != eg; it = Step(it, spos)) {
             ctr[2]++;
             if (IsUsed(it, spos)) return false;
@@ -955,6 +979,11 @@ int main(int argc, char **argv)
     if (lcbo_generate_output(L, argv[6], !atoi(argv[7]), atoi(argv[8]), m, &found, &cov, err, sizeof err)) {
         fprintf(stderr, "error: %s\n", err);
         return 1;
+    }
+    if (const char *dump = getenv("LCBO_DUMP_BLOCKS")) { // raw blocksInstance_ in commit order, for experiments
+        FILE *f = fopen(dump, "w");
+        for (auto &bk : L->blocks) fprintf(f, "%d %zu %zu %zu\n", bk.id, bk.chr, bk.start, bk.end);
+        fclose(f);
     }
     uint64_t c[8];
     lcbo_get_counters(L, c);

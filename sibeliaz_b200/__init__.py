@@ -1,0 +1,306 @@
+"""sibeliaz_b200 -- B200-native sibeliaz-lcb hot path (JunctionStorage + BlocksFinder).
+
+Thin ctypes mirror of the reference's C++ call sequence (SibeliaZ-LCB/sibeliaz.cpp:125-143) on top of
+the C ABI in include/sibeliaz_lcb.h:
+
+    storage = JunctionStorage(graph, fastas, k, abundance)        # junctionstorage.h:653
+    finder = BlocksFinder(storage, k)                             # blocksfinder.h:213
+    finder.find_blocks(min_block, max_branch, max_flank)          # blocksfinder.h:453
+    finder.generate_output(out_dir, gen_seq, chunks)              # blocksfinder.h:605
+
+Python is plumbing for tests and bench only; all work happens in libsibeliaz_lcb.so (C++/CUDA, sm_100a).
+There is no CPU fallback: constructing a BlocksFinder without a usable B200-class GPU raises LcbError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsibeliaz_lcb.so")
+CLI_PATH = os.path.join(_HERE, "bin", "sibeliaz-lcb")
+
+LCB_OK = 0
+ERR_NAMES = {1: "LCB_ERR_ARG", 2: "LCB_ERR_IO", 3: "LCB_ERR_FORMAT", 4: "LCB_ERR_CUDA", 5: "LCB_ERR_CAPACITY",
+             6: "LCB_ERR_STATE"}
+
+EXPORTS = ["lcb_index_load", "lcb_index_get_view", "lcb_index_num_chr", "lcb_index_chr_name", "lcb_index_chr_length",
+           "lcb_index_free", "lcb_default_params", "lcb_create", "lcb_comm_unique_id", "lcb_comm_init",
+           "lcb_enumerate_seeds", "lcb_get_seeds", "lcb_find_blocks", "lcb_free_blocks", "lcb_get_stats",
+           "lcb_last_error", "lcb_destroy", "lcb_write_output", "lcb_version"]
+
+
+class LcbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s: %s" % (ERR_NAMES.get(code, code), message))
+        self.code = code
+
+
+class IndexView(C.Structure):
+    _fields_ = [("n_chr", C.c_int32), ("n_records", C.c_int64), ("n_vertices", C.c_int64),
+                ("chr_off", C.POINTER(C.c_int64)), ("pos_id", C.POINTER(C.c_int32)), ("pos_bp", C.POINTER(C.c_uint32)),
+                ("next_ch", C.POINTER(C.c_uint8)), ("prev_rc", C.POINTER(C.c_uint8)), ("vtx_off", C.POINTER(C.c_int64)),
+                ("occ_g", C.POINTER(C.c_int64))]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("k", "max_branch", "min_block", "max_flank", "looking_depth", "phase_size",
+                                         "window_init", "window_max", "device", "collect_counters")]
+
+
+class BlockInstance(C.Structure):
+    _fields_ = [("id", C.c_int32), ("chr", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32)]
+
+
+BLOCK_DTYPE = np.dtype([("id", "<i4"), ("chr", "<u4"), ("start", "<u4"), ("end", "<u4")])
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_records", "n_vertices", "n_seeds", "n_block_instances", "n_blocks", "windows",
+                                          "rounds", "traversals_first", "traversals_rerun", "kernel_launches", "t_walk",
+                                          "t_occ", "t_scan", "t_score")] + \
+               [("ms_enumerate", C.c_double), ("ms_find", C.c_double), ("ms_traverse_kernels", C.c_double),
+                ("traverse_launches", C.c_uint64), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the in-tree C-ABI library (built by sibeliaz_b200.build); never falls back to anything else."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise LcbError(4, "%s is missing: run `python -m sibeliaz_b200.build` (there is no fallback path)" % path)
+    lib = C.CDLL(path)
+    lib.lcb_index_load.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    lib.lcb_index_get_view.argtypes = [C.c_void_p, C.POINTER(IndexView)]
+    lib.lcb_index_num_chr.argtypes = [C.c_void_p]
+    lib.lcb_index_num_chr.restype = C.c_int32
+    lib.lcb_index_chr_name.argtypes = [C.c_void_p, C.c_int32]
+    lib.lcb_index_chr_name.restype = C.c_char_p
+    lib.lcb_index_chr_length.argtypes = [C.c_void_p, C.c_int32]
+    lib.lcb_index_chr_length.restype = C.c_int64
+    lib.lcb_index_free.argtypes = [C.c_void_p]
+    lib.lcb_index_free.restype = None
+    lib.lcb_default_params.argtypes = [C.POINTER(Params)]
+    lib.lcb_default_params.restype = None
+    lib.lcb_create.argtypes = [C.POINTER(IndexView), C.POINTER(Params), C.POINTER(C.c_void_p)]
+    lib.lcb_comm_unique_id.argtypes = [C.c_void_p]
+    lib.lcb_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.lcb_enumerate_seeds.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.lcb_get_seeds.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    lib.lcb_find_blocks.argtypes = [C.c_void_p, C.POINTER(C.POINTER(BlockInstance)), C.POINTER(C.c_uint64), C.POINTER(Stats)]
+    lib.lcb_free_blocks.argtypes = [C.POINTER(BlockInstance)]
+    lib.lcb_free_blocks.restype = None
+    lib.lcb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.lcb_last_error.argtypes = [C.c_void_p]
+    lib.lcb_last_error.restype = C.c_char_p
+    lib.lcb_destroy.argtypes = [C.c_void_p]
+    lib.lcb_destroy.restype = None
+    lib.lcb_write_output.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
+    lib.lcb_version.restype = C.c_char_p
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class JunctionStorage:
+    """Host-side junction index (reference: Sibelia::JunctionStorage, junctionstorage.h:116-698)."""
+
+    def __init__(self, graph_file, fasta_files, k, abundance=150):
+        lib = load_library()
+        self._lib = lib
+        self.k = int(k)
+        self._h = C.c_void_p()
+        files = (C.c_char_p * len(fasta_files))(*[os.fsencode(f) for f in fasta_files])
+        err = C.create_string_buffer(1024)
+        rc = lib.lcb_index_load(os.fsencode(graph_file), files, len(fasta_files), int(k), int(abundance),
+                                C.byref(self._h), err, len(err))
+        if rc:
+            raise LcbError(rc, err.value.decode(errors="replace"))
+        self.view = IndexView()
+        lib.lcb_index_get_view(self._h, C.byref(self.view))
+
+    # names follow the reference's accessors
+    def get_chr_number(self):
+        return self._lib.lcb_index_num_chr(self._h)
+
+    def get_chr_description(self, c):
+        return self._lib.lcb_index_chr_name(self._h, c).decode()
+
+    def get_chr_length(self, c):
+        return self._lib.lcb_index_chr_length(self._h, c)
+
+    @property
+    def n_records(self):
+        return self.view.n_records
+
+    @property
+    def n_vertices(self):
+        return self.view.n_vertices
+
+    def arrays(self):
+        """Copies of the SoA arrays as numpy (parity tests)."""
+        v = self.view
+        N, V, Cn = v.n_records, v.n_vertices, v.n_chr
+        mk = lambda p, n, dt: np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].astype(dt, copy=True) if n else np.zeros(0, dt)
+        return dict(chr_off=mk(v.chr_off, Cn + 1, np.int64), pos_id=mk(v.pos_id, N, np.int32), pos_bp=mk(v.pos_bp, N, np.uint32),
+                    next_ch=mk(v.next_ch, N, np.uint8), prev_rc=mk(v.prev_rc, N, np.uint8),
+                    vtx_off=mk(v.vtx_off, V + 1, np.int64), occ_g=mk(v.occ_g, N, np.int64))
+
+    def close(self):
+        if self._h:
+            self._lib.lcb_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ArrayStorage:
+    """An index given directly as numpy SoA arrays (what a foreign host would pass through the C ABI)."""
+
+    def __init__(self, arrays, k):
+        self.k = int(k)
+        self._keep = {n: np.ascontiguousarray(arrays[n], dt) for n, dt in
+                      (("chr_off", np.int64), ("pos_id", np.int32), ("pos_bp", np.uint32), ("next_ch", np.uint8),
+                       ("prev_rc", np.uint8), ("vtx_off", np.int64), ("occ_g", np.int64))}
+        a = self._keep
+        v = IndexView()
+        v.n_chr = len(a["chr_off"]) - 1
+        v.n_records = len(a["pos_id"])
+        v.n_vertices = len(a["vtx_off"]) - 1
+        v.chr_off = _ptr(a["chr_off"], C.c_int64)
+        v.pos_id = _ptr(a["pos_id"], C.c_int32)
+        v.pos_bp = _ptr(a["pos_bp"], C.c_uint32)
+        v.next_ch = _ptr(a["next_ch"], C.c_uint8)
+        v.prev_rc = _ptr(a["prev_rc"], C.c_uint8)
+        v.vtx_off = _ptr(a["vtx_off"], C.c_int64)
+        v.occ_g = _ptr(a["occ_g"], C.c_int64)
+        self.view = v
+        self._h = None
+
+    @property
+    def n_records(self):
+        return self.view.n_records
+
+
+class BlocksFinder:
+    """Device context (reference: Sibelia::BlocksFinder, blocksfinder.h:178-929)."""
+
+    def __init__(self, storage, k=None, device=0, window_init=0, window_max=0, collect_counters=False):
+        self._lib = load_library()
+        self.storage = storage
+        self.k = int(k if k is not None else storage.k)
+        self.device = device
+        self._window = (window_init, window_max)
+        self._collect = collect_counters
+        self._ctx = C.c_void_p()
+        self._params = None
+        self.blocks = None
+        self.stats = None
+
+    def _create(self, min_block, max_branch, max_flank, looking_depth):
+        if self._ctx:
+            self._lib.lcb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+        p = Params()
+        self._lib.lcb_default_params(C.byref(p))
+        p.k, p.min_block, p.max_branch, p.max_flank, p.looking_depth = self.k, min_block, max_branch, max_flank, looking_depth
+        p.device = self.device
+        p.window_init, p.window_max = self._window
+        p.collect_counters = 1 if self._collect else 0
+        rc = self._lib.lcb_create(C.byref(self.storage.view), C.byref(p), C.byref(self._ctx))
+        if rc:
+            msg = self._lib.lcb_last_error(self._ctx).decode() if self._ctx else "lcb_create failed"
+            if self._ctx:
+                self._lib.lcb_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise LcbError(rc, msg)
+        self._params = p
+
+    def _check(self, rc):
+        if rc:
+            raise LcbError(rc, self._lib.lcb_last_error(self._ctx).decode())
+
+    def comm_init(self, rank, n_ranks, id_bytes):
+        self._check(self._lib.lcb_comm_init(self._ctx, rank, n_ranks, id_bytes))
+
+    def create(self, min_block=200, max_branch=200, max_flank=None, looking_depth=8):
+        self._create(int(min_block), int(max_branch), int(max_branch if max_flank is None else max_flank), int(looking_depth))
+        return self
+
+    def enumerate_seeds(self):
+        if not self._ctx:
+            self.create()
+        n = C.c_uint64()
+        self._check(self._lib.lcb_enumerate_seeds(self._ctx, C.byref(n)))
+        return n.value
+
+    def seeds(self):
+        n = self.enumerate_seeds()
+        out = dict(vid=np.zeros(n, np.int64), ch=np.zeros(n, np.uint8), count=np.zeros(n, np.uint64),
+                   rank=np.zeros(n, np.uint64), res_pos=np.zeros(n, np.uint64), res_chr=np.zeros(n, np.uint64))
+        self._check(self._lib.lcb_get_seeds(self._ctx, *[out[k].ctypes.data for k in ("vid", "ch", "count", "rank", "res_pos", "res_chr")]))
+        return out
+
+    def find_blocks(self, min_block=200, max_branch=200, max_flank=None, looking_depth=8, sample_size=0, threads=1,
+                    debug_out=""):
+        """FindBlocks(minBlockSize, maxBranchSize, maxFlankingSize, lookingDepth, sampleSize, threads, debugOut);
+        the last three are accepted for signature parity and ignored (the reference ignores sampleSize/debugOut too)."""
+        if not self._ctx or self._params is None or (self._params.min_block, self._params.max_branch) != (int(min_block), int(max_branch)):
+            self.create(min_block, max_branch, max_flank, looking_depth)
+        ptr = C.POINTER(BlockInstance)()
+        n = C.c_uint64()
+        st = Stats()
+        self._check(self._lib.lcb_find_blocks(self._ctx, C.byref(ptr), C.byref(n), C.byref(st)))
+        if n.value:
+            buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value * C.sizeof(BlockInstance),))
+            self.blocks = np.frombuffer(bytes(buf), dtype=BLOCK_DTYPE).copy()
+        else:
+            self.blocks = np.zeros(0, BLOCK_DTYPE)
+        self._lib.lcb_free_blocks(ptr)
+        self.stats = st.as_dict()
+        return self.blocks
+
+    def generate_output(self, out_dir, gen_seq=False, chunks=0, min_block=None):
+        if self.blocks is None:
+            raise LcbError(6, "find_blocks has not run")
+        if self.storage._h is None:
+            raise LcbError(6, "generate_output needs a JunctionStorage loaded from files")
+        found, cov = C.c_int64(), C.c_double()
+        err = C.create_string_buffer(1024)
+        b = np.ascontiguousarray(self.blocks)
+        m = self._params.min_block if min_block is None else int(min_block)
+        rc = self._lib.lcb_write_output(self.storage._h, b.ctypes.data, len(b), m, os.fsencode(out_dir), int(bool(gen_seq)),
+                                        int(chunks), C.byref(found), C.byref(cov), err, len(err))
+        if rc:
+            raise LcbError(rc, err.value.decode(errors="replace"))
+        return found.value, cov.value
+
+    def close(self):
+        if self._ctx:
+            self._lib.lcb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

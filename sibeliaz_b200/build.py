@@ -1,0 +1,89 @@
+"""In-tree build of the sm_100a shared library and the sibeliaz-lcb CLI (explicit nvcc, no JIT cache).
+
+    python -m sibeliaz_b200.build            # build if sources are newer than the artefacts
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+BINDIR = os.path.join(HERE, "bin")
+LIB = os.path.join(LIBDIR, "libsibeliaz_lcb.so")
+CLI = os.path.join(BINDIR, "sibeliaz-lcb")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-pthread"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _host_cxx():
+    # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); the system compiler is the safe choice
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+
+
+def _nccl():
+    """(include_dir, lib_path) of a usable NCCL: the one bundled with torch, else the system one."""
+    cands = []
+    try:
+        import nvidia.nccl as n  # wheel layout used by torch
+        base = os.path.dirname(n.__file__) if getattr(n, "__file__", None) else list(n.__path__)[0]
+        cands.append((os.path.join(base, "include"), os.path.join(base, "lib", "libnccl.so.2")))
+    except Exception:
+        pass
+    cands.append(("/usr/include", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"))
+    for inc, lib in cands:
+        if os.path.exists(os.path.join(inc, "nccl.h")) and os.path.exists(lib):
+            return inc, lib
+    return None
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(BINDIR, exist_ok=True)
+    inc = os.path.join(ROOT, "include")
+    srcs = [os.path.join(CSRC, f) for f in ("lcb_device.cu", "lcb_host.cpp")]
+    deps = srcs + [os.path.join(CSRC, "lcb_traverse.cuh"), os.path.join(inc, "sibeliaz_lcb.h"), __file__]
+    nvcc = _nvcc()
+    if force or _newer(LIB, deps):
+        cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", LIB] + srcs
+        nccl = _nccl()
+        if nccl:
+            cmd += ["-DLCB_WITH_NCCL", "-I", nccl[0], "-L", os.path.dirname(nccl[1]), "-Xlinker", "-l:" + os.path.basename(nccl[1]),
+                    "-Xlinker", "-rpath," + os.path.dirname(nccl[1])]
+        cmd += ["-cudart", "shared"]
+        out = _run(cmd)
+        if verbose:
+            print(out)
+    main_src = os.path.join(CSRC, "sibeliaz_lcb_main.cpp")
+    if os.path.exists(main_src) and (force or _newer(CLI, [main_src, LIB])):
+        _run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, main_src, "-o", CLI, "-L", LIBDIR, "-lsibeliaz_lcb",
+              "-Wl,-rpath,$ORIGIN/../lib"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,1099 @@
+// lcb_device.cu -- device side of the B200 sibeliaz-lcb path and the C ABI around it (include/sibeliaz_lcb.h).
+//
+// What runs here replaces BlocksFinder::FindBlocks (SibeliaZ-LCB/blocksfinder.h:453-530):
+//   * seed (bundle) enumeration + sort                         blocksfinder.h:461-503, :517
+//   * the carving-path traversal per seed (lcb_traverse.cuh)   blocksfinder.h:228-310, path.h
+//   * the 256-seed phase / ordered-commit protocol             blocksfinder.h:334-433
+//
+// The commit protocol is sequential in the reference.  Here it is evaluated as a FIXPOINT over a window
+// of W seeds (W a multiple of the phase size; all earlier seeds are final):
+//
+//   r0_i = Process(i, edge used  <=>  epoch < phase_start(i))                 "speculative" result
+//   conf_i = |r0_i| > 1 and some edge of r0_i has epoch < i                   blocksfinder.h:375-398
+//   r1_i = Process(i, edge used  <=>  epoch < i)          (only if conf_i)    blocksfinder.h:404-412
+//   final_i = conf_i ? (|r1_i| > 1 ? r1_i : {}) : (|r0_i| > 1 ? r0_i : {})
+//   epoch'[e] = min { i : e in edges(final_i) }  over the window, on top of the committed epochs
+//
+// final_i depends only on epochs < i, so the system has exactly one solution -- the reference's result --
+// and Jacobi iteration reaches it: every round re-evaluates (all in parallel) only the seeds whose recorded
+// read-set saw a changed epoch.  Block ids and the blocksInstance_ order are then a prefix sum in seed order.
+#include "sibeliaz_lcb.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lcb_traverse.cuh"
+
+#ifdef LCB_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace lcb;
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+struct Control { // device-resident round state, mirrored to pinned host memory once per round
+    unsigned head;      // work-queue cursor of the running traversal launch
+    unsigned n0, n1;    // lengths of the two work lists (slot 0: speculative, slot 1: commit-time re-run)
+    unsigned dirty;     // seeds whose dependencies changed in the last validation
+    unsigned err;       // first LCB_ERR_* raised by a kernel
+    unsigned pool_overflow;
+    unsigned long long inst_used, rs_used; // bump allocators
+    unsigned long long ct_walk, ct_occ, ct_scan, ct_score;
+    unsigned long long runs0, runs1;
+    unsigned n_blocks, n_out; // emit: blocks / instances of the current window
+};
+
+struct Window { // per-window arrays, indexed by j = seed - w0
+    unsigned *res_off[2], *res_cnt[2]; // best instances of slot s in inst_pool
+    unsigned *rs_off[2], *rs_cnt[2];   // read-set of slot s in rs_pool
+    unsigned char *conf, *has1;
+    unsigned *blk, *out_off;
+    unsigned *list0, *list1;
+    int4 *inst_pool;
+    int2 *rs_pool;
+    unsigned long long inst_cap, rs_cap;
+};
+
+#define CUDA_TRY(x)                                                                                       \
+    do {                                                                                                  \
+        cudaError_t e_ = (x);                                                                             \
+        if (e_ != cudaSuccess) {                                                                          \
+            ctx->error = std::string(#x) + ": " + cudaGetErrorString(e_);                                 \
+            return LCB_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// traversal kernel: persistent warps pull (seed, slot) items from a list
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
+                                                        const int *__restrict__ seed_vid,
+                                                        const unsigned char *__restrict__ seed_ch, unsigned w0,
+                                                        unsigned phase, int slot, const unsigned *__restrict__ list,
+                                                        const unsigned *__restrict__ n_ptr, Window win, Control *ctl,
+                                                        unsigned char *arena_base, size_t arena_stride, int collect)
+{
+    __shared__ WarpSmem smem[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + wib;
+    Ctx c;
+    c.ix = ix;
+    c.pr = pr;
+    c.E = E;
+    c.lane = lane;
+    c.sm = &smem[wib];
+    c.err = 0;
+    c.ct.walk = c.ct.occ = c.ct.scan = c.ct.score = 0;
+    {
+        unsigned char *p = arena_base + warp_global * arena_stride;
+        c.ar.inst = (Inst *)p, p += sizeof(Inst) * kInstMax;
+        c.ar.best = (int4 *)p, p += sizeof(int4) * kInstMax;
+        c.ar.hash = (int2 *)p, p += sizeof(int2) * kHashMax;
+        c.ar.redge = (int4 *)p, p += sizeof(int4) * kPathMax;
+        c.ar.vote = (int2 *)p, p += sizeof(int2) * kVoteMax;
+        c.ar.rs = (int2 *)p, p += sizeof(int2) * kReadSetMax;
+        c.ar.hslot = (int *)p, p += sizeof(int) * kPathMax;
+        c.ar.ord = (unsigned short *)p, p += sizeof(unsigned short) * kInstMax;
+        c.ar.good = (unsigned short *)p, p += sizeof(unsigned short) * kInstMax;
+    }
+    const unsigned n = *n_ptr;
+    unsigned done = 0;
+    while (true) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(&ctl->head, 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if (idx >= n) break;
+        const unsigned j = list[idx];
+        const unsigned i = w0 + j;
+        c.thresh = slot == 0 ? (i / phase) * phase : i;
+        process_seed(c, seed_vid[i], seed_ch[i]);
+        if (c.err) {
+            if (lane == 0) atomicCAS(&ctl->err, 0u, (unsigned)c.err);
+            break;
+        }
+        // publish bestInstance and the read-set
+        unsigned long long io = 0, ro = 0;
+        if (lane == 0) {
+            io = atomicAdd(&ctl->inst_used, (unsigned long long)c.nbest);
+            ro = atomicAdd(&ctl->rs_used, (unsigned long long)c.nrs);
+        }
+        io = __shfl_sync(kFull, io, 0);
+        ro = __shfl_sync(kFull, ro, 0);
+        if (io + c.nbest > win.inst_cap || ro + c.nrs > win.rs_cap) {
+            if (lane == 0) atomicExch(&ctl->pool_overflow, 1u);
+            break;
+        }
+        for (int t = lane; t < c.nbest; t += 32) win.inst_pool[io + t] = c.best[t];
+        for (int t = lane; t < c.nrs; t += 32) win.rs_pool[ro + t] = c.ar.rs[t];
+        if (lane == 0) {
+            win.res_off[slot][j] = (unsigned)io;
+            win.res_cnt[slot][j] = (unsigned)c.nbest;
+            win.rs_off[slot][j] = (unsigned)ro;
+            win.rs_cnt[slot][j] = (unsigned)c.nrs;
+        }
+        done++;
+    }
+    if (lane == 0) {
+        if (done) atomicAdd(slot == 0 ? &ctl->runs0 : &ctl->runs1, (unsigned long long)done);
+        if (collect) {
+            atomicAdd(&ctl->ct_walk, c.ct.walk);
+            atomicAdd(&ctl->ct_occ, c.ct.occ);
+            atomicAdd(&ctl->ct_scan, c.ct.scan);
+            atomicAdd(&ctl->ct_score, c.ct.score);
+        }
+    }
+}
+
+// edges of one instance as an epoch index range: Finalize's MarkUsed loop (blocksfinder.h:327-330)
+__device__ __forceinline__ void inst_edges(const int4 &b, int &lo, int &hi)
+{
+    int fg = b.x & 0x7FFFFFFF, bg = b.y;
+    lo = min(fg, bg);
+    hi = max(fg, bg) - 1;
+}
+
+// does any edge of result `slot 0` of seed j carry an epoch < limit?   (warp-wide)
+__device__ __forceinline__ bool result_conflicts(const Window &win, unsigned j, const uint32_t *E, uint32_t limit,
+                                                 int lane)
+{
+    const unsigned cnt = win.res_cnt[0][j], off = win.res_off[0][j];
+    bool hit = false;
+    for (unsigned t = 0; t < cnt && !hit; t++) {
+        int lo, hi;
+        inst_edges(win.inst_pool[off + t], lo, hi);
+        for (int base = lo; base <= hi && !hit; base += 32) {
+            int f = base + lane;
+            hit = __any_sync(kFull, f <= hi && E[f] < limit);
+        }
+    }
+    return hit;
+}
+
+// commit-time conflict test for freshly evaluated seeds (blocksfinder.h:375-398); queues re-runs
+__global__ void k_conflict(const uint32_t *__restrict__ E, unsigned w0, const unsigned *__restrict__ list,
+                           const unsigned *__restrict__ n_ptr, Window win, Control *ctl)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned n = *n_ptr;
+    for (unsigned idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += gridDim.x * (blockDim.x >> 5)) {
+        const unsigned j = list[idx];
+        bool conf = false;
+        if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, E, w0 + j, lane);
+        if (lane == 0) {
+            win.conf[j] = conf;
+            if (conf && !win.has1[j]) {
+                win.has1[j] = 1;
+                win.list1[atomicAdd(&ctl->n1, 1u)] = j;
+            }
+            if (!conf) win.has1[j] = 0;
+        }
+    }
+}
+
+__device__ __forceinline__ void final_result(const Window &win, unsigned j, unsigned &off, unsigned &cnt)
+{
+    const int s = win.conf[j] ? 1 : 0;
+    cnt = win.res_cnt[s][j];
+    off = win.res_off[s][j];
+    if (cnt <= 1) cnt = 0; // `if (instance.size() > 1)` blocksfinder.h:375,408
+}
+
+// epoch'[e] = min(seed index) over the window's final results
+__global__ void k_claim(uint32_t *__restrict__ Enew, unsigned w0, unsigned n, Window win)
+{
+    const int lane = threadIdx.x & 31;
+    for (unsigned j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += gridDim.x * (blockDim.x >> 5)) {
+        unsigned off, cnt;
+        final_result(win, j, off, cnt);
+        for (unsigned t = 0; t < cnt; t++) {
+            int lo, hi;
+            inst_edges(win.inst_pool[off + t], lo, hi);
+            for (int f = lo + lane; f <= hi; f += 32) atomicMin(&Enew[f], w0 + j);
+        }
+    }
+}
+
+// did any epoch in the read-set change its meaning (< limit) between Ecur and Enew?
+__device__ __forceinline__ bool readset_changed(const int2 *rs, unsigned cnt, const uint32_t *Ecur,
+                                                const uint32_t *Enew, uint32_t limit, int lane)
+{
+    bool changed = false;
+    for (unsigned base = 0; base < cnt && !changed; base += 32) {
+        bool ch = false;
+        if (base + lane < cnt) {
+            int2 iv = rs[base + lane];
+            for (int f = iv.x; f <= iv.y && !ch; f++) ch = (Ecur[f] < limit) != (Enew[f] < limit);
+        }
+        changed = __any_sync(kFull, ch);
+    }
+    return changed;
+}
+
+// re-validate every seed of the window against the new epochs; build next round's work lists
+__global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned w0,
+                           unsigned n, unsigned phase, Window win, Control *ctl)
+{
+    const int lane = threadIdx.x & 31;
+    for (unsigned j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += gridDim.x * (blockDim.x >> 5)) {
+        const unsigned i = w0 + j;
+        const uint32_t T = (i / phase) * phase;
+        unsigned dirty = 0;
+        if (readset_changed(win.rs_pool + win.rs_off[0][j], win.rs_cnt[0][j], Ecur, Enew, T, lane)) {
+            if (lane == 0) {
+                win.list0[atomicAdd(&ctl->n0, 1u)] = j;
+                win.has1[j] = 0;
+            }
+            dirty = 1;
+        } else {
+            bool conf = false;
+            if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, Enew, i, lane);
+            const bool was = win.conf[j] != 0;
+            if (conf != was) dirty = 1;
+            bool rerun = false;
+            if (conf) {
+                if (!win.has1[j]) rerun = true;
+                else rerun = readset_changed(win.rs_pool + win.rs_off[1][j], win.rs_cnt[1][j], Ecur, Enew, i, lane);
+            }
+            if (lane == 0) {
+                win.conf[j] = conf;
+                if (rerun) {
+                    win.has1[j] = 1;
+                    win.list1[atomicAdd(&ctl->n1, 1u)] = j;
+                }
+                if (!conf) win.has1[j] = 0;
+            }
+            if (rerun) dirty = 1;
+        }
+        if (lane == 0 && dirty) atomicAdd(&ctl->dirty, 1u);
+    }
+}
+
+__global__ void k_iota(unsigned *list, unsigned n)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) list[i] = i;
+}
+
+// Finalize (blocksfinder.h:312-332) for a converged window: block ids and output offsets are prefix
+// sums in seed order (one block, W <= 65536)
+__global__ void __launch_bounds__(1024) k_emit_scan(unsigned n, Window win, Control *ctl, unsigned blocks_before,
+                                                     unsigned out_before)
+{
+    __shared__ unsigned sb[1024], so[1024];
+    const unsigned per = (n + 1023) / 1024;
+    const unsigned lo = threadIdx.x * per, hi = min(n, lo + per);
+    unsigned nb = 0, no = 0;
+    for (unsigned j = lo; j < hi; j++) {
+        unsigned off, cnt;
+        final_result(win, j, off, cnt);
+        nb += cnt ? 1 : 0;
+        no += cnt;
+    }
+    sb[threadIdx.x] = nb, so[threadIdx.x] = no;
+    __syncthreads();
+    for (unsigned d = 1; d < 1024; d <<= 1) {
+        unsigned vb = threadIdx.x >= d ? sb[threadIdx.x - d] : 0, vo = threadIdx.x >= d ? so[threadIdx.x - d] : 0;
+        __syncthreads();
+        sb[threadIdx.x] += vb, so[threadIdx.x] += vo;
+        __syncthreads();
+    }
+    unsigned b = blocks_before + sb[threadIdx.x] - nb, o = out_before + so[threadIdx.x] - no;
+    for (unsigned j = lo; j < hi; j++) {
+        unsigned off, cnt;
+        final_result(win, j, off, cnt);
+        win.out_off[j] = o;
+        win.blk[j] = cnt ? ++b : 0;
+        o += cnt;
+    }
+    if (threadIdx.x == 1023) {
+        ctl->n_blocks = sb[1023];
+        ctl->n_out = so[1023];
+    }
+}
+
+__global__ void k_emit_write(Index ix, int k, unsigned n, Window win, lcb_block_instance *out)
+{
+    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    unsigned off, cnt;
+    final_result(win, j, off, cnt);
+    for (unsigned t = 0; t < cnt; t++) {
+        int4 b = win.inst_pool[off + t];
+        const bool pos = b.x < 0;
+        const int fg = b.x & 0x7FFFFFFF;
+        int a = 0, e = ix.C;
+        while (e - a > 1) {
+            int mid = (a + e) >> 1;
+            if ((int)ix.chr_off[mid] <= fg) a = mid;
+            else e = mid;
+        }
+        lcb_block_instance r;
+        r.chr = (uint32_t)a;
+        if (pos) { // blocksfinder.h:320
+            r.id = (int32_t)win.blk[j];
+            r.start = (uint32_t)b.z;
+            r.end = (uint32_t)b.w + (uint32_t)k;
+        } else { // blocksfinder.h:324
+            r.id = -(int32_t)win.blk[j];
+            r.start = (uint32_t)b.w;
+            r.end = (uint32_t)b.z + (uint32_t)k;
+        }
+        out[win.out_off[j] + t] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// seed enumeration (blocksfinder.h:461-503): one thread per signed vertex
+// ------------------------------------------------------------------------------------------------
+struct SeedArrays {
+    int *vid;
+    unsigned char *ch;
+    unsigned *count;
+    unsigned long long *rank;
+    unsigned *res_pos, *res_chr;
+};
+
+template <bool FILL>
+__global__ void k_seed_enum(Index ix, unsigned *__restrict__ per_vertex, const unsigned *__restrict__ offset, SeedArrays out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = 2LL * ix.V;
+    if (t >= total) return;
+    // t -> v in (-V, V): t = v + V
+    const int v = (int)(t - ix.V);
+    const int av = v < 0 ? -v : v;
+    if (av == 0 || t == 0) { // v = -V does not exist (reference loops v in [-V+1, V-1]); vertex 0 is unused
+        if (!FILL) per_vertex[t] = 0;
+        return;
+    }
+    const unsigned o0 = ix.vtx_off[av], o1 = ix.vtx_off[av + 1];
+    unsigned emitted = 0;
+    unsigned w = FILL ? offset[t] : 0;
+    for (unsigned a = o0; a < o1; a++) {
+        const int ga = (int)ix.occ[a];
+        const bool pa = ix.rec[ga].x == v;
+        const unsigned char ca = pa ? ix.chs[ga].x : ix.chs[ga].y;
+        bool first = true;
+        for (unsigned b = o0; b < a && first; b++) {
+            const int gb = (int)ix.occ[b];
+            const unsigned char cb = ix.rec[gb].x == v ? ix.chs[gb].x : ix.chs[gb].y;
+            first = cb != ca;
+        }
+        if (!first) continue;
+        unsigned count = 0;
+        bool good = false;
+        unsigned long long rank = 0, base = 1;
+        unsigned long long best = ~0ULL; // (pos, chr) packed for the lexicographic min
+        for (unsigned b = a; b < o1; b++) {
+            const int gb = (int)ix.occ[b];
+            const int2 rb = ix.rec[gb];
+            const bool pb = rb.x == v;
+            const unsigned char cb = pb ? ix.chs[gb].x : ix.chs[gb].y;
+            if (cb != ca) continue;
+            count++;
+            int lo = 0, hi = ix.C;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if ((int)ix.chr_off[mid] <= gb) lo = mid;
+                else hi = mid;
+            }
+            rank += (unsigned long long)lo * base;
+            base *= 31ULL;
+            if (pb) {
+                good = true;
+                unsigned long long key = ((unsigned long long)(unsigned)rb.y << 32) | (unsigned)lo;
+                best = key < best ? key : best;
+            }
+        }
+        if (count > 1 && good) {
+            if (FILL) {
+                out.vid[w] = v;
+                out.ch[w] = ca;
+                out.count[w] = count;
+                out.rank[w] = rank;
+                out.res_pos[w] = (unsigned)(best >> 32);
+                out.res_chr[w] = (unsigned)best;
+                w++;
+            }
+            emitted++;
+        }
+    }
+    if (!FILL) per_vertex[t] = emitted;
+}
+
+// ---- exclusive scan (u32), three small kernels -------------------------------------------------------
+constexpr int kScanTile = 2048;
+__global__ void __launch_bounds__(256) k_scan_tiles(const unsigned *in, unsigned *out, unsigned *tile_sum, size_t n)
+{
+    __shared__ unsigned s[256];
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * 8;
+    unsigned v[8], sum = 0;
+    for (int q = 0; q < 8; q++) {
+        v[q] = base + q < n ? in[base + q] : 0;
+        sum += v[q];
+    }
+    s[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        unsigned x = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+        __syncthreads();
+        s[threadIdx.x] += x;
+        __syncthreads();
+    }
+    unsigned run = s[threadIdx.x] - sum;
+    for (int q = 0; q < 8; q++) {
+        if (base + q < n) out[base + q] = run;
+        run += v[q];
+    }
+    if (threadIdx.x == 255) tile_sum[blockIdx.x] = s[255];
+}
+__global__ void k_scan_sums(unsigned *tile_sum, unsigned tiles, unsigned *total)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned run = 0;
+        for (unsigned i = 0; i < tiles; i++) {
+            unsigned x = tile_sum[i];
+            tile_sum[i] = run;
+            run += x;
+        }
+        *total = run;
+    }
+}
+__global__ void k_scan_add(unsigned *out, const unsigned *tile_sum, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += tile_sum[i / kScanTile];
+}
+
+// ---- stable LSD radix sort of a permutation by 8-bit digits of a key word ---------------------------------
+constexpr int kSortTile = 2048; // elements per block
+template <typename K>
+__global__ void __launch_bounds__(256) k_radix_hist(const unsigned *perm, const K *key, int shift, unsigned n, unsigned *hist, int flip)
+{
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned base = blockIdx.x * kSortTile;
+    for (int q = 0; q < kSortTile / 256; q++) {
+        unsigned i = base + q * 256 + threadIdx.x;
+        if (i < n) {
+            unsigned d = (unsigned)(key[perm[i]] >> shift) & 255u;
+            if (flip) d = 255u - d;
+            atomicAdd(&h[d], 1u);
+        }
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x]; // digit-major
+}
+template <typename K>
+__global__ void __launch_bounds__(256) k_radix_scatter(const unsigned *perm_in, unsigned *perm_out, const K *key, int shift,
+                                                         unsigned n, const unsigned *offs, int flip)
+{
+    __shared__ unsigned run[256];
+    __shared__ unsigned wc[8][256];
+    run[threadIdx.x] = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    for (int w = 0; w < 8; w++) wc[w][threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned base = blockIdx.x * kSortTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < kSortTile / 256; q++) {
+        unsigned i = base + q * 256 + threadIdx.x;
+        bool live = i < n;
+        unsigned p = live ? perm_in[i] : 0;
+        unsigned d = live ? ((unsigned)(key[p] >> shift) & 255u) : 256u + (unsigned)lane; // dead lanes match nobody
+        if (live && flip) d = 255u - d;
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        unsigned before = __popc(peers & ((1u << lane) - 1));
+        if (live && before == 0) wc[warp][d] = __popc(peers);
+        __syncthreads();
+        if (live) {
+            unsigned pre = 0;
+            for (int w = 0; w < warp; w++) pre += wc[w][d];
+            perm_out[run[d] + pre + before] = p;
+        }
+        __syncthreads();
+        {
+            unsigned tot = 0;
+            for (int w = 0; w < 8; w++) {
+                tot += wc[w][threadIdx.x];
+                wc[w][threadIdx.x] = 0;
+            }
+            run[threadIdx.x] += tot;
+        }
+        __syncthreads();
+    }
+}
+template <typename T>
+__global__ void k_gather(const unsigned *perm, const T *in, T *out, unsigned n)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+__global__ void k_is_uniform_digit(const unsigned *hist, unsigned blocks, unsigned n, unsigned *flag)
+{
+    // one thread per digit: if a single digit holds all n keys the pass is the identity
+    unsigned d = threadIdx.x, tot = 0;
+    for (unsigned b = 0; b < blocks; b++) tot += hist[(size_t)d * blocks + b];
+    if (tot == n) *flag = 1;
+}
+
+} // namespace
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct lcb_ctx {
+    std::string error;
+    lcb_params prm;
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr;
+    // index
+    Index ix{};
+    int2 *d_rec = nullptr;
+    uchar2 *d_chs = nullptr;
+    uint32_t *d_vtx_off = nullptr, *d_occ = nullptr, *d_chr_off = nullptr;
+    uint32_t *d_E[3] = {nullptr, nullptr, nullptr};
+    // seeds
+    uint64_t n_seeds = 0;
+    bool seeds_ready = false;
+    int *d_seed_vid = nullptr;
+    unsigned char *d_seed_ch = nullptr;
+    unsigned *d_seed_count = nullptr, *d_seed_res_pos = nullptr, *d_seed_res_chr = nullptr;
+    unsigned long long *d_seed_rank = nullptr;
+    // window
+    Window win{};
+    unsigned wmax = 0;
+    Control *d_ctl = nullptr, *h_ctl = nullptr;
+    unsigned char *d_arena = nullptr;
+    size_t arena_stride = 0;
+    int grid_traverse = 0;
+    lcb_block_instance *d_out = nullptr;
+    lcb_stats st{};
+    int rank = 0, n_ranks = 1;
+    std::vector<void *> allocs;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(lcb_ctx *ctx, T **p, size_t n)
+{
+    void *q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    ctx->allocs.push_back(q);
+    *p = (T *)q;
+    return LCB_OK;
+}
+
+int exclusive_scan(lcb_ctx *ctx, const unsigned *in, unsigned *out, size_t n, unsigned *d_total, unsigned *d_tile_sum)
+{
+    unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
+    k_scan_tiles<<<tiles, 256, 0, ctx->stream>>>(in, out, d_tile_sum, n);
+    k_scan_sums<<<1, 32, 0, ctx->stream>>>(d_tile_sum, tiles, d_total);
+    k_scan_add<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, d_tile_sum, n);
+    ctx->st.kernel_launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return LCB_OK;
+}
+
+// stable sort pass(es) of `perm` by one key word; skips digits on which all keys agree
+template <typename K>
+int radix_sort_word(lcb_ctx *ctx, unsigned **perm, unsigned **tmp, const K *key, int bits, bool descending, unsigned n,
+                    unsigned *d_hist, unsigned *d_flag)
+{
+    unsigned blocks = (n + kSortTile - 1) / kSortTile;
+    for (int shift = 0; shift < bits; shift += 8) {
+        CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(unsigned), ctx->stream));
+        k_radix_hist<K><<<blocks, 256, 0, ctx->stream>>>(*perm, key, shift, n, d_hist, descending ? 1 : 0);
+        k_is_uniform_digit<<<1, 256, 0, ctx->stream>>>(d_hist, blocks, n, d_flag);
+        unsigned flag = 0;
+        CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->st.kernel_launches += 2;
+        if (flag) continue;
+        // digit-major exclusive scan of hist gives every (digit, block) its output base
+        size_t hn = (size_t)256 * blocks;
+        unsigned *d_total = d_flag + 1;
+        int rc = exclusive_scan(ctx, d_hist, d_hist, hn, d_total, d_hist + hn);
+        if (rc) return rc;
+        k_radix_scatter<K><<<blocks, 256, 0, ctx->stream>>>(*perm, *tmp, key, shift, n, d_hist, descending ? 1 : 0);
+        ctx->st.kernel_launches += 1;
+        std::swap(*perm, *tmp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LCB_OK;
+}
+
+} // namespace
+
+extern "C" void lcb_default_params(lcb_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->k = 25;
+    p->max_branch = 200;
+    p->min_block = 200;
+    p->max_flank = 200;
+    p->looking_depth = 8;
+    p->phase_size = 256;
+    p->window_init = 4096;
+    p->window_max = 32768;
+    p->device = 0;
+    p->collect_counters = 0;
+}
+
+extern "C" const char *lcb_last_error(lcb_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+extern "C" void lcb_destroy(lcb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb_ctx **out)
+{
+    if (!v || !params || !out) return LCB_ERR_ARG;
+    lcb_ctx *ctx = new lcb_ctx;
+    *out = ctx; // returned even on failure so that lcb_last_error works; caller destroys it
+    ctx->prm = *params;
+    lcb_params &p = ctx->prm;
+    if (p.phase_size <= 0) p.phase_size = 256;
+    if (p.looking_depth <= 0) p.looking_depth = 8;
+    if (p.window_init <= 0) p.window_init = 4096;
+    if (p.window_max <= 0) p.window_max = 32768;
+    p.window_max = std::min(p.window_max, 65536);
+    p.window_max = std::max(p.phase_size, p.window_max / p.phase_size * p.phase_size);
+    p.window_init = std::max(p.phase_size, std::min(p.window_init, p.window_max) / p.phase_size * p.phase_size);
+    if (v->n_records < 0 || v->n_records >= (int64_t)0x7FFFFFF0 || v->n_vertices >= (int64_t)0x3FFFFFF0 || v->n_chr < 0) {
+        ctx->error = "index too large for 32-bit device indices";
+        return LCB_ERR_ARG;
+    }
+    if (p.k <= 0 || p.max_branch < 0 || p.min_block < 0) {
+        ctx->error = "bad parameters";
+        return LCB_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        ctx->error = "no CUDA device: this library has no CPU fallback";
+        return LCB_ERR_CUDA;
+    }
+    ctx->device = p.device;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major < 10) {
+        ctx->error = std::string("device ") + prop.name + " is not sm_100-class";
+        return LCB_ERR_CUDA;
+    }
+    ctx->sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    const int64_t N = v->n_records, V = v->n_vertices;
+    const int C = v->n_chr;
+    auto t0 = std::chrono::steady_clock::now();
+    // ---- pack + upload the index (8 B + 2 B per record, u32 CSR) ----
+    {
+        std::vector<int2> rec((size_t)N);
+        std::vector<uchar2> chs((size_t)N);
+        for (int64_t g = 0; g < N; g++) {
+            rec[(size_t)g] = make_int2(v->pos_id[g], (int)v->pos_bp[g]);
+            chs[(size_t)g] = make_uchar2(v->next_ch[g], v->prev_rc[g]);
+        }
+        std::vector<uint32_t> vo((size_t)V + 2, 0), oc((size_t)N), co((size_t)C + 1);
+        for (int64_t i = 0; i <= V; i++) vo[(size_t)i] = (uint32_t)v->vtx_off[i];
+        vo[(size_t)V + 1] = vo[(size_t)V];
+        for (int64_t i = 0; i < N; i++) oc[(size_t)i] = (uint32_t)v->occ_g[i];
+        for (int i = 0; i <= C; i++) co[(size_t)i] = (uint32_t)v->chr_off[i];
+        int rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_rec, (size_t)N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_chs, (size_t)N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_occ, (size_t)N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
+        for (int e = 0; e < 3; e++)
+            if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, rec.data(), sizeof(int2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_chs, chs.data(), sizeof(uchar2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_vtx_off, vo.data(), sizeof(uint32_t) * ((size_t)V + 2), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, oc.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_chr_off, co.data(), sizeof(uint32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->st.h2d_bytes = (uint64_t)N * (8 + 2 + 4) + (uint64_t)(V + 2) * 4 + (uint64_t)(C + 1) * 4;
+    }
+    ctx->st.ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->ix.rec = ctx->d_rec;
+    ctx->ix.chs = ctx->d_chs;
+    ctx->ix.vtx_off = ctx->d_vtx_off;
+    ctx->ix.occ = ctx->d_occ;
+    ctx->ix.chr_off = ctx->d_chr_off;
+    ctx->ix.C = C;
+    ctx->ix.N = (int)N;
+    ctx->ix.V = (int)V;
+    ctx->st.n_records = (uint64_t)N;
+    ctx->st.n_vertices = (uint64_t)V;
+    // ---- window state, pools, arena ----
+    int rc;
+    const unsigned W = (unsigned)p.window_max;
+    ctx->wmax = W;
+    for (int s = 0; s < 2; s++) {
+        if ((rc = dev_alloc(ctx, &ctx->win.res_off[s], W))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->win.res_cnt[s], W))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->win.rs_off[s], W))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->win.rs_cnt[s], W))) return rc;
+    }
+    if ((rc = dev_alloc(ctx, &ctx->win.conf, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.has1, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.blk, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.out_off, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.list0, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.list1, W))) return rc;
+    ctx->win.inst_cap = 16ull << 20;
+    ctx->win.rs_cap = 128ull << 20;
+    if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.rs_pool, (size_t)ctx->win.rs_cap))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ctl, 1))) return rc;
+    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctl, sizeof(Control)));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    ctx->grid_traverse = per_sm * ctx->sms;
+    ctx->arena_stride = sizeof(Inst) * kInstMax + sizeof(int4) * kInstMax + sizeof(int2) * kHashMax + sizeof(int4) * kPathMax +
+                        sizeof(int2) * kVoteMax + sizeof(int2) * kReadSetMax + sizeof(int) * kPathMax +
+                        2 * sizeof(unsigned short) * kInstMax;
+    ctx->arena_stride = (ctx->arena_stride + 255) & ~(size_t)255;
+    size_t arena_bytes = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock;
+    if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes))) return rc;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_arena, 0, arena_bytes, ctx->stream)); // the spill hash must start all-empty
+    if ((rc = dev_alloc(ctx, &ctx->d_out, (size_t)N + 1))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LCB_OK;
+}
+
+extern "C" int lcb_comm_unique_id(void *id_bytes)
+{
+#ifdef LCB_WITH_NCCL
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return LCB_ERR_CUDA;
+    static_assert(sizeof(id) <= LCB_COMM_ID_BYTES, "id size");
+    memset(id_bytes, 0, LCB_COMM_ID_BYTES);
+    memcpy(id_bytes, &id, sizeof id);
+    return LCB_OK;
+#else
+    (void)id_bytes;
+    return LCB_ERR_STATE;
+#endif
+}
+
+extern "C" int lcb_comm_init(lcb_ctx *ctx, int rank, int n_ranks, const void *id_bytes)
+{
+    if (!ctx) return LCB_ERR_ARG;
+    (void)id_bytes;
+    if (n_ranks == 1) {
+        ctx->rank = 0, ctx->n_ranks = 1;
+        return LCB_OK;
+    }
+    ctx->error = "multi-GPU support is not compiled in";
+    (void)rank;
+    return LCB_ERR_STATE;
+}
+
+extern "C" int lcb_enumerate_seeds(lcb_ctx *ctx, uint64_t *n_seeds)
+{
+    if (!ctx) return LCB_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->seeds_ready) {
+        if (n_seeds) *n_seeds = ctx->n_seeds;
+        return LCB_OK;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    const size_t slots = 2 * (size_t)ctx->ix.V;
+    unsigned *d_cnt = nullptr, *d_off = nullptr, *d_tile = nullptr, *d_total = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_cnt, slots + 1))) return rc;
+    if ((rc = dev_alloc(ctx, &d_off, slots + 1))) return rc;
+    if ((rc = dev_alloc(ctx, &d_tile, slots / kScanTile + 2))) return rc;
+    if ((rc = dev_alloc(ctx, &d_total, 4))) return rc;
+    const unsigned blocks = (unsigned)((slots + 255) / 256);
+    SeedArrays none{};
+    if (slots) k_seed_enum<false><<<blocks, 256, 0, ctx->stream>>>(ctx->ix, d_cnt, nullptr, none);
+    ctx->st.kernel_launches += 1;
+    unsigned total = 0;
+    if (slots) {
+        if ((rc = exclusive_scan(ctx, d_cnt, d_off, slots, d_total, d_tile))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const unsigned S = total;
+    ctx->n_seeds = S;
+    SeedArrays raw{}, srt{};
+    if ((rc = dev_alloc(ctx, &raw.vid, S))) return rc;
+    if ((rc = dev_alloc(ctx, &raw.ch, S))) return rc;
+    if ((rc = dev_alloc(ctx, &raw.count, S))) return rc;
+    if ((rc = dev_alloc(ctx, &raw.rank, S))) return rc;
+    if ((rc = dev_alloc(ctx, &raw.res_pos, S))) return rc;
+    if ((rc = dev_alloc(ctx, &raw.res_chr, S))) return rc;
+    if ((rc = dev_alloc(ctx, &srt.vid, S))) return rc;
+    if ((rc = dev_alloc(ctx, &srt.ch, S))) return rc;
+    if ((rc = dev_alloc(ctx, &srt.count, S))) return rc;
+    if ((rc = dev_alloc(ctx, &srt.rank, S))) return rc;
+    if ((rc = dev_alloc(ctx, &srt.res_pos, S))) return rc;
+    if ((rc = dev_alloc(ctx, &srt.res_chr, S))) return rc;
+    if (S) {
+        k_seed_enum<true><<<blocks, 256, 0, ctx->stream>>>(ctx->ix, nullptr, d_off, raw);
+        ctx->st.kernel_launches += 1;
+        // Bundle::operator< (blocksfinder.h:195-208): count desc, rank asc, resolve=(pos, chr) asc -- a total order,
+        // so a stable LSD radix sort from the least significant key reproduces std::sort's result exactly
+        unsigned *perm = nullptr, *tmp = nullptr, *d_hist = nullptr, *d_flag = nullptr;
+        const unsigned sblocks = (S + kSortTile - 1) / kSortTile;
+        if ((rc = dev_alloc(ctx, &perm, S))) return rc;
+        if ((rc = dev_alloc(ctx, &tmp, S))) return rc;
+        if ((rc = dev_alloc(ctx, &d_hist, (size_t)256 * sblocks + (256 * sblocks) / kScanTile + 8))) return rc;
+        if ((rc = dev_alloc(ctx, &d_flag, 4))) return rc;
+        k_iota<<<(S + 255) / 256, 256, 0, ctx->stream>>>(perm, S);
+        if ((rc = radix_sort_word<unsigned>(ctx, &perm, &tmp, raw.res_chr, 32, false, S, d_hist, d_flag))) return rc;
+        if ((rc = radix_sort_word<unsigned>(ctx, &perm, &tmp, raw.res_pos, 32, false, S, d_hist, d_flag))) return rc;
+        if ((rc = radix_sort_word<unsigned long long>(ctx, &perm, &tmp, raw.rank, 64, false, S, d_hist, d_flag))) return rc;
+        if ((rc = radix_sort_word<unsigned>(ctx, &perm, &tmp, raw.count, 32, true, S, d_hist, d_flag))) return rc;
+        const unsigned gb = (S + 255) / 256;
+        k_gather<<<gb, 256, 0, ctx->stream>>>(perm, raw.vid, srt.vid, S);
+        k_gather<<<gb, 256, 0, ctx->stream>>>(perm, raw.ch, srt.ch, S);
+        k_gather<<<gb, 256, 0, ctx->stream>>>(perm, raw.count, srt.count, S);
+        k_gather<<<gb, 256, 0, ctx->stream>>>(perm, raw.rank, srt.rank, S);
+        k_gather<<<gb, 256, 0, ctx->stream>>>(perm, raw.res_pos, srt.res_pos, S);
+        k_gather<<<gb, 256, 0, ctx->stream>>>(perm, raw.res_chr, srt.res_chr, S);
+        ctx->st.kernel_launches += 7;
+    }
+    ctx->d_seed_vid = srt.vid;
+    ctx->d_seed_ch = srt.ch;
+    ctx->d_seed_count = srt.count;
+    ctx->d_seed_rank = srt.rank;
+    ctx->d_seed_res_pos = srt.res_pos;
+    ctx->d_seed_res_chr = srt.res_chr;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->st.ms_enumerate = ms;
+    ctx->st.n_seeds = S;
+    ctx->seeds_ready = true;
+    if (n_seeds) *n_seeds = S;
+    return LCB_OK;
+}
+
+extern "C" int lcb_get_seeds(lcb_ctx *ctx, int64_t *vid, uint8_t *ch, uint64_t *count, uint64_t *rank, uint64_t *res_pos,
+                             uint64_t *res_chr)
+{
+    if (!ctx || !ctx->seeds_ready) return LCB_ERR_STATE;
+    const size_t S = ctx->n_seeds;
+    std::vector<int> hv(S);
+    std::vector<unsigned> hu(S);
+    std::vector<unsigned long long> hr(S);
+    if (vid) {
+        CUDA_TRY(cudaMemcpy(hv.data(), ctx->d_seed_vid, S * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < S; i++) vid[i] = hv[i];
+    }
+    if (ch) CUDA_TRY(cudaMemcpy(ch, ctx->d_seed_ch, S, cudaMemcpyDeviceToHost));
+    if (count) {
+        CUDA_TRY(cudaMemcpy(hu.data(), ctx->d_seed_count, S * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < S; i++) count[i] = hu[i];
+    }
+    if (rank) {
+        CUDA_TRY(cudaMemcpy(hr.data(), ctx->d_seed_rank, S * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < S; i++) rank[i] = hr[i];
+    }
+    if (res_pos) {
+        CUDA_TRY(cudaMemcpy(hu.data(), ctx->d_seed_res_pos, S * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < S; i++) res_pos[i] = hu[i];
+    }
+    if (res_chr) {
+        CUDA_TRY(cudaMemcpy(hu.data(), ctx->d_seed_res_chr, S * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < S; i++) res_chr[i] = hu[i];
+    }
+    return LCB_OK;
+}
+
+namespace {
+
+int launch_traverse(lcb_ctx *ctx, const uint32_t *E, unsigned w0, int slot, const unsigned *list, const unsigned *n_ptr)
+{
+    Params pr{ctx->prm.k, ctx->prm.max_branch, ctx->prm.min_block, ctx->prm.max_flank, ctx->prm.looking_depth};
+    CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, sizeof(unsigned), ctx->stream));
+    k_traverse<<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, w0,
+                                                                 (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
+                                                                 ctx->d_ctl, ctx->d_arena, ctx->arena_stride,
+                                                                 ctx->prm.collect_counters);
+    ctx->st.kernel_launches++;
+    ctx->st.traverse_launches++;
+    return LCB_OK;
+}
+
+int fetch_control(lcb_ctx *ctx)
+{
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    return LCB_OK;
+}
+
+} // namespace
+
+extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t *n_out, lcb_stats *stats)
+{
+    if (!ctx || !out || !n_out) return LCB_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc;
+    if (!ctx->seeds_ready && (rc = lcb_enumerate_seeds(ctx, nullptr))) return rc;
+    auto t_begin = std::chrono::steady_clock::now();
+    const unsigned S = (unsigned)ctx->n_seeds;
+    const unsigned phase = (unsigned)ctx->prm.phase_size;
+    const size_t N = (size_t)ctx->ix.N;
+    uint32_t *Ebase = ctx->d_E[0], *Ea = ctx->d_E[1], *Eb = ctx->d_E[2];
+    CUDA_TRY(cudaMemsetAsync(Ebase, 0xFF, (N + 32) * sizeof(uint32_t), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
+    memset(ctx->h_ctl, 0, sizeof(Control));
+    unsigned blocks_done = 0, out_done = 0;
+    unsigned W = (unsigned)ctx->prm.window_init;
+    const unsigned vgrid = (unsigned)ctx->sms * 8;
+    float trav_ms = 0;
+    ctx->st.windows = ctx->st.rounds = 0;
+    for (unsigned w0 = 0; w0 < S;) {
+        const unsigned n = std::min(W, S - w0);
+        // fresh window: every seed needs its speculative evaluation
+        CUDA_TRY(cudaMemsetAsync(ctx->win.conf, 0, n, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->win.has1, 0, n, ctx->stream));
+        k_iota<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->win.list0, n);
+        ctx->st.kernel_launches++;
+        {
+            Control z{};
+            z.n0 = n;
+            z.ct_walk = ctx->h_ctl->ct_walk, z.ct_occ = ctx->h_ctl->ct_occ, z.ct_scan = ctx->h_ctl->ct_scan,
+            z.ct_score = ctx->h_ctl->ct_score, z.runs0 = ctx->h_ctl->runs0, z.runs1 = ctx->h_ctl->runs1;
+            *ctx->h_ctl = z;
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Control), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        uint32_t *Ecur = Ebase, *Enew = Ea, *Efree = Eb;
+        bool retry = false;
+        unsigned first_dirty = 0;
+        for (unsigned round = 1;; round++) {
+            ctx->st.rounds++;
+            // A. speculative evaluations
+            CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+            if ((rc = launch_traverse(ctx, Ecur, w0, 0, ctx->win.list0, &ctx->d_ctl->n0))) return rc;
+            CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+            // B. commit-time conflicts of the freshly evaluated seeds
+            k_conflict<<<vgrid, 256, 0, ctx->stream>>>(Ecur, w0, ctx->win.list0, &ctx->d_ctl->n0, ctx->win, ctx->d_ctl);
+            // C. commit-time re-runs
+            if ((rc = launch_traverse(ctx, Ecur, w0, 1, ctx->win.list1, &ctx->d_ctl->n1))) return rc;
+            // D. new epochs
+            CUDA_TRY(cudaMemcpyAsync(Enew, Ebase, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, w0, n, ctx->win);
+            // E. validation + next work lists
+            CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream)); // n0, n1, dirty
+            k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, w0, n, phase, ctx->win, ctx->d_ctl);
+            ctx->st.kernel_launches += 3;
+            if ((rc = fetch_control(ctx))) return rc;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            trav_ms += ms;
+            if (ctx->h_ctl->err) {
+                ctx->error = "a per-seed device buffer overflowed its hard cap (path, instance or read-set too large)";
+                return (int)ctx->h_ctl->err;
+            }
+            if (ctx->h_ctl->pool_overflow) {
+                retry = true;
+                break;
+            }
+            if (round == 1) first_dirty = ctx->h_ctl->dirty;
+            // rotate epoch buffers: the new epochs become current
+            if (Ecur == Ebase) {
+                Ecur = Enew, Enew = Efree;
+            } else {
+                std::swap(Ecur, Enew);
+            }
+            if (ctx->h_ctl->dirty == 0) break;
+        }
+        if (retry) {
+            if (W <= phase) {
+                ctx->error = "window result pools overflowed at the minimum window size";
+                return LCB_ERR_CAPACITY;
+            }
+            W = std::max(phase, W / 2 / phase * phase);
+            continue;
+        }
+        // window converged: Ecur holds base + this window's claims
+        k_emit_scan<<<1, 1024, 0, ctx->stream>>>(n, ctx->win, ctx->d_ctl, blocks_done, out_done);
+        k_emit_write<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ix, ctx->prm.k, n, ctx->win, ctx->d_out);
+        ctx->st.kernel_launches += 2;
+        if ((rc = fetch_control(ctx))) return rc;
+        blocks_done += ctx->h_ctl->n_blocks;
+        out_done += ctx->h_ctl->n_out;
+        Ebase = Ecur; // the converged epochs become the committed base; the other two buffers are scratch again
+        {
+            int q = 0;
+            uint32_t *other[2] = {nullptr, nullptr};
+            for (int e = 0; e < 3; e++)
+                if (ctx->d_E[e] != Ebase) other[q++] = ctx->d_E[e];
+            Ea = other[0], Eb = other[1];
+        }
+        ctx->st.windows++;
+        w0 += n;
+        // adapt the window: interference inside the window shows up as first-round invalidations
+        if (first_dirty * 5 > n) W = std::max(phase, W / 2 / phase * phase);
+        else if (first_dirty * 20 < n) W = std::min((unsigned)ctx->prm.window_max, W * 2);
+    }
+    // ---- results ----
+    auto t_d2h = std::chrono::steady_clock::now();
+    lcb_block_instance *host = (lcb_block_instance *)malloc(sizeof(lcb_block_instance) * std::max<size_t>(out_done, 1));
+    if (!host) {
+        ctx->error = "out of host memory";
+        return LCB_ERR_ARG;
+    }
+    CUDA_TRY(cudaMemcpyAsync(host, ctx->d_out, sizeof(lcb_block_instance) * out_done, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    auto t_end = std::chrono::steady_clock::now();
+    ctx->st.ms_d2h = std::chrono::duration<double, std::milli>(t_end - t_d2h).count();
+    ctx->st.d2h_bytes = sizeof(lcb_block_instance) * (uint64_t)out_done;
+    ctx->st.ms_find = std::chrono::duration<double, std::milli>(t_end - t_begin).count();
+    ctx->st.ms_traverse_kernels = trav_ms;
+    ctx->st.n_block_instances = out_done;
+    ctx->st.n_blocks = blocks_done;
+    ctx->st.traversals_first = ctx->h_ctl->runs0;
+    ctx->st.traversals_rerun = ctx->h_ctl->runs1;
+    ctx->st.t_walk = ctx->h_ctl->ct_walk;
+    ctx->st.t_occ = ctx->h_ctl->ct_occ;
+    ctx->st.t_scan = ctx->h_ctl->ct_scan;
+    ctx->st.t_score = ctx->h_ctl->ct_score;
+    *out = host;
+    *n_out = out_done;
+    if (stats) *stats = ctx->st;
+    return LCB_OK;
+}
+
+extern "C" void lcb_free_blocks(lcb_block_instance *p) { free(p); }
+
+extern "C" int lcb_get_stats(lcb_ctx *ctx, lcb_stats *stats)
+{
+    if (!ctx || !stats) return LCB_ERR_ARG;
+    *stats = ctx->st;
+    return LCB_OK;
+}

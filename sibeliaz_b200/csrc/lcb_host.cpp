@@ -1,0 +1,500 @@
+// lcb_host.cpp -- host front end of the B200 sibeliaz-lcb path: input parsing, SoA index build and
+// the output stage.  Mirrors the behaviour (not the code) of the reference:
+//   junction file   SibeliaZ-LCB/common/junctionapi.h:80-98
+//   FASTA           SibeliaZ-LCB/common/streamfastaparser.cpp:28-92, common/dnachar.cpp:13,52-58
+//   index           SibeliaZ-LCB/junctionstorage.h:572-650
+//   output          SibeliaZ-LCB/blocksfinder.h:533-670, blocksfinder.cpp:109-174
+// Everything here is host-only C++ (no CUDA); the device side lives in lcb_device.cu.
+#include "sibeliaz_lcb.h"
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <stdexcept>
+#include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+
+namespace {
+
+struct Failure : std::runtime_error {
+    int code;
+    Failure(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+// Read-only mapping of a whole file (falls back to read() for empty / special files).
+struct MappedFile {
+    const uint8_t *data = nullptr;
+    size_t size = 0;
+    std::vector<uint8_t> owned;
+    bool mapped = false;
+    bool open(const char *path)
+    {
+        int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p != MAP_FAILED) {
+                madvise(p, (size_t)st.st_size, MADV_SEQUENTIAL);
+                data = (const uint8_t *)p;
+                size = (size_t)st.st_size;
+                mapped = true;
+                ::close(fd);
+                return true;
+            }
+        }
+        uint8_t buf[1 << 16];
+        ssize_t n;
+        while ((n = ::read(fd, buf, sizeof buf)) > 0) owned.insert(owned.end(), buf, buf + n);
+        ::close(fd);
+        data = owned.data();
+        size = owned.size();
+        return true;
+    }
+    ~MappedFile()
+    {
+        if (mapped) munmap((void *)data, size);
+    }
+};
+
+// Character classes for the FASTA scanner: 0 = invalid, 1 = whitespace, 2 = '>', else upper-cased base.
+struct FastaTable {
+    uint8_t t[256];
+    FastaTable()
+    {
+        memset(t, 0, sizeof t);
+        const char *valid = "ACGTURYKMSWBDHWNXV"; // dnachar.cpp:13
+        for (const char *p = valid; *p; ++p) {
+            t[(uint8_t)*p] = (uint8_t)*p;
+            t[(uint8_t)tolower(*p)] = (uint8_t)*p;
+        }
+        for (int c = 0; c < 256; c++)
+            if (isspace(c)) t[c] = 1;
+        t[(uint8_t)'>'] = 2;
+    }
+};
+const FastaTable kFasta;
+
+inline uint8_t Complement(uint8_t c) // dnachar.cpp:52-58
+{
+    switch (c) {
+    case 'A': return 'T';
+    case 'C': return 'G';
+    case 'G': return 'C';
+    case 'T': return 'A';
+    }
+    return 'N';
+}
+
+struct FastaRecords {
+    std::vector<std::string> name;
+    std::vector<std::string> seq;
+};
+
+void ParseFasta(const char *path, FastaRecords &out)
+{
+    MappedFile f;
+    if (!f.open(path)) throw Failure(LCB_ERR_IO, std::string("Can't open file ") + path);
+    const uint8_t *p = f.data, *end = f.data + f.size;
+    std::string header;
+    while (p < end) {
+        if (*p != '>')
+            throw Failure(LCB_ERR_FORMAT, std::string("The FASTA header should start with a '>', started with '") + (char)*p + "'");
+        ++p;
+        const uint8_t *nl = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
+        const uint8_t *line_end = nl ? nl : end;
+        if (nl) { // header := first blank-delimited token; an empty header line keeps the previous name
+            const uint8_t *a = p;
+            while (a < line_end && isspace(*a)) ++a;
+            const uint8_t *b = a;
+            while (b < line_end && !isspace(*b)) ++b;
+            if (b > a) header.assign((const char *)a, (size_t)(b - a));
+        }
+        p = nl ? nl + 1 : end;
+        out.name.push_back(header);
+        out.seq.emplace_back();
+        std::string &s = out.seq.back();
+        // size the record first so the bases land with one allocation
+        const uint8_t *q = (const uint8_t *)memchr(p, '>', (size_t)(end - p));
+        const uint8_t *rec_end = q ? q : end;
+        s.resize((size_t)(rec_end - p));
+        char *w = &s[0];
+        for (const uint8_t *r = p; r < rec_end; ++r) {
+            uint8_t c = kFasta.t[*r];
+            if (c > 2) *w++ = (char)c;
+            else if (c == 0)
+                throw Failure(LCB_ERR_FORMAT, std::string("Found an invalid character '") + (char)*r + "' in sequence " + header);
+        }
+        s.resize((size_t)(w - s.data()));
+        p = rec_end;
+    }
+}
+
+} // namespace
+
+struct lcb_index {
+    int k = 0;
+    int32_t C = 0;
+    int64_t N = 0, V = 0;
+    std::vector<int64_t> chr_off, vtx_off, occ_g;
+    std::vector<int32_t> pos_id;
+    std::vector<uint32_t> pos_bp;
+    std::vector<uint8_t> next_ch, prev_rc;
+    FastaRecords fasta;
+    std::string error;
+};
+
+extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_files, int n_fasta, int k, int abundance,
+                              lcb_index **out, char *err, size_t errlen)
+{
+    if (!graph_file || !out || n_fasta < 0 || k <= 0) return LCB_ERR_ARG;
+    lcb_index *ix = new lcb_index;
+    try {
+        ix->k = k;
+        // FASTA files parse concurrently with the junction stream (one thread per file, capped)
+        std::vector<FastaRecords> per_file((size_t)n_fasta);
+        std::vector<std::string> fasta_err((size_t)n_fasta);
+        std::vector<int> fasta_code((size_t)n_fasta, LCB_OK);
+        {
+            unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            unsigned workers = std::min<unsigned>(hw, (unsigned)std::max(1, n_fasta));
+            std::vector<std::thread> pool;
+            for (unsigned w = 0; w < workers; w++)
+                pool.emplace_back([&, w]() {
+                    for (int i = (int)w; i < n_fasta; i += (int)workers) {
+                        try {
+                            ParseFasta(fasta_files[i], per_file[(size_t)i]);
+                        } catch (Failure &e) {
+                            fasta_code[(size_t)i] = e.code;
+                            fasta_err[(size_t)i] = e.what();
+                        }
+                    }
+                });
+
+            // ---- junction records: {u32 pos; i64 id} packed little-endian, 12 bytes ----
+            MappedFile g;
+            if (!g.open(graph_file)) {
+                for (auto &t : pool) t.join();
+                throw Failure(LCB_ERR_IO, "Can't read the input file");
+            }
+            const size_t nrec = g.size / 12;
+            std::vector<uint32_t> rec_chr;
+            std::vector<uint32_t> occ_count; // occurrences per |id| before filtering
+            rec_chr.reserve(nrec);
+            ix->pos_id.reserve(nrec);
+            ix->pos_bp.reserve(nrec);
+            uint32_t chr = 0, max_chr = 0;
+            int64_t max_abs = -1;
+            for (size_t i = 0; i < nrec; i++) {
+                uint32_t pos;
+                int64_t id;
+                memcpy(&pos, g.data + i * 12, 4);
+                memcpy(&id, g.data + i * 12 + 4, 8);
+                if (pos == UINT32_MAX || id == INT64_MAX) { // chromosome separator
+                    ++chr;
+                    continue;
+                }
+                int64_t a = id < 0 ? -id : id;
+                if (a > max_abs) {
+                    max_abs = a;
+                    if ((size_t)a >= occ_count.size()) occ_count.resize((size_t)a + 1 + occ_count.size() / 2, 0);
+                }
+                ++occ_count[(size_t)a];
+                ix->pos_id.push_back((int32_t)id); // int32 truncation as in Position/Vertex
+                ix->pos_bp.push_back(pos);
+                rec_chr.push_back(chr);
+                max_chr = chr;
+            }
+            ix->V = max_abs + 1;
+            ix->C = rec_chr.empty() ? 0 : (int32_t)max_chr + 1;
+            // ---- abundance filter (strict <), compaction in place, per-chromosome offsets ----
+            ix->chr_off.assign((size_t)ix->C + 1, 0);
+            std::vector<int64_t> kept_per_vertex((size_t)ix->V + 1, 0);
+            size_t w = 0;
+            for (size_t i = 0; i < rec_chr.size(); i++) {
+                int64_t id = ix->pos_id[i];
+                // the filter uses the 64-bit |id|; ids beyond int32 would already have broken the reference
+                size_t a = (size_t)(id < 0 ? -id : id);
+                if (occ_count[a] < (size_t)abundance) {
+                    ix->pos_id[w] = ix->pos_id[i];
+                    ix->pos_bp[w] = ix->pos_bp[i];
+                    rec_chr[w] = rec_chr[i];
+                    ++ix->chr_off[(size_t)rec_chr[i] + 1];
+                    ++kept_per_vertex[a];
+                    ++w;
+                }
+            }
+            ix->N = (int64_t)w;
+            ix->pos_id.resize(w);
+            ix->pos_bp.resize(w);
+            rec_chr.resize(w);
+            for (int32_t c = 0; c < ix->C; c++) ix->chr_off[(size_t)c + 1] += ix->chr_off[(size_t)c];
+            // ---- CSR of occurrences; counting sort keeps genome order == (chr, idx) order ----
+            ix->vtx_off.assign((size_t)ix->V + 1, 0);
+            for (int64_t v = 0; v < ix->V; v++) ix->vtx_off[(size_t)v + 1] = ix->vtx_off[(size_t)v] + kept_per_vertex[(size_t)v];
+            ix->occ_g.resize(w);
+            {
+                std::vector<int64_t> cursor(ix->vtx_off.begin(), ix->vtx_off.end() - (ix->V ? 1 : 0));
+                for (size_t gi = 0; gi < w; gi++) {
+                    int64_t id = ix->pos_id[gi];
+                    ix->occ_g[(size_t)cursor[(size_t)(id < 0 ? -id : id)]++] = (int64_t)gi;
+                }
+            }
+            for (auto &t : pool) t.join();
+            for (int i = 0; i < n_fasta; i++)
+                if (fasta_code[(size_t)i] != LCB_OK) throw Failure(fasta_code[(size_t)i], fasta_err[(size_t)i]);
+            for (auto &pf : per_file)
+                for (size_t r = 0; r < pf.seq.size(); r++) {
+                    ix->fasta.name.push_back(std::move(pf.name[r]));
+                    ix->fasta.seq.push_back(std::move(pf.seq[r]));
+                }
+            if ((int64_t)ix->fasta.seq.size() < ix->C)
+                throw Failure(LCB_ERR_FORMAT, "the graph refers to more sequences than the FASTA files contain");
+            // ---- the two characters the traversal needs per junction ----
+            ix->next_ch.resize(w);
+            ix->prev_rc.resize(w);
+            for (size_t gi = 0; gi < w; gi++) {
+                const std::string &s = ix->fasta.seq[rec_chr[gi]];
+                size_t p = ix->pos_bp[gi];
+                if (p + (size_t)k > s.size()) throw Failure(LCB_ERR_FORMAT, "junction position beyond the end of its sequence (wrong -k or FASTA?)");
+                ix->next_ch[gi] = p + (size_t)k < s.size() ? (uint8_t)s[p + (size_t)k] : 0;
+                ix->prev_rc[gi] = p > 0 ? Complement((uint8_t)s[p - 1]) : (uint8_t)'N';
+            }
+        }
+    } catch (Failure &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        int code = e.code;
+        delete ix;
+        return code;
+    } catch (std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        delete ix;
+        return LCB_ERR_IO;
+    }
+    *out = ix;
+    return LCB_OK;
+}
+
+extern "C" int lcb_index_get_view(const lcb_index *ix, lcb_index_view *v)
+{
+    if (!ix || !v) return LCB_ERR_ARG;
+    v->n_chr = ix->C;
+    v->n_records = ix->N;
+    v->n_vertices = ix->V;
+    v->chr_off = ix->chr_off.data();
+    v->pos_id = ix->pos_id.data();
+    v->pos_bp = ix->pos_bp.data();
+    v->next_ch = ix->next_ch.data();
+    v->prev_rc = ix->prev_rc.data();
+    v->vtx_off = ix->vtx_off.data();
+    v->occ_g = ix->occ_g.data();
+    return LCB_OK;
+}
+
+extern "C" int32_t lcb_index_num_chr(const lcb_index *ix) { return ix ? ix->C : 0; }
+extern "C" const char *lcb_index_chr_name(const lcb_index *ix, int32_t c)
+{
+    return (ix && c >= 0 && (size_t)c < ix->fasta.name.size()) ? ix->fasta.name[(size_t)c].c_str() : "";
+}
+extern "C" int64_t lcb_index_chr_length(const lcb_index *ix, int32_t c)
+{
+    return (ix && c >= 0 && (size_t)c < ix->fasta.seq.size()) ? (int64_t)ix->fasta.seq[(size_t)c].size() : -1;
+}
+extern "C" void lcb_index_free(lcb_index *ix) { delete ix; }
+
+// =================================================================================================
+// Output stage.  Byte-identical GFF needs the same comparison sequence fed to the same libstdc++
+// std::sort (an unstable introsort) as the reference does at blocksfinder.h:103/623, :662 and
+// blocksfinder.cpp:146 -- so the three sorts below are kept, on records in the same order.
+// =================================================================================================
+namespace {
+
+struct OutBlock {
+    int32_t id;
+    uint32_t chr;
+    uint64_t start, end;
+    int32_t abs_id() const { return id < 0 ? -id : id; }
+};
+
+struct TextBuffer {
+    std::string s;
+    void put(const char *p, size_t n) { s.append(p, n); }
+    void put(const std::string &x) { s.append(x); }
+    void put(char c) { s.push_back(c); }
+    void num(uint64_t v)
+    {
+        char tmp[24];
+        int n = 0;
+        do {
+            tmp[n++] = (char)('0' + v % 10);
+            v /= 10;
+        } while (v);
+        while (n) s.push_back(tmp[--n]);
+    }
+};
+
+void WriteFile(const std::string &path, const std::string &data)
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) throw Failure(LCB_ERR_IO, "Cannot open file " + path);
+    size_t done = fwrite(data.data(), 1, data.size(), f);
+    if (fclose(f) != 0 || done != data.size()) throw Failure(LCB_ERR_IO, "Cannot write file " + path);
+}
+
+} // namespace
+
+extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *blocks, uint64_t n, int min_block,
+                                const char *out_dir, int gen_seq, int chunks, int64_t *blocks_found, double *coverage,
+                                char *err, size_t errlen)
+{
+    if (!ix || (!blocks && n) || !out_dir) return LCB_ERR_ARG;
+    try {
+        if (gen_seq && chunks <= 0) throw Failure(LCB_ERR_ARG, "--chunks must be positive when block sequences are written");
+        const int32_t C = ix->C;
+        int32_t max_id = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            if (blocks[i].chr >= (uint32_t)C) throw Failure(LCB_ERR_ARG, "block instance refers to an unknown sequence");
+            max_id = std::max(max_id, blocks[i].id < 0 ? -blocks[i].id : blocks[i].id);
+        }
+        std::vector<int> copies((size_t)max_id + 1, 0);
+        std::vector<OutBlock> inst(n);
+        for (uint64_t i = 0; i < n; i++) {
+            inst[i] = OutBlock{blocks[i].id, blocks[i].chr, blocks[i].start, blocks[i].end};
+            ++copies[(size_t)inst[i].abs_id()];
+        }
+        // (1) blocksfinder.h:623 -- by (copies desc, id asc), unstable
+        auto by_multiplicity = [&copies](const OutBlock &a, const OutBlock &b) {
+            int ma = copies[(size_t)a.abs_id()], mb = copies[(size_t)b.abs_id()];
+            if (ma != mb) return ma > mb;
+            return a.abs_id() < b.abs_id();
+        };
+        std::sort(inst.begin(), inst.end(), by_multiplicity);
+        // trimming against per-base coverage bitmaps, blocksfinder.h:607-656
+        std::vector<std::vector<bool>> covered((size_t)C);
+        for (int32_t c = 0; c < C; c++) covered[(size_t)c].assign(ix->fasta.seq[(size_t)c].size() + 1, false);
+        std::vector<OutBlock> kept, group;
+        int64_t next_id = 1;
+        for (size_t lo = 0; lo < inst.size();) {
+            size_t hi = lo;
+            while (hi < inst.size() && !by_multiplicity(inst[lo], inst[hi])) ++hi;
+            group.clear();
+            for (size_t i = lo; i < hi; i++) {
+                std::vector<bool> &cov = covered[inst[i].chr];
+                uint64_t s = inst[i].start, e = inst[i].end;
+                while (cov[s] && s < e) ++s;
+                while (cov[e] && e > s) --e;
+                if (e - s >= (uint64_t)min_block) {
+                    group.push_back(OutBlock{(int32_t)(inst[i].id > 0 ? next_id : -next_id), inst[i].chr, s, e});
+                    std::fill(cov.begin() + (ptrdiff_t)s, cov.begin() + (ptrdiff_t)e, true);
+                }
+            }
+            if (group.size() > 1) {
+                ++next_id;
+                kept.insert(kept.end(), group.begin(), group.end());
+            } else {
+                for (const OutBlock &b : group)
+                    std::fill(covered[b.chr].begin() + (ptrdiff_t)b.start, covered[b.chr].begin() + (ptrdiff_t)b.end, false);
+            }
+            lo = hi;
+        }
+        uint64_t total = 0, in_blocks = 0;
+        for (int32_t c = 0; c < C; c++) total += ix->fasta.seq[(size_t)c].size();
+        for (const OutBlock &b : kept) in_blocks += b.end - b.start;
+        if (blocks_found) *blocks_found = next_id - 1;
+        if (coverage) *coverage = total ? double(in_blocks) / double(total) : 0.0;
+        // (2) blocksfinder.h:662 -- BlockInstance::operator< = (|id|, chr, start), unstable
+        std::sort(kept.begin(), kept.end(), [](const OutBlock &a, const OutBlock &b) {
+            if (a.abs_id() != b.abs_id()) return a.abs_id() < b.abs_id();
+            if (a.chr != b.chr) return a.chr < b.chr;
+            return a.start < b.start;
+        });
+        if (mkdir(out_dir, 0755) != 0 && errno != EEXIST) throw Failure(LCB_ERR_IO, std::string("Cannot create dir ") + out_dir);
+        auto by_id = [](const OutBlock &a, const OutBlock &b) { return a.abs_id() < b.abs_id(); };
+        {
+            // (3) blocksfinder.cpp:146 -- by |id| only, unstable, on a copy
+            std::vector<OutBlock> rows(kept);
+            std::sort(rows.begin(), rows.end(), by_id);
+            TextBuffer t;
+            t.s.reserve(64 + rows.size() * 64);
+            t.put("##gff-version 3.1.26\n", 21);
+            for (int32_t c = 0; c < C; c++) {
+                t.put("##sequence-region ", 18);
+                t.put(ix->fasta.name[(size_t)c]);
+                t.put(" 1 ", 3);
+                t.num(ix->fasta.seq[(size_t)c].size());
+                t.put('\n');
+            }
+            for (const OutBlock &b : rows) {
+                t.put(ix->fasta.name[b.chr]);
+                t.put("\tSibeliaZ\tSO:0000856\t", 21);
+                t.num(b.start + 1);
+                t.put('\t');
+                t.num(b.end);
+                t.put("\t.\t", 3);
+                t.put(b.id > 0 ? '+' : '-');
+                t.put("\t.\tID=", 6);
+                t.num((uint64_t)b.abs_id());
+                t.put('\n');
+            }
+            WriteFile(std::string(out_dir) + "/blocks_coords.gff", t.s);
+        }
+        if (gen_seq) {
+            // blocksfinder.h:533-582: one line per block, blocks dealt round-robin over `chunks` files
+            std::vector<OutBlock> rows(kept);
+            std::sort(rows.begin(), rows.end(), by_id);
+            std::vector<TextBuffer> chunk((size_t)chunks);
+            size_t which = 0;
+            for (size_t lo = 0; lo < rows.size();) {
+                size_t hi = lo;
+                while (hi < rows.size() && !by_id(rows[lo], rows[hi])) ++hi;
+                TextBuffer &t = chunk[which];
+                for (size_t i = lo; i < hi; i++) {
+                    const OutBlock &b = rows[i];
+                    const std::string &s = ix->fasta.seq[b.chr];
+                    uint64_t len = b.end - b.start;
+                    t.put("> ", 2);
+                    t.put(ix->fasta.name[b.chr]);
+                    t.put(';');
+                    if (b.id > 0) {
+                        t.num(b.start);
+                        t.put(';');
+                        t.num(len);
+                        t.put(";+;", 3);
+                        t.num(s.size());
+                        t.put('@');
+                        t.put(s.data() + b.start, (size_t)len);
+                    } else {
+                        t.num(s.size() - b.end);
+                        t.put(';');
+                        t.num(len);
+                        t.put(";-;", 3);
+                        t.num(s.size());
+                        t.put('@');
+                        for (uint64_t j = 0; j < len; j++) t.put((char)Complement((uint8_t)s[b.end - 1 - j]));
+                    }
+                    t.put('@');
+                }
+                t.put('\n');
+                which = (which + 1) % (size_t)chunks;
+                lo = hi;
+            }
+            for (int i = 0; i < chunks; i++) WriteFile(std::string(out_dir) + "/" + std::to_string(i) + ".tmp", chunk[(size_t)i].s);
+        }
+    } catch (Failure &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return e.code;
+    } catch (std::exception &e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return LCB_ERR_IO;
+    }
+    return LCB_OK;
+}
+
+extern "C" const char *lcb_version(void) { return "sibeliaz-lcb-b200 0.1 (output-compatible with SibeliaZ-LCB 1.2.7)"; }

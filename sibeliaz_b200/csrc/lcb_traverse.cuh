@@ -1,0 +1,764 @@
+// lcb_traverse.cuh -- warp-per-seed carving-path traversal for sm_100a.
+//
+// One warp evaluates ProcessVertex::Process (SibeliaZ-LCB/blocksfinder.h:228-310) for one seed:
+// Path::Init (path.h:33-46), the forward/backward extension loops driven by MostPopularVertex
+// (blocksfinder.h:708-768) and Path::PointPushBack/Front (path.h:430-602), Path::Score (path.h:604-628).
+//
+// Design (B200-first, not a translation):
+//  * the reference's `used` bit per edge becomes a 32-bit EPOCH per edge: the index of the seed that
+//    claimed it (0xFFFFFFFF = free).  A traversal sees an edge as used iff epoch < its threshold
+//    (phase start for the speculative evaluation, its own seed index for a commit-time re-run), so
+//    thousands of seeds of different phases run concurrently against ONE array with no snapshots;
+//  * every epoch the traversal's outcome depends on is recorded as a read-set of index intervals, so a
+//    later round can re-validate the result instead of recomputing it (lcb_device.cu);
+//  * per-seed state (path vertex->distance hash, instance table in multiset order, vote table, best
+//    snapshot) lives in shared memory and spills to a per-warp HBM scratch arena only for big paths;
+//  * lanes are spent on the memory-latency-bound parts: look-ahead walks (one lane per depth), occurrence
+//    lists (one lane per occurrence), `used` scans, ordered searches via ballot; control flow is warp-uniform.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lcb {
+
+constexpr uint32_t kFree = 0xFFFFFFFFu;
+constexpr int kNotSet = 0x7FFFFFFF;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// ---- capacities -----------------------------------------------------------------------------------
+constexpr int kInstSmem = 32;      // instances kept in shared memory
+constexpr int kInstMax = 4096;     // hard cap (HBM arena)
+constexpr int kHashSmem = 256;     // path hash slots in shared memory (<=128 vertices)
+constexpr int kHashMax = 65536;    // hard cap: 32768 path vertices
+constexpr int kPathMax = 32768;
+constexpr int kVoteSmem = 64;      // vote candidates in shared memory
+constexpr int kVoteMax = 8192;
+constexpr int kReadSetMax = 65536; // read-set intervals per traversal
+
+struct Inst { // Path::Instance (path.h:53-181) with cached end-point data; 56 bytes
+    int fg, bg;         // front_/back_ : global record index
+    int fv, bv;         // strand-signed vertex id at front/back
+    unsigned fbp, bbp;  // raw base-pair position at front/back
+    int fdist, bdist;   // frontDistance_/backDistance_
+    int key;            // compareIdx_ as a global index
+    int rlo, rhi;       // read extent over epoch indices (rlo > rhi: empty)
+    int clo, chi;       // chromosome bounds [clo, chi) of this instance
+    unsigned flags;     // bit0 strand (+), bit1 frontFinished, bit2 backFinished
+};
+constexpr unsigned kPos = 1u, kFFin = 2u, kBFin = 4u;
+
+struct Index { // device view of the SoA junction index
+    const int2 *rec;        // {id, bp} per record
+    const uchar2 *chs;      // {next_ch, prev_rc} per record
+    const uint32_t *vtx_off;
+    const uint32_t *occ;
+    const uint32_t *chr_off;
+    int C, N, V;
+};
+
+struct Params {
+    int k, b, m, flank, depth;
+};
+
+struct WarpSmem { // ~5 KB per warp
+    Inst inst[kInstSmem];
+    int4 best[kInstSmem];
+    int2 hash[kHashSmem];
+    int2 vote[kVoteSmem];
+    unsigned short ord[kInstSmem];
+    unsigned short good[kInstSmem];
+};
+
+struct WarpArena { // per-warp HBM scratch (spill + variable-length logs)
+    Inst *inst;           // kInstMax
+    int4 *best;           // kInstMax
+    unsigned short *ord;  // kInstMax
+    unsigned short *good; // kInstMax
+    int2 *hash;           // kHashMax
+    int *hslot;           // kPathMax: slots occupied in the HBM hash (for O(path) clearing)
+    int4 *redge;          // kPathMax: successful right edges {end vertex, length, source g, source strand}
+    int2 *vote;           // kVoteMax
+    int2 *rs;             // kReadSetMax: read-set intervals [lo, hi] over epoch indices
+};
+
+struct Counters {
+    unsigned long long walk, occ, scan, score;
+};
+
+struct Ctx { // warp-uniform traversal state (registers)
+    Index ix;
+    Params pr;
+    const uint32_t *E;
+    uint32_t thresh;
+    int lane;
+    // storage (shared or arena)
+    Inst *inst;
+    int4 *best;
+    unsigned short *ord, *good;
+    int2 *hash;
+    int2 *vote;
+    int icap, hmask, vcap;
+    bool hbig;
+    WarpSmem *sm;
+    WarpArena ar;
+    // path
+    int origin, right_vertex, left_vertex;
+    int right_flank, left_flank; // rightBodyFlank_, leftBodyFlank_
+    int nright, nleft;           // successful pushes
+    int ninst, ngood, nbest, hcount, nrs;
+    int err; // 0 or LCB_ERR_CAPACITY
+    Counters ct;
+};
+
+__device__ __forceinline__ int ffs_lane(unsigned m) { return __ffs((int)m) - 1; }
+
+__device__ __forceinline__ unsigned hash_of(int key) { return (unsigned)key * 2654435761u; }
+
+// vertex -> path distance (DistanceKeeper, distancekeeper.h:9-41), open addressing, key 0 = empty
+__device__ __forceinline__ int hash_find(const int2 *h, int mask, int key)
+{
+    unsigned s = (hash_of(key) >> 12) & (unsigned)mask;
+    while (true) {
+        int2 kv = h[s];
+        if (kv.x == key) return kv.y;
+        if (kv.x == 0) return kNotSet;
+        s = (s + 1) & (unsigned)mask;
+    }
+}
+
+__device__ __forceinline__ void chr_bounds(const Index &ix, int g, int &lo, int &hi)
+{
+    int a = 0, b = ix.C; // chr_off[a] <= g < chr_off[b]
+    while (b - a > 1) {
+        int mid = (a + b) >> 1;
+        if ((int)__ldg(ix.chr_off + mid) <= g) a = mid;
+        else b = mid;
+    }
+    lo = (int)__ldg(ix.chr_off + a);
+    hi = (int)__ldg(ix.chr_off + a + 1);
+}
+
+__device__ __forceinline__ void ctx_reset_storage(Ctx &c)
+{
+    c.inst = c.sm->inst;
+    c.best = c.sm->best;
+    c.ord = c.sm->ord;
+    c.good = c.sm->good;
+    c.vote = c.sm->vote;
+    c.icap = kInstSmem;
+    c.vcap = kVoteSmem;
+}
+
+__device__ __forceinline__ void hash_clear(Ctx &c)
+{
+    if (c.hbig) { // only the slots the path occupied
+        for (int i = c.lane; i < c.hcount; i += 32) c.ar.hash[c.ar.hslot[i]].x = 0;
+    } else {
+        for (int i = c.lane; i < kHashSmem; i += 32) c.hash[i] = make_int2(0, 0);
+    }
+    __syncwarp();
+    c.hcount = 0;
+}
+
+// uniform insert (all lanes pass the same key); grows shared -> arena at half load
+__device__ __noinline__ void hash_insert(Ctx &c, int key, int val)
+{
+    if (!c.hbig && (c.hcount + 1) * 2 > kHashSmem) {
+        // migrate: arena table is kept all-zero between uses
+        int n = 0;
+        for (int base = 0; base < kHashSmem; base += 32) {
+            int2 kv = c.hash[base + c.lane];
+            bool live = kv.x != 0;
+            unsigned m = __ballot_sync(kFull, live);
+            if (live) {
+                unsigned s = (hash_of(kv.x) >> 12) & (unsigned)(kHashMax - 1);
+                while (atomicCAS(&c.ar.hash[s].x, 0, kv.x) != 0) s = (s + 1) & (unsigned)(kHashMax - 1);
+                c.ar.hash[s].y = kv.y;
+                c.ar.hslot[n + __popc(m & ((1u << c.lane) - 1))] = (int)s;
+            }
+            n += __popc(m);
+        }
+        __syncwarp();
+        c.hash = c.ar.hash;
+        c.hmask = kHashMax - 1;
+        c.hbig = true;
+    }
+    if (c.hbig && c.hcount + 1 > kPathMax) {
+        c.err = LCB_ERR_CAPACITY;
+        return;
+    }
+    if (c.lane == 0) {
+        unsigned s = (hash_of(key) >> 12) & (unsigned)c.hmask;
+        while (c.hash[s].x != 0) s = (s + 1) & (unsigned)c.hmask;
+        c.hash[s] = make_int2(key, val);
+        if (c.hbig) c.ar.hslot[c.hcount] = (int)s;
+    }
+    c.hcount++;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void rs_add(Ctx &c, int lo, int hi) // uniform
+{
+    if (c.nrs >= kReadSetMax) {
+        c.err = LCB_ERR_CAPACITY;
+        return;
+    }
+    if (c.lane == 0) c.ar.rs[c.nrs] = make_int2(lo, hi);
+    c.nrs++;
+}
+
+__device__ __forceinline__ void inst_extend_reads(Inst &I, int lo, int hi) // single writer
+{
+    if (lo < I.rlo) I.rlo = lo;
+    if (hi > I.rhi) I.rhi = hi;
+}
+
+// spill the instance tables from shared memory to the arena
+__device__ __noinline__ void inst_grow(Ctx &c)
+{
+    if (c.icap != kInstSmem) {
+        c.err = LCB_ERR_CAPACITY;
+        return;
+    }
+    for (int i = c.lane; i < c.ninst; i += 32) {
+        c.ar.inst[i] = c.inst[i];
+        c.ar.ord[i] = c.ord[i];
+    }
+    for (int i = c.lane; i < c.ngood; i += 32) c.ar.good[i] = c.good[i];
+    for (int i = c.lane; i < c.nbest; i += 32) c.ar.best[i] = c.best[i];
+    __syncwarp();
+    c.inst = c.ar.inst;
+    c.ord = c.ar.ord;
+    c.good = c.ar.good;
+    c.best = c.ar.best;
+    c.icap = kInstMax;
+}
+
+// position of the first instance (multiset order) whose key > `key`  (std::multiset::upper_bound)
+__device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
+{
+    for (int base = 0; base < c.ninst; base += 32) {
+        int i = base + c.lane;
+        bool gt = i < c.ninst && c.inst[c.ord[i]].key > key;
+        unsigned m = __ballot_sync(kFull, gt);
+        if (m) return base + ffs_lane(m);
+    }
+    return c.ninst;
+}
+
+// Instance(it, distance) + multiset insert + allInstance_.push_back   (path.h:82-91, :43, :492, :561)
+__device__ __noinline__ void inst_insert(Ctx &c, int at, int g, bool pos, int v, unsigned bp, int dist, int flag_idx,
+                                         int clo, int chi)
+{
+    if (c.ninst >= c.icap) {
+        inst_grow(c);
+        if (c.err) return;
+    }
+    int id = c.ninst;
+    for (int top = c.ninst - 1; top >= at; top -= 32) { // shift [at, ninst) up by one, high chunks first
+        int i = top - c.lane;
+        unsigned short x = 0;
+        if (i >= at) x = c.ord[i];
+        __syncwarp();
+        if (i >= at) c.ord[i + 1] = x;
+        __syncwarp();
+    }
+    if (c.lane == 0) {
+        Inst I;
+        I.fg = I.bg = g;
+        I.fv = I.bv = v;
+        I.fbp = I.bbp = bp;
+        I.fdist = I.bdist = dist;
+        I.key = g;
+        I.rlo = flag_idx >= 0 ? flag_idx : 0x7FFFFFFF;
+        I.rhi = flag_idx >= 0 ? flag_idx : -1;
+        I.clo = clo;
+        I.chi = chi;
+        I.flags = pos ? kPos : 0u;
+        c.inst[id] = I;
+        c.ord[at] = (unsigned short)id;
+    }
+    c.ninst++;
+    __syncwarp();
+}
+
+// Path::Clear (path.h:650-677): also flushes the per-instance read extents into the read-set log
+__device__ __noinline__ void path_clear(Ctx &c)
+{
+    for (int base = 0; base < c.ninst; base += 32) {
+        int i = base + c.lane;
+        int lo = 0, hi = -1;
+        if (i < c.ninst) {
+            lo = c.inst[i].rlo;
+            hi = c.inst[i].rhi;
+        }
+        bool live = lo <= hi;
+        unsigned m = __ballot_sync(kFull, live);
+        int n = __popc(m);
+        if (c.nrs + n > kReadSetMax) {
+            c.err = LCB_ERR_CAPACITY;
+            break;
+        }
+        if (live) c.ar.rs[c.nrs + __popc(m & ((1u << c.lane) - 1))] = make_int2(lo, hi);
+        c.nrs += n;
+    }
+    hash_clear(c);
+    if (c.hbig) { // arena table is all-zero again; go back to shared memory
+        c.hbig = false;
+        c.hash = c.sm->hash;
+        c.hmask = kHashSmem - 1;
+        for (int i = c.lane; i < kHashSmem; i += 32) c.hash[i] = make_int2(0, 0);
+    }
+    // the best snapshot survives Clear(): keep it where it is, move the rest back to shared memory
+    if (c.icap != kInstSmem && c.nbest <= kInstSmem) {
+        for (int i = c.lane; i < c.nbest; i += 32) c.sm->best[i] = c.best[i];
+        __syncwarp();
+        ctx_reset_storage(c);
+    } else if (c.icap != kInstSmem) {
+        c.inst = c.ar.inst; // stay in the arena
+    }
+    c.ninst = c.ngood = 0;
+    c.nright = c.nleft = 0;
+    __syncwarp();
+}
+
+// per-lane occurrence record used by Init and PointPush*
+struct Occ {
+    int g, v_id, clo, chi, flag;
+    unsigned bp;
+    bool pos, used;
+};
+
+__device__ __forceinline__ Occ load_occurrence(const Ctx &c, unsigned o, int vertex)
+{
+    Occ r;
+    r.g = (int)__ldg(c.ix.occ + o);
+    int2 rc = __ldg(c.ix.rec + r.g);
+    r.v_id = rc.x;
+    r.bp = (unsigned)rc.y;
+    r.pos = rc.x == vertex; // JunctionIterator::IsPositiveStrand, junctionstorage.h:408-411
+    chr_bounds(c.ix, r.g, r.clo, r.chi);
+    bool has = r.pos || r.g > r.clo; // IsUsed on the - strand at idx 0 is false (junctionstorage.h:277-282)
+    r.flag = has ? (r.pos ? r.g : r.g - 1) : -1;
+    r.used = has ? (__ldcg(c.E + r.flag) < c.thresh) : false;
+    return r;
+}
+
+// Path::Init (path.h:33-46)
+__device__ __noinline__ void path_init(Ctx &c, int vid, unsigned char ch)
+{
+    c.origin = c.right_vertex = c.left_vertex = vid;
+    c.right_flank = c.left_flank = 0;
+    hash_insert(c, vid, 0);
+    int av = vid < 0 ? -vid : vid;
+    unsigned o0 = __ldg(c.ix.vtx_off + av), o1 = __ldg(c.ix.vtx_off + av + 1);
+    for (unsigned base = o0; base < o1; base += 32) {
+        unsigned o = base + (unsigned)c.lane;
+        Occ q;
+        bool match = false;
+        if (o < o1) {
+            q = load_occurrence(c, o, vid);
+            uchar2 cc = __ldg(c.ix.chs + q.g);
+            match = (q.pos ? cc.x : cc.y) == ch; // seqIt.GetChar(), junctionstorage.h:234-243
+        }
+        unsigned mm = __ballot_sync(kFull, match);
+        while (mm) { // occurrences in (chr, idx) order
+            int src = ffs_lane(mm);
+            mm &= mm - 1;
+            int g = __shfl_sync(kFull, q.g, src);
+            bool pos = __shfl_sync(kFull, (int)q.pos, src);
+            bool used = __shfl_sync(kFull, (int)q.used, src);
+            unsigned bp = __shfl_sync(kFull, q.bp, src);
+            int flag = __shfl_sync(kFull, q.flag, src);
+            int clo = __shfl_sync(kFull, q.clo, src), chi = __shfl_sync(kFull, q.chi, src);
+            if (used) {
+                rs_add(c, flag, flag); // outcome depends on this epoch although no instance is born
+            } else {
+                int at = ord_upper_bound(c, g);
+                inst_insert(c, at, g, pos, vid, bp, 0, flag, clo, chi);
+            }
+            if (c.err) return;
+        }
+    }
+}
+
+// any epoch < thresh in [lo, hi]?   (the `used` scan of Path::Compatible, path.h:387-393)
+__device__ __forceinline__ bool scan_used(Ctx &c, int lo, int hi)
+{
+    bool any = false;
+    for (int base = lo; base <= hi && !any; base += 32) {
+        int f = base + c.lane;
+        bool u = f <= hi && __ldcg(c.E + f) < c.thresh;
+        any = __any_sync(kFull, u);
+    }
+    c.ct.scan += (unsigned long long)(hi - lo + 1);
+    return any;
+}
+
+// Path::PointPushBack / PointPushFront with their workers (path.h:430-602).  BACK: `v` = e.GetEndVertex(),
+// FRONT: `v` = e.GetStartVertex().  e_ch_g/e_ch_pos locate the junction whose char is e.GetChar();
+// e_other is e.GetEndVertex() for FRONT (the far-branch test `start1.GetVertexId() != e.GetEndVertex()`).
+template <bool BACK>
+__device__ __noinline__ bool path_push(Ctx &c, int v, int len, int e_ch_g, bool e_ch_pos, int e_other)
+{
+    if (hash_find(c.hash, c.hmask, v) != kNotSet) return false; // vertex already in the path
+    const int dist = BACK ? c.right_flank + len : c.left_flank - len;
+    hash_insert(c, v, dist);
+    if (c.err) return true;
+    int av = v < 0 ? -v : v;
+    unsigned o0 = __ldg(c.ix.vtx_off + av), o1 = __ldg(c.ix.vtx_off + av + 1);
+    c.ct.occ += o1 - o0;
+    for (unsigned base = o0; base < o1; base += 32) {
+        unsigned o = base + (unsigned)c.lane;
+        Occ q;
+        q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = 0, q.chi = 0;
+        if (o < o1) q = load_occurrence(c, o, v);
+        int cnt = (int)min(32u, o1 - base);
+        for (int j = 0; j < cnt; j++) {
+            const int g = __shfl_sync(kFull, q.g, j);
+            const bool pos = __shfl_sync(kFull, (int)q.pos, j);
+            const bool used = __shfl_sync(kFull, (int)q.used, j);
+            const unsigned bp = __shfl_sync(kFull, q.bp, j);
+            const int flag = __shfl_sync(kFull, q.flag, j);
+            const int clo = __shfl_sync(kFull, q.clo, j), chi = __shfl_sync(kFull, q.chi, j);
+            const int ub = ord_upper_bound(c, g);
+            int hi_id = -1, lo_id = -1; // neighbours inside this chromosome's multiset
+            if (ub < c.ninst) {
+                int id = c.ord[ub];
+                if (c.inst[id].key < chi) hi_id = id;
+            }
+            if (ub > 0) {
+                int id = c.ord[ub - 1];
+                if (c.inst[id].key >= clo) lo_id = id;
+            }
+            if (hi_id >= 0) { // Instance::Within, path.h:170-175
+                int a = c.inst[hi_id].fg, b = c.inst[hi_id].bg;
+                if (g >= min(a, b) && g <= max(a, b)) continue;
+            }
+            // BACK: + occurrences look at the predecessor, - at upper_bound; FRONT: the other way round
+            const int cand = (pos == BACK) ? lo_id : hi_id;
+            bool extend = false;
+            int scan_lo = 0, scan_hi = -1;
+            if (cand >= 0) { // Path::Compatible (path.h:380-428), pure tests first, epoch scan last
+                const Inst I = c.inst[cand];
+                const bool cpos = (I.flags & kPos) != 0;
+                const int cg = BACK ? I.bg : I.fg;
+                const unsigned cbp = BACK ? I.bbp : I.fbp;
+                const int cdist = BACK ? I.bdist : I.fdist;
+                if (cpos == pos) {
+                    long long rd = BACK ? (long long)bp - (long long)cbp : (long long)cbp - (long long)bp;
+                    if (!pos) rd = -rd;
+                    const long long ad = BACK ? (long long)dist - cdist : (long long)cdist - dist;
+                    bool ok = rd >= 0;
+                    if (ok && (rd > c.pr.b || ad > c.pr.b)) {
+                        // only the exact next junction along the strand may continue the instance
+                        const int step = pos ? 1 : -1;
+                        const bool adjacent = BACK ? (g == cg + step) : (cg == g + step);
+                        ok = adjacent;
+                        if (ok) {
+                            uchar2 ce = __ldg(c.ix.chs + e_ch_g);
+                            unsigned char ech = e_ch_pos ? ce.x : ce.y;
+                            uchar2 cs = __ldg(c.ix.chs + (BACK ? cg : g));
+                            unsigned char sch = pos ? cs.x : cs.y;
+                            ok = sch == ech;
+                            if (!BACK) ok = ok && I.fv == e_other;
+                        }
+                    }
+                    if (ok) {
+                        scan_lo = min(cg, g);
+                        scan_hi = max(cg, g) - 1;
+                        ok = !scan_used(c, scan_lo, scan_hi);
+                    }
+                    extend = ok;
+                }
+            }
+            const int cend_v = cand >= 0 ? (BACK ? c.inst[cand].bv : c.inst[cand].fv) : 0;
+            if (cand >= 0 && scan_lo <= scan_hi && c.lane == 0) inst_extend_reads(c.inst[cand], scan_lo, scan_hi);
+            if (extend && cend_v != v) {
+                const unsigned fin = BACK ? kBFin : kFFin;
+                if (c.lane == 0 && !(c.inst[cand].flags & fin)) {
+                    Inst &I = c.inst[cand];
+                    unsigned a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
+                    bool prev_good = (long long)a >= c.pr.m; // IsGoodInstance, path.h:645-648
+                    if (BACK) { // ChangeBack, path.h:124-133
+                        I.bg = g, I.bv = v, I.bbp = bp, I.bdist = dist;
+                        if (pos) I.key = g;
+                    } else { // ChangeFront, path.h:113-122
+                        I.fg = g, I.fv = v, I.fbp = bp, I.fdist = dist;
+                        if (!pos) I.key = g;
+                    }
+                    a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
+                    if (!prev_good && (long long)a >= c.pr.m) c.good[c.ngood] = (unsigned short)cand, c.ngood |= 0x40000000;
+                    if (flag >= 0) inst_extend_reads(I, flag, flag);
+                    if (used) I.flags |= fin;
+                }
+                // lane 0 flagged a goodInstance_ append in bit 30; make the count uniform again
+                int ng = __shfl_sync(kFull, c.ngood, 0);
+                c.ngood = (ng & 0x40000000) ? (ng & 0x3FFFFFFF) + 1 : ng;
+                __syncwarp();
+            } else if (!used) {
+                inst_insert(c, ub, g, pos, v, bp, dist, flag, clo, chi);
+                if (c.err) return true;
+            } else if (flag >= 0) {
+                rs_add(c, flag, flag);
+            }
+            __syncwarp();
+        }
+    }
+    if (BACK) {
+        if (c.nright >= kPathMax) {
+            c.err = LCB_ERR_CAPACITY;
+            return true;
+        }
+        if (c.lane == 0) c.ar.redge[c.nright] = make_int4(v, len, e_ch_g, (int)e_ch_pos);
+        c.nright++;
+        c.right_flank = dist;
+        c.right_vertex = v;
+    } else {
+        c.nleft++;
+        c.left_flank = dist;
+        c.left_vertex = v;
+    }
+    __syncwarp();
+    return true;
+}
+
+// Path::Score (path.h:604-628): any flank penalty >= maxFlankingSize makes the whole score -INT32_MAX
+__device__ __forceinline__ long long path_score(Ctx &c)
+{
+    long long sum = 0;
+    bool bad = false;
+    for (int base = 0; base < c.ngood; base += 32) {
+        int i = base + c.lane;
+        if (i < c.ngood) {
+            const Inst &I = c.inst[c.good[i]];
+            long long real = I.fbp > I.bbp ? (long long)(I.fbp - I.bbp) : (long long)(I.bbp - I.fbp);
+            long long rp = (long long)c.right_flank - I.bdist;
+            long long lp = (long long)(-c.left_flank) + I.fdist;
+            if (lp >= c.pr.flank || rp >= c.pr.flank) bad = true;
+            sum += real - (rp + lp) * (rp + lp);
+        }
+    }
+    c.ct.score += (unsigned long long)c.ngood;
+    bad = __any_sync(kFull, bad);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
+    return bad ? -(long long)0x7FFFFFFF : sum;
+}
+
+// bestInstance = copies of *goodInstance_[i] in list order (blocksfinder.h:818-825, :881-888)
+__device__ __forceinline__ void snapshot_best(Ctx &c)
+{
+    for (int i = c.lane; i < c.ngood; i += 32) {
+        const Inst &I = c.inst[c.good[i]];
+        c.best[i] = make_int4(I.fg | ((I.flags & kPos) ? (int)0x80000000 : 0), I.bg, (int)I.fbp, (int)I.bbp);
+    }
+    c.nbest = c.ngood;
+    __syncwarp();
+}
+
+struct Next { // result of MostPopularVertex
+    int vid, og, d;
+    bool opos;
+};
+
+// BlocksFinder::MostPopularVertex (blocksfinder.h:708-768).  Lanes = look-ahead depths of one instance;
+// the vote itself is replayed in reference order (running arg-max with the origin tie-break).
+__device__ __noinline__ Next most_popular_vertex(Ctx &c, bool forward, bool try_used)
+{
+    Next best;
+    best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
+    long long best_count = 0;
+    int nvote = 0;
+    const int start_vid = forward ? c.right_vertex : c.left_vertex;
+    const bool use_good = c.ngood >= 2;
+    const int n = use_good ? c.ngood : c.ninst;
+    for (int q = 0; q < n; q++) {
+        const int id = use_good ? (int)c.good[q] : q;
+        const Inst I = c.inst[id];
+        const int og = forward ? I.bg : I.fg;
+        if ((forward ? I.bv : I.fv) != start_vid) continue;
+        const bool pos = (I.flags & kPos) != 0;
+        const unsigned weight = (I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp) + 1u;
+        const unsigned obp = forward ? I.bbp : I.fbp;
+        const int step = (forward == pos) ? 1 : -1;
+        int read_lo = 0x7FFFFFFF, read_hi = -1;
+        for (int d0 = 0;; d0 += 16) {
+            const int d = d0 + c.lane + 1;
+            const int g = og + step * d;
+            bool in_range = c.lane < 16 && g >= I.clo && g < I.chi; // it.Valid()
+            int vid = 0, flag = -1;
+            bool used = false, inpath = false;
+            if (in_range) {
+                int2 rc = __ldcg(c.ix.rec + g);
+                vid = pos ? rc.x : -rc.x;
+                long long dp = (long long)(unsigned)rc.y - (long long)obp;
+                if (dp < 0) dp = -dp;
+                in_range = d < c.pr.depth || dp <= c.pr.b;
+                if (in_range) {
+                    bool has = pos || g > I.clo;
+                    flag = has ? (pos ? g : g - 1) : -1;
+                    if (has && !try_used) used = __ldcg(c.E + flag) < c.thresh;
+                    inpath = hash_find(c.hash, c.hmask, vid) != kNotSet;
+                }
+            }
+            const bool ok = in_range && !inpath && !used;
+            const unsigned fail = __ballot_sync(kFull, !ok);
+            const int nok = ffs_lane(fail); // lanes >= 16 always fail, so fail != 0
+            // loop-body executions: the ok steps plus the step that hit `break`
+            const bool stop_in_body = nok < 16 && __shfl_sync(kFull, (int)in_range, nok & 31);
+            c.ct.walk += (unsigned long long)(nok + (stop_in_body ? 1 : 0));
+            // epochs this walk depended on: the ok steps, and the stopping step when it stopped on `used`
+            if (!try_used) {
+                bool dep = flag >= 0 && (c.lane < nok || (c.lane == nok && in_range && !inpath));
+                int lo = dep ? flag : 0x7FFFFFFF, hi = dep ? flag : -1;
+#pragma unroll
+                for (int s = 8; s; s >>= 1) {
+                    lo = min(lo, __shfl_xor_sync(kFull, lo, s));
+                    hi = max(hi, __shfl_xor_sync(kFull, hi, s));
+                }
+                lo = __shfl_sync(kFull, lo, 0), hi = __shfl_sync(kFull, hi, 0);
+                read_lo = min(read_lo, lo), read_hi = max(read_hi, hi);
+            }
+            for (int j = 0; j < nok; j++) { // the vote, in walk order
+                const int cv = __shfl_sync(kFull, vid, j);
+                int slot = -1;
+                for (int base = 0; base < nvote && slot < 0; base += 32) {
+                    int i = base + c.lane;
+                    unsigned m = __ballot_sync(kFull, i < nvote && c.vote[i].x == cv);
+                    if (m) slot = base + ffs_lane(m);
+                }
+                unsigned cnt;
+                if (slot < 0) {
+                    if (nvote >= c.vcap) {
+                        if (c.vcap == kVoteSmem) {
+                            for (int i = c.lane; i < nvote; i += 32) c.ar.vote[i] = c.vote[i];
+                            __syncwarp();
+                            c.vote = c.ar.vote, c.vcap = kVoteMax;
+                        } else {
+                            c.err = LCB_ERR_CAPACITY;
+                            return best;
+                        }
+                    }
+                    slot = nvote++;
+                    cnt = weight;
+                } else {
+                    cnt = (unsigned)c.vote[slot].y + weight;
+                }
+                __syncwarp();
+                if (c.lane == 0) c.vote[slot] = make_int2(cv, (int)cnt);
+                __syncwarp();
+                // origin < ret.origin: (strand, chr, idx), - strand first (junctionstorage.h:349-362)
+                bool less = (pos != best.opos) ? (!pos && best.opos) : (og < best.og);
+                if ((long long)cnt > best_count || ((long long)cnt == best_count && less)) {
+                    best_count = cnt;
+                    best.vid = cv, best.og = og, best.opos = pos, best.d = d0 + j + 1;
+                }
+            }
+            if (nok < 16) break;
+        }
+        if (read_lo <= read_hi && c.lane == 0) inst_extend_reads(c.inst[id], read_lo, read_hi);
+        __syncwarp();
+    }
+    c.vote = c.sm->vote, c.vcap = kVoteSmem;
+    return best;
+}
+
+// ExtendPathForward / ExtendPathBackward (blocksfinder.h:770-895)
+template <bool FORWARD>
+__device__ __noinline__ bool extend_path(Ctx &c, int &best_size, long long &best_score, long long &now_score)
+{
+    Next nx = most_popular_vertex(c, FORWARD, false);
+    if (FORWARD && nx.vid == 0 && !c.err) nx = most_popular_vertex(c, true, true);
+    if (c.err || nx.vid == 0) return false;
+    bool success = false;
+    const int step = (FORWARD == nx.opos) ? 1 : -1;
+    int prev_v = 0;
+    unsigned prev_bp = 0;
+    for (int j0 = 0; j0 <= nx.d; j0 += 32) { // junctions og .. og+step*d, re-read (cache-hot)
+        int j = j0 + c.lane;
+        int2 rc = make_int2(0, 0);
+        if (j <= nx.d) rc = __ldcg(c.ix.rec + (nx.og + step * j));
+        int cnt = min(32, nx.d - j0 + 1);
+        for (int t = 0; t < cnt; t++) {
+            int idv = __shfl_sync(kFull, rc.x, t);
+            unsigned bp = (unsigned)__shfl_sync(kFull, rc.y, t);
+            int v = nx.opos ? idv : -idv;
+            int jj = j0 + t;
+            if (jj > 0) {
+                int len = (int)(bp > prev_bp ? bp - prev_bp : prev_bp - bp);
+                int g_prev = nx.og + step * (jj - 1), g_now = nx.og + step * jj;
+                bool ok = FORWARD ? path_push<true>(c, v, len, g_prev, nx.opos, 0)
+                                  : path_push<false>(c, v, len, g_now, nx.opos, prev_v);
+                if (c.err) return false;
+                success = ok;
+                if (ok) {
+                    now_score = path_score(c);
+                    if (now_score > best_score) {
+                        best_score = now_score;
+                        best_size = (FORWARD ? c.nright : c.nleft) + 1;
+                        if (now_score > 0) {
+                            if (c.ngood > c.icap) { c.err = LCB_ERR_CAPACITY; return false; }
+                            snapshot_best(c);
+                        }
+                    }
+                }
+            }
+            prev_v = v;
+            prev_bp = bp;
+        }
+    }
+    return success;
+}
+
+// ProcessVertex::Process (blocksfinder.h:228-310).  On return c.best[0..nbest) is bestInstance and
+// c.ar.rs[0..nrs) the read-set.
+__device__ __noinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
+{
+    c.hbig = false;
+    c.hash = c.sm->hash;
+    c.hmask = kHashSmem - 1;
+    ctx_reset_storage(c);
+    c.ninst = c.ngood = c.nbest = c.hcount = c.nrs = 0;
+    c.nright = c.nleft = 0;
+    for (int i = c.lane; i < kHashSmem; i += 32) c.hash[i] = make_int2(0, 0);
+    __syncwarp();
+    path_init(c, vid, ch);
+    if (c.err) return;
+    long long best_score = 0, score = 0;
+    int best_right = 1, best_left = 1;
+    const int min_run = c.pr.b * 2;
+    if (c.ninst > 0) { // a seed without live instances cannot move (MostPopularVertex finds nothing)
+        while (true) {
+            bool ret = true, positive = false;
+            int prev_len = c.right_flank - c.left_flank;
+            while ((ret = extend_path<true>(c, best_right, best_score, score)) &&
+                   (c.right_flank - c.left_flank) - prev_len <= min_run)
+                positive = positive || score > 0;
+            if (c.err) return;
+            if (!ret || !positive) break;
+        }
+        const int replay = best_right - 1;
+        path_clear(c);
+        if (c.err) return;
+        path_init(c, vid, ch);
+        for (int i = 0; i < replay && !c.err; i++) {
+            int4 e = c.ar.redge[i];
+            path_push<true>(c, e.x, e.y, e.z, e.w != 0, 0);
+        }
+        if (c.err) return;
+        while (true) {
+            bool ret = true, positive = false;
+            int prev_len = c.right_flank - c.left_flank;
+            while ((ret = extend_path<false>(c, best_left, best_score, score)) &&
+                   (c.right_flank - c.left_flank) - prev_len <= min_run)
+                ;
+            positive = positive || score > 0; // runs once: stray ';' at blocksfinder.h:297
+            if (c.err) return;
+            if (!ret || !positive) break;
+        }
+    }
+    path_clear(c);
+}
+
+} // namespace lcb
