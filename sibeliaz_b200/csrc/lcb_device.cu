@@ -582,7 +582,7 @@ struct lcb_ctx {
     lcb_stats st{};
     int rank = 0, n_ranks = 1;
     std::vector<void *> allocs;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 };
 
 namespace {
@@ -663,6 +663,8 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -706,6 +708,8 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(cudaEventCreate(&ctx->ev2));
+    CUDA_TRY(cudaEventCreate(&ctx->ev3));
     const int64_t N = v->n_records, V = v->n_vertices;
     const int C = v->n_chr;
     auto t0 = std::chrono::steady_clock::now();
@@ -1003,7 +1007,9 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             // B. commit-time conflicts of the freshly evaluated seeds
             k_conflict<<<vgrid, 256, 0, ctx->stream>>>(Ecur, w0, ctx->win.list0, &ctx->d_ctl->n0, ctx->win, ctx->d_ctl);
             // C. commit-time re-runs
+            CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
             if ((rc = launch_traverse(ctx, Ecur, w0, 1, ctx->win.list1, &ctx->d_ctl->n1))) return rc;
+            CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
             // D. new epochs
             CUDA_TRY(cudaMemcpyAsync(Enew, Ebase, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
             k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, w0, n, ctx->win);
@@ -1014,6 +1020,8 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             if ((rc = fetch_control(ctx))) return rc;
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            trav_ms += ms;
+            cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
             trav_ms += ms;
             if (ctx->h_ctl->err) {
                 ctx->error = "a per-seed device buffer overflowed its hard cap (path, instance or read-set too large)";

@@ -160,25 +160,30 @@ __device__ __forceinline__ void hash_clear(Ctx &c)
     c.hcount = 0;
 }
 
+// move the shared-memory path hash into the (all-zero) arena table; returns nothing, caller repoints
+__device__ __noinline__ void hash_migrate(const int2 *src, int2 *dst, int *hslot, int lane)
+{
+    int n = 0;
+    for (int base = 0; base < kHashSmem; base += 32) {
+        int2 kv = src[base + lane];
+        bool live = kv.x != 0;
+        unsigned m = __ballot_sync(kFull, live);
+        if (live) {
+            unsigned s = (hash_of(kv.x) >> 12) & (unsigned)(kHashMax - 1);
+            while (atomicCAS(&dst[s].x, 0, kv.x) != 0) s = (s + 1) & (unsigned)(kHashMax - 1);
+            dst[s].y = kv.y;
+            hslot[n + __popc(m & ((1u << lane) - 1))] = (int)s;
+        }
+        n += __popc(m);
+    }
+    __syncwarp();
+}
+
 // uniform insert (all lanes pass the same key); grows shared -> arena at half load
-__device__ __noinline__ void hash_insert(Ctx &c, int key, int val)
+__device__ __forceinline__ void hash_insert(Ctx &c, int key, int val)
 {
     if (!c.hbig && (c.hcount + 1) * 2 > kHashSmem) {
-        // migrate: arena table is kept all-zero between uses
-        int n = 0;
-        for (int base = 0; base < kHashSmem; base += 32) {
-            int2 kv = c.hash[base + c.lane];
-            bool live = kv.x != 0;
-            unsigned m = __ballot_sync(kFull, live);
-            if (live) {
-                unsigned s = (hash_of(kv.x) >> 12) & (unsigned)(kHashMax - 1);
-                while (atomicCAS(&c.ar.hash[s].x, 0, kv.x) != 0) s = (s + 1) & (unsigned)(kHashMax - 1);
-                c.ar.hash[s].y = kv.y;
-                c.ar.hslot[n + __popc(m & ((1u << c.lane) - 1))] = (int)s;
-            }
-            n += __popc(m);
-        }
-        __syncwarp();
+        hash_migrate(c.hash, c.ar.hash, c.ar.hslot, c.lane);
         c.hash = c.ar.hash;
         c.hmask = kHashMax - 1;
         c.hbig = true;
@@ -214,19 +219,24 @@ __device__ __forceinline__ void inst_extend_reads(Inst &I, int lo, int hi) // si
 }
 
 // spill the instance tables from shared memory to the arena
-__device__ __noinline__ void inst_grow(Ctx &c)
+__device__ __noinline__ void inst_spill(const WarpSmem *sm, WarpArena ar, int ninst, int ngood, int nbest, int lane)
+{
+    for (int i = lane; i < ninst; i += 32) {
+        ar.inst[i] = sm->inst[i];
+        ar.ord[i] = sm->ord[i];
+    }
+    for (int i = lane; i < ngood; i += 32) ar.good[i] = sm->good[i];
+    for (int i = lane; i < nbest; i += 32) ar.best[i] = sm->best[i];
+    __syncwarp();
+}
+
+__device__ __forceinline__ void inst_grow(Ctx &c)
 {
     if (c.icap != kInstSmem) {
         c.err = LCB_ERR_CAPACITY;
         return;
     }
-    for (int i = c.lane; i < c.ninst; i += 32) {
-        c.ar.inst[i] = c.inst[i];
-        c.ar.ord[i] = c.ord[i];
-    }
-    for (int i = c.lane; i < c.ngood; i += 32) c.ar.good[i] = c.good[i];
-    for (int i = c.lane; i < c.nbest; i += 32) c.ar.best[i] = c.best[i];
-    __syncwarp();
+    inst_spill(c.sm, c.ar, c.ninst, c.ngood, c.nbest, c.lane);
     c.inst = c.ar.inst;
     c.ord = c.ar.ord;
     c.good = c.ar.good;
@@ -247,7 +257,7 @@ __device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
 }
 
 // Instance(it, distance) + multiset insert + allInstance_.push_back   (path.h:82-91, :43, :492, :561)
-__device__ __noinline__ void inst_insert(Ctx &c, int at, int g, bool pos, int v, unsigned bp, int dist, int flag_idx,
+__device__ __forceinline__ void inst_insert(Ctx &c, int at, int g, bool pos, int v, unsigned bp, int dist, int flag_idx,
                                          int clo, int chi)
 {
     if (c.ninst >= c.icap) {
@@ -283,7 +293,7 @@ __device__ __noinline__ void inst_insert(Ctx &c, int at, int g, bool pos, int v,
 }
 
 // Path::Clear (path.h:650-677): also flushes the per-instance read extents into the read-set log
-__device__ __noinline__ void path_clear(Ctx &c)
+__device__ __forceinline__ void path_clear(Ctx &c)
 {
     for (int base = 0; base < c.ninst; base += 32) {
         int i = base + c.lane;
@@ -340,12 +350,12 @@ __device__ __forceinline__ Occ load_occurrence(const Ctx &c, unsigned o, int ver
     chr_bounds(c.ix, r.g, r.clo, r.chi);
     bool has = r.pos || r.g > r.clo; // IsUsed on the - strand at idx 0 is false (junctionstorage.h:277-282)
     r.flag = has ? (r.pos ? r.g : r.g - 1) : -1;
-    r.used = has ? (__ldcg(c.E + r.flag) < c.thresh) : false;
+    r.used = has ? (__ldg(c.E + r.flag) < c.thresh) : false;
     return r;
 }
 
 // Path::Init (path.h:33-46)
-__device__ __noinline__ void path_init(Ctx &c, int vid, unsigned char ch)
+__device__ __forceinline__ void path_init(Ctx &c, int vid, unsigned char ch)
 {
     c.origin = c.right_vertex = c.left_vertex = vid;
     c.right_flank = c.left_flank = 0;
@@ -388,7 +398,7 @@ __device__ __forceinline__ bool scan_used(Ctx &c, int lo, int hi)
     bool any = false;
     for (int base = lo; base <= hi && !any; base += 32) {
         int f = base + c.lane;
-        bool u = f <= hi && __ldcg(c.E + f) < c.thresh;
+        bool u = f <= hi && __ldg(c.E + f) < c.thresh;
         any = __any_sync(kFull, u);
     }
     c.ct.scan += (unsigned long long)(hi - lo + 1);
@@ -398,8 +408,7 @@ __device__ __forceinline__ bool scan_used(Ctx &c, int lo, int hi)
 // Path::PointPushBack / PointPushFront with their workers (path.h:430-602).  BACK: `v` = e.GetEndVertex(),
 // FRONT: `v` = e.GetStartVertex().  e_ch_g/e_ch_pos locate the junction whose char is e.GetChar();
 // e_other is e.GetEndVertex() for FRONT (the far-branch test `start1.GetVertexId() != e.GetEndVertex()`).
-template <bool BACK>
-__device__ __noinline__ bool path_push(Ctx &c, int v, int len, int e_ch_g, bool e_ch_pos, int e_other)
+__device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int len, int e_ch_g, bool e_ch_pos, int e_other)
 {
     if (hash_find(c.hash, c.hmask, v) != kNotSet) return false; // vertex already in the path
     const int dist = BACK ? c.right_flank + len : c.left_flank - len;
@@ -564,7 +573,7 @@ struct Next { // result of MostPopularVertex
 
 // BlocksFinder::MostPopularVertex (blocksfinder.h:708-768).  Lanes = look-ahead depths of one instance;
 // the vote itself is replayed in reference order (running arg-max with the origin tie-break).
-__device__ __noinline__ Next most_popular_vertex(Ctx &c, bool forward, bool try_used)
+__device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool try_used)
 {
     Next best;
     best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
@@ -590,7 +599,7 @@ __device__ __noinline__ Next most_popular_vertex(Ctx &c, bool forward, bool try_
             int vid = 0, flag = -1;
             bool used = false, inpath = false;
             if (in_range) {
-                int2 rc = __ldcg(c.ix.rec + g);
+                int2 rc = __ldg(c.ix.rec + g);
                 vid = pos ? rc.x : -rc.x;
                 long long dp = (long long)(unsigned)rc.y - (long long)obp;
                 if (dp < 0) dp = -dp;
@@ -598,7 +607,7 @@ __device__ __noinline__ Next most_popular_vertex(Ctx &c, bool forward, bool try_
                 if (in_range) {
                     bool has = pos || g > I.clo;
                     flag = has ? (pos ? g : g - 1) : -1;
-                    if (has && !try_used) used = __ldcg(c.E + flag) < c.thresh;
+                    if (has && !try_used) used = __ldg(c.E + flag) < c.thresh;
                     inpath = hash_find(c.hash, c.hmask, vid) != kNotSet;
                 }
             }
@@ -665,11 +674,14 @@ __device__ __noinline__ Next most_popular_vertex(Ctx &c, bool forward, bool try_
 }
 
 // ExtendPathForward / ExtendPathBackward (blocksfinder.h:770-895)
-template <bool FORWARD>
-__device__ __noinline__ bool extend_path(Ctx &c, int &best_size, long long &best_score, long long &now_score)
+__device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &best_size, long long &best_score, long long &now_score)
 {
-    Next nx = most_popular_vertex(c, FORWARD, false);
-    if (FORWARD && nx.vid == 0 && !c.err) nx = most_popular_vertex(c, true, true);
+    Next nx;
+    nx.vid = 0;
+    for (int attempt = 0; attempt < 2 && nx.vid == 0 && !c.err; attempt++) { // forward retries with tryUsed (:782-785)
+        if (attempt == 1 && !FORWARD) break;
+        nx = most_popular_vertex(c, FORWARD, attempt == 1);
+    }
     if (c.err || nx.vid == 0) return false;
     bool success = false;
     const int step = (FORWARD == nx.opos) ? 1 : -1;
@@ -678,7 +690,7 @@ __device__ __noinline__ bool extend_path(Ctx &c, int &best_size, long long &best
     for (int j0 = 0; j0 <= nx.d; j0 += 32) { // junctions og .. og+step*d, re-read (cache-hot)
         int j = j0 + c.lane;
         int2 rc = make_int2(0, 0);
-        if (j <= nx.d) rc = __ldcg(c.ix.rec + (nx.og + step * j));
+        if (j <= nx.d) rc = __ldg(c.ix.rec + (nx.og + step * j));
         int cnt = min(32, nx.d - j0 + 1);
         for (int t = 0; t < cnt; t++) {
             int idv = __shfl_sync(kFull, rc.x, t);
@@ -688,8 +700,7 @@ __device__ __noinline__ bool extend_path(Ctx &c, int &best_size, long long &best
             if (jj > 0) {
                 int len = (int)(bp > prev_bp ? bp - prev_bp : prev_bp - bp);
                 int g_prev = nx.og + step * (jj - 1), g_now = nx.og + step * jj;
-                bool ok = FORWARD ? path_push<true>(c, v, len, g_prev, nx.opos, 0)
-                                  : path_push<false>(c, v, len, g_now, nx.opos, prev_v);
+                bool ok = path_push(c, FORWARD, v, len, FORWARD ? g_prev : g_now, nx.opos, prev_v);
                 if (c.err) return false;
                 success = ok;
                 if (ok) {
@@ -697,10 +708,7 @@ __device__ __noinline__ bool extend_path(Ctx &c, int &best_size, long long &best
                     if (now_score > best_score) {
                         best_score = now_score;
                         best_size = (FORWARD ? c.nright : c.nleft) + 1;
-                        if (now_score > 0) {
-                            if (c.ngood > c.icap) { c.err = LCB_ERR_CAPACITY; return false; }
-                            snapshot_best(c);
-                        }
+                        if (now_score > 0) snapshot_best(c);
                     }
                 }
             }
@@ -713,7 +721,7 @@ __device__ __noinline__ bool extend_path(Ctx &c, int &best_size, long long &best
 
 // ProcessVertex::Process (blocksfinder.h:228-310).  On return c.best[0..nbest) is bestInstance and
 // c.ar.rs[0..nrs) the read-set.
-__device__ __noinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
+__device__ __forceinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
 {
     c.hbig = false;
     c.hash = c.sm->hash;
@@ -723,37 +731,33 @@ __device__ __noinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
     c.nright = c.nleft = 0;
     for (int i = c.lane; i < kHashSmem; i += 32) c.hash[i] = make_int2(0, 0);
     __syncwarp();
-    path_init(c, vid, ch);
-    if (c.err) return;
     long long best_score = 0, score = 0;
-    int best_right = 1, best_left = 1;
+    int best_size[2] = {1, 1}; // bestLeftSize, bestRightSize
     const int min_run = c.pr.b * 2;
-    if (c.ninst > 0) { // a seed without live instances cannot move (MostPopularVertex finds nothing)
-        while (true) {
-            bool ret = true, positive = false;
-            int prev_len = c.right_flank - c.left_flank;
-            while ((ret = extend_path<true>(c, best_right, best_score, score)) &&
-                   (c.right_flank - c.left_flank) - prev_len <= min_run)
-                positive = positive || score > 0;
+    for (int phase = 1; phase >= 0; phase--) { // 1: forward, 0: backward
+        const bool forward = phase == 1;
+        int replay = 0;
+        if (!forward) {
+            replay = best_size[1] - 1;
+            path_clear(c);
             if (c.err) return;
-            if (!ret || !positive) break;
         }
-        const int replay = best_right - 1;
-        path_clear(c);
-        if (c.err) return;
         path_init(c, vid, ch);
-        for (int i = 0; i < replay && !c.err; i++) {
+        if (c.err) return;
+        if (c.ninst == 0) break; // a seed without live instances cannot move (MostPopularVertex finds nothing)
+        for (int i = 0; i < replay && !c.err; i++) { // re-play the best right part (blocksfinder.h:271-284)
             int4 e = c.ar.redge[i];
-            path_push<true>(c, e.x, e.y, e.z, e.w != 0, 0);
+            path_push(c, true, e.x, e.y, e.z, e.w != 0, 0);
         }
         if (c.err) return;
         while (true) {
             bool ret = true, positive = false;
-            int prev_len = c.right_flank - c.left_flank;
-            while ((ret = extend_path<false>(c, best_left, best_score, score)) &&
-                   (c.right_flank - c.left_flank) - prev_len <= min_run)
-                ;
-            positive = positive || score > 0; // runs once: stray ';' at blocksfinder.h:297
+            const int prev_len = c.right_flank - c.left_flank;
+            while ((ret = extend_path(c, forward, best_size[phase], best_score, score)) &&
+                   (c.right_flank - c.left_flank) - prev_len <= min_run) {
+                if (forward) positive = positive || score > 0; // backward: empty body, stray ';' at blocksfinder.h:297
+            }
+            if (!forward) positive = positive || score > 0;
             if (c.err) return;
             if (!ret || !positive) break;
         }

@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""Developer timing helper: generate a star synthetic, build its junction file with the reference twopaco,
+run the product (and optionally the oracle / the compiled reference) and print stats.  Not a test."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genomes", type=int, default=4)
+    ap.add_argument("--length", type=int, default=10000000)
+    ap.add_argument("--k", type=int, default=21)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--kind", default="star")
+    ap.add_argument("--rate", type=float, default=0.05)
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--wmax", type=int, default=0)
+    ap.add_argument("--oracle", action="store_true")
+    ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--dir", default="/tmp/lcb_time")
+    a = ap.parse_args()
+    import numpy as np
+    import sibeliaz_b200 as sb
+    from oracle_binding import Oracle, run_reference_lcb, run_twopaco
+    from tools.gen_synthetic import generate
+    d = os.path.join(a.dir, "%s_%dx%d_k%d_s%d" % (a.kind, a.genomes, a.length, a.k, a.seed))
+    os.makedirs(d, exist_ok=True)
+    dbg = os.path.join(d, "g.dbg")
+    t = time.time()
+    fas = generate(d, a.kind, a.genomes, a.length, a.rate, a.seed)
+    if not os.path.exists(dbg):
+        run_twopaco(fas, a.k, dbg, threads=min(16, os.cpu_count() or 1))
+    print("input ready in %.1fs" % (time.time() - t), flush=True)
+    t = time.time()
+    st = sb.JunctionStorage(dbg, fas, a.k, 150)
+    print("load %.2fs  records %d vertices %d" % (time.time() - t, st.n_records, st.n_vertices), flush=True)
+    for rep in range(a.reps):
+        bf = sb.BlocksFinder(st, a.k, window_init=a.window, window_max=a.wmax or a.window, collect_counters=True)
+        t = time.time()
+        bf.create(50, 200)
+        t_create = time.time() - t
+        t = time.time()
+        bf.enumerate_seeds()
+        t_enum = time.time() - t
+        t = time.time()
+        blocks = bf.find_blocks(50, 200)
+        t_find = time.time() - t
+        s = bf.stats
+        print(json.dumps(dict(rep=rep, create_s=round(t_create, 3), enum_s=round(t_enum, 3), find_s=round(t_find, 3),
+                              jps=round(st.n_records / (t_enum + t_find)), **{k: (round(v, 2) if isinstance(v, float) else v) for k, v in s.items()})), flush=True)
+        bf.close()
+    if a.oracle:
+        t = time.time()
+        orc = Oracle(dbg, fas, a.k, 150)
+        ob = orc.find_blocks(50, 200)
+        print("oracle %.2fs" % (time.time() - t), orc.counters)
+        ok = len(ob["id"]) == len(blocks) and np.array_equal(ob["id"], blocks["id"]) and np.array_equal(ob["start"], blocks["start"].astype(np.uint64)) \
+            and np.array_equal(ob["end"], blocks["end"].astype(np.uint64)) and np.array_equal(ob["chr"], blocks["chr"])
+        print("PARITY", ok, len(ob["id"]), len(blocks))
+    if a.ref:
+        out = os.path.join(d, "refout")
+        os.makedirs(out, exist_ok=True)
+        for th in (1, min(32, os.cpu_count() or 1)):
+            t = time.time()
+            run_reference_lcb(dbg, fas, a.k, out, threads=th)
+            print("reference -t %d total %.2fs" % (th, time.time() - t), flush=True)
+
+
+if __name__ == "__main__":
+    main()
