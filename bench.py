@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""bench.py -- junctions traversed/sec of the sibeliaz-lcb hot loop (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps K ...   # the reference's own CPU path (oracle/_ref)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the FindBlocks equivalent (seed enumeration + sort + carving-path traversal +
+ordered commit; blocksfinder.h:453-530) over the workload, J/s = kept junction records / step time.
+Workload = BASELINE configs[1]: synthetic 4 x 10 Mbp star phylogeny (0.05 subs/site, seed 1), k=21,
+-b 200 -m 50 -a 150 (inputs: tools/gen_synthetic.py, junction file by the reference twopaco).
+
+  value      step timed with CUDA events on the library's stream, index already resident in HBM
+  e2e        the same through the C ABI from HOST arrays: lcb_create (pinned staging + H2D) + enumerate +
+             find_blocks (+ D2H of the block instances) + lcb_destroy, every step
+  roofline   k_traverse: algorithmic bytes (13*T_walk + 17*T_occ + T_scan + 32*T_score, step counts from the
+             oracle on this workload) / summed CUDA-event time of its launches, vs the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  oracle/_ref/sibeliaz-lcb-ref (the unmodified reference) on this box's host cores
+
+Only the cpu_baseline / --impl reference legs and the one-off parity check touch oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "junctions traversed/sec (sibeliaz-lcb hot loop)"
+UNIT = "junctions/s"
+WORKLOADS = {
+    # name: (kind, genomes, length, rate, seed, k)
+    "star4x10M_k21": ("star", 4, 10_000_000, 0.05, 1, 21),
+    "star4x1M_k21": ("star", 4, 1_000_000, 0.05, 1, 21),
+    "star4x100M_k25": ("star", 4, 100_000_000, 0.05, 1, 25),
+}
+B, M, A = 200, 50, 150
+
+
+def prepare_workload(name, rank):
+    """FASTA + junction file, cached under /tmp; rank 0 builds, others wait."""
+    from tools.gen_synthetic import generate
+    from oracle_binding import REF_TWOPACO, run_twopaco
+    kind, g, length, rate, seed, k = WORKLOADS[name]
+    d = os.path.join(os.environ.get("LCB_BENCH_DIR", "/tmp/sibeliaz_b200_bench"), name)
+    dbg, done = os.path.join(d, "g.dbg"), os.path.join(d, ".done")
+    fas = [os.path.join(d, "g%d.fa" % i) for i in range(g)]
+    if rank == 0 and not os.path.exists(done):
+        os.makedirs(d, exist_ok=True)
+        generate(d, kind, g, length, rate, seed)
+        if not os.path.exists(REF_TWOPACO):
+            raise RuntimeError("oracle/_ref/twopaco (input producer, built by __graft_entry__.build()) is missing")
+        run_twopaco(fas, k, dbg, threads=min(16, os.cpu_count() or 1))
+        open(done, "w").close()
+    while not os.path.exists(done):
+        time.sleep(0.2)
+    return dbg, fas, k
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def time_reference(dbg, fas, k, threads):
+    """Runs oracle/_ref/sibeliaz-lcb-ref and returns (t_find_s, t_total_s): FindBlocks is the span between the
+    reference's own 'Analyzing the graph...' and 'Generating the output...' stdout lines (sibeliaz.cpp:133,142)."""
+    from oracle_binding import REF_LCB
+    out = os.path.join(os.path.dirname(dbg), "ref_out")
+    os.makedirs(out, exist_ok=True)
+    cmd = [REF_LCB, "--graph", dbg] + fas + ["-k", str(k), "-b", str(B), "-o", out, "-m", str(M), "-t", str(threads), "--abundance", str(A), "--noseq"]
+    t0 = time.perf_counter()
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, bufsize=0)
+    marks, buf = {}, b""
+    while True:
+        c = p.stdout.read(1)
+        if not c:
+            break
+        buf += c
+        if c == b"\n":
+            line = buf.decode(errors="replace")
+            buf = b""
+            for key in ("Analyzing the graph", "Generating the output"):
+                if key in line and key not in marks:
+                    marks[key] = time.perf_counter()
+    p.wait()
+    t1 = time.perf_counter()
+    if p.returncode or len(marks) < 2:
+        raise RuntimeError("reference sibeliaz-lcb failed")
+    return marks["Generating the output"] - marks["Analyzing the graph"], t1 - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="star4x10M_k21", choices=sorted(WORKLOADS))
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    host_threads = min(32, os.cpu_count() or 1)  # the sibeliaz wrapper caps sibeliaz-lcb at 32 threads (sibeliaz:139)
+    config = {"workload": "synthetic star 4x10 Mbp, 0.05 subs/site, seed 1, k=21, -b 200 -m 50 -a 150 (BASELINE configs[1])"
+              if a.workload == "star4x10M_k21" else a.workload, "name": a.workload,
+              "l2_policy": "index + epochs + per-seed state are re-created/re-written every step and the traversal is a dependent "
+                           "random walk; no L2 flush is issued between steps (working set 35 MB < L2: cache-resident by nature)"}
+
+    # ------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        dbg, fas, k = prepare_workload(a.workload, 0)
+        import sibeliaz_b200 as sb
+        n_records = sb.JunctionStorage(dbg, fas, k, A).n_records
+        for _ in range(min(warmup, 1)):
+            time_reference(dbg, fas, k, host_threads)
+        t_find = 0.0
+        for _ in range(steps):
+            t_find += time_reference(dbg, fas, k, host_threads)[0]
+        value = steps * n_records / t_find
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": min(warmup, 1),
+                "ms_per_step": 1000.0 * t_find / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads, "kind": "reference",
+                                 "sample": "whole workload per step: unmodified reference sibeliaz-lcb -t %d, FindBlocks span" % host_threads},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import numpy as np
+    import torch
+    import sibeliaz_b200 as sb
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dbg, fas, k = prepare_workload(a.workload, rank)
+    storage = sb.JunctionStorage(dbg, fas, k, A)
+    n_records = storage.n_records
+    win = dict(window_init=a.window, window_max=a.window) if a.window else {}
+
+    def make_finder(collect=False):
+        bf = sb.BlocksFinder(storage, k, device=local_rank, collect_counters=collect, **win)
+        bf.create(M, B)
+        if world > 1:
+            idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                import ctypes
+                buf = ctypes.create_string_buffer(128)
+                sb.load_library().lcb_comm_unique_id(buf)
+                idb = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+            dist.broadcast(idb, 0)
+            bf.comm_init(rank, world, bytes(idb.cpu().tolist()))
+        return bf
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # one-off parity check against the oracle (the checker), which also yields the algorithmic step counts
+    parity, alg_bytes, counters = None, None, None
+    bf = make_finder()
+    blocks = bf.find_blocks(M, B)
+    if rank == 0:
+        from oracle_binding import Oracle
+        orc = Oracle(dbg, fas, k, A)
+        ob = orc.find_blocks(M, B)
+        parity = bool(len(ob["id"]) == len(blocks) and np.array_equal(ob["id"], blocks["id"]) and np.array_equal(ob["chr"], blocks["chr"])
+                      and np.array_equal(ob["start"], blocks["start"].astype(np.uint64)) and np.array_equal(ob["end"], blocks["end"].astype(np.uint64)))
+        counters = orc.counters
+        alg_bytes = 13 * counters["t_walk"] + 17 * counters["t_occ"] + counters["t_scan"] + 32 * counters["t_score"]
+        orc.close()
+
+    # ---- value: index resident in HBM, whole FindBlocks equivalent per step, device-timed
+    for _ in range(warmup):
+        bf.reset_seeds()
+        bf.find_blocks(M, B)
+    sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms, trav_ms, trav_launches, launches = [], 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        bf.reset_seeds()
+        bf.find_blocks(M, B)
+        step_ms.append(bf.stats["ms_step_device"])
+        trav_ms += bf.stats["ms_traverse_kernels"]
+        trav_launches += bf.stats["traverse_launches"]
+        launches += bf.stats["kernel_launches"]
+    sync()
+    wall_ms = 1000.0 * (time.perf_counter() - t0)
+    clocks = sampler.summary()
+    dev_ms = float(sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = t.tolist()
+    total_records = n_records * steps  # every rank works on the same junction set; the seeds are what is sharded
+    value = total_records / (dev_ms / 1000.0)
+    stats = dict(bf.stats)
+    bf.close()
+
+    # ---- e2e: host arrays -> lcb_create (H2D) -> enumerate -> find (D2H) -> destroy, every step
+    e2e_t, h2d, d2h = 0.0, 0, 0
+    for it in range(1 + steps):
+        sync()
+        t0 = time.perf_counter()
+        f = make_finder()
+        blk = f.find_blocks(M, B)
+        h2d, d2h = f.stats["h2d_bytes"], f.stats["d2h_bytes"]
+        f.close()
+        sync()
+        if it > 0:
+            e2e_t += time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = t.item()
+    e2e_value = total_records / e2e_t
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = (alg_bytes * steps / 1e9) / (trav_ms / 1000.0) if trav_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_traverse", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_step": alg_bytes, "launches_per_step": trav_launches / steps,
+                "kernel_ms_per_step": trav_ms / steps, "kernel_share_of_step": trav_ms / dev_ms if dev_ms else None,
+                "note": "latency-bound dependent random walk: see DESIGN.md section 5"}
+    cpu = None
+    if not a.no_cpu_baseline:
+        try:
+            tf, tt = time_reference(dbg, fas, k, host_threads)
+            cpu = {"value": n_records / tf, "unit": UNIT, "cores": host_threads, "kind": "reference",
+                   "sample": "whole workload once: unmodified reference sibeliaz-lcb -t %d; FindBlocks span %.3f s, whole binary %.3f s" % (host_threads, tf, tt)}
+        except Exception as e:  # the baseline is reported, never required for the GPU numbers
+            cpu = {"value": None, "unit": UNIT, "cores": host_threads, "kind": "reference", "sample": "failed: %s" % e}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/uint32",
+            "data": "synthetic", "config": config, "parity_vs_oracle": parity,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1000.0 * e2e_t / steps},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "detail": {"records": int(n_records), "seeds": int(stats["n_seeds"]), "block_instances": int(stats["n_block_instances"]),
+                       "windows": int(stats["windows"]), "rounds": int(stats["rounds"]), "traversals": int(stats["traversals_first"] + stats["traversals_rerun"]),
+                       "wall_ms_per_step": wall_ms / steps, "ms_enumerate": stats["ms_enumerate"], "oracle_counters": counters}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

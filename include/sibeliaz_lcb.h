@@ -102,6 +102,8 @@ typedef struct lcb_stats {
     double ms_traverse_kernels;            /* sum of CUDA-event durations of the traversal kernel */
     uint64_t traverse_launches;
     double ms_h2d, ms_d2h;                 /* index upload / result download                      */
+    double ms_step_device;                 /* CUDA-event time from the start of seed enumeration to the end of
+                                              find_blocks on the library's stream (when find_blocks enumerates)  */
     uint64_t h2d_bytes, d2h_bytes;
 } lcb_stats;
 
@@ -122,6 +124,10 @@ int lcb_enumerate_seeds(lcb_ctx *, uint64_t *n_seeds);
 int lcb_get_seeds(lcb_ctx *, int64_t *vid, uint8_t *ch, uint64_t *count, uint64_t *rank, uint64_t *res_pos,
                   uint64_t *res_chr);
 
+/* Forget the enumerated seeds so that the next lcb_find_blocks repeats the whole FindBlocks equivalent
+ * (enumeration + sort + traversal + commit) on the resident index; used to time repeated passes. */
+int lcb_reset_seeds(lcb_ctx *);
+
 /* Traversal + ordered commit (blocksfinder.h:228-433).  *out is library-owned until lcb_free_blocks;
  * records are in the reference's commit order (that order feeds the output stage's unstable sorts). */
 int lcb_find_blocks(lcb_ctx *, lcb_block_instance **out, uint64_t *n, lcb_stats *stats);
@@ -137,6 +143,9 @@ void lcb_destroy(lcb_ctx *);
 int lcb_write_output(const lcb_index *, const lcb_block_instance *blocks, uint64_t n, int min_block,
                      const char *out_dir, int gen_seq, int chunks, int64_t *blocks_found, double *coverage,
                      char *err, size_t errlen);
+
+/* Returns the process-wide cache of device scratch / pinned staging blocks to the driver. */
+void lcb_trim_cache(void);
 
 const char *lcb_version(void);
 

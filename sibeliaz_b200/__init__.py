@@ -24,7 +24,7 @@ LCB_OK = 0
 ERR_NAMES = {1: "LCB_ERR_ARG", 2: "LCB_ERR_IO", 3: "LCB_ERR_FORMAT", 4: "LCB_ERR_CUDA", 5: "LCB_ERR_CAPACITY",
              6: "LCB_ERR_STATE"}
 
-EXPORTS = ["lcb_index_load", "lcb_index_get_view", "lcb_index_num_chr", "lcb_index_chr_name", "lcb_index_chr_length",
+EXPORTS = ["lcb_trim_cache", "lcb_reset_seeds", "lcb_index_load", "lcb_index_get_view", "lcb_index_num_chr", "lcb_index_chr_name", "lcb_index_chr_length",
            "lcb_index_free", "lcb_default_params", "lcb_create", "lcb_comm_unique_id", "lcb_comm_init",
            "lcb_enumerate_seeds", "lcb_get_seeds", "lcb_find_blocks", "lcb_free_blocks", "lcb_get_stats",
            "lcb_last_error", "lcb_destroy", "lcb_write_output", "lcb_version"]
@@ -60,8 +60,9 @@ class Stats(C.Structure):
                                           "rounds", "traversals_first", "traversals_rerun", "kernel_launches", "t_walk",
                                           "t_occ", "t_scan", "t_score")] + \
                [("ms_enumerate", C.c_double), ("ms_find", C.c_double), ("ms_traverse_kernels", C.c_double),
-                ("traverse_launches", C.c_uint64), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
+                ("traverse_launches", C.c_uint64), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("ms_step_device", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+    # keep in sync with lcb_stats in include/sibeliaz_lcb.h (ms_step_device sits right after ms_d2h)
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -97,6 +98,7 @@ def load_library(path=None):
     lib.lcb_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.lcb_enumerate_seeds.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.lcb_get_seeds.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    lib.lcb_reset_seeds.argtypes = [C.c_void_p]
     lib.lcb_find_blocks.argtypes = [C.c_void_p, C.POINTER(C.POINTER(BlockInstance)), C.POINTER(C.c_uint64), C.POINTER(Stats)]
     lib.lcb_free_blocks.argtypes = [C.POINTER(BlockInstance)]
     lib.lcb_free_blocks.restype = None
@@ -278,6 +280,9 @@ class BlocksFinder:
         self._lib.lcb_free_blocks(ptr)
         self.stats = st.as_dict()
         return self.blocks
+
+    def reset_seeds(self):
+        self._check(self._lib.lcb_reset_seeds(self._ctx))
 
     def generate_output(self, out_dir, gen_seq=False, chunks=0, min_block=None):
         if self.blocks is None:

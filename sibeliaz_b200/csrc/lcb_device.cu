@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -581,18 +582,64 @@ struct lcb_ctx {
     lcb_block_instance *d_out = nullptr;
     lcb_stats st{};
     int rank = 0, n_ranks = 1;
-    std::vector<void *> allocs;
+    std::vector<void *> allocs, seed_allocs;
+    std::vector<size_t> alloc_bytes, seed_alloc_bytes;
+    bool arena_dirty = false;
+    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
+    bool step_timed = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 };
 
 namespace {
 
+// Process-wide cache of device / pinned blocks: contexts are created and destroyed per call by hosts that hand
+// over HOST arrays each time (bench.py's e2e leg, the CLI), and cudaMalloc/cudaFree of multi-GB scratch would
+// otherwise dominate.  Blocks return to the cache in lcb_destroy and are really freed by lcb_trim_cache().
+struct CachedBlock {
+    void *p;
+    size_t bytes;
+    int device;   // -1: pinned host memory
+    bool zeroed;  // arena invariant: every traversal leaves its spill hash all-zero
+};
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+
+cudaError_t cached_alloc(void **p, size_t bytes, int device, bool *was_cached)
+{
+    bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_cache.size(); i++)
+            if (g_cache[i].device == device && g_cache[i].bytes >= bytes && g_cache[i].bytes <= bytes + bytes / 4 + 4096 &&
+                (best < 0 || g_cache[i].bytes < g_cache[(size_t)best].bytes))
+                best = (int)i;
+        if (best >= 0) {
+            *p = g_cache[(size_t)best].p;
+            g_cache.erase(g_cache.begin() + best);
+            if (was_cached) *was_cached = true;
+            return cudaSuccess;
+        }
+    }
+    if (was_cached) *was_cached = false;
+    return device < 0 ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes);
+}
+
+void cached_free(void *p, size_t bytes, int device)
+{
+    bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache.push_back(CachedBlock{p, bytes, device, false});
+}
+
 template <typename T>
-int dev_alloc(lcb_ctx *ctx, T **p, size_t n)
+int dev_alloc(lcb_ctx *ctx, T **p, size_t n, bool *was_cached = nullptr)
 {
     void *q = nullptr;
-    CUDA_TRY(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CUDA_TRY(cached_alloc(&q, bytes, ctx->device, was_cached));
     ctx->allocs.push_back(q);
+    ctx->alloc_bytes.push_back(bytes);
     *p = (T *)q;
     return LCB_OK;
 }
@@ -647,8 +694,8 @@ extern "C" void lcb_default_params(lcb_params *p)
     p->max_flank = 200;
     p->looking_depth = 8;
     p->phase_size = 256;
-    p->window_init = 4096;
-    p->window_max = 32768;
+    p->window_init = 16384;
+    p->window_max = 131072;
     p->device = 0;
     p->collect_counters = 0;
 }
@@ -659,8 +706,15 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (void *p : ctx->allocs) cudaFree(p);
-    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 0; i < ctx->allocs.size(); i++) {
+        if (ctx->allocs[i] == (void *)ctx->d_arena && ctx->arena_dirty) cudaFree(ctx->allocs[i]); // invariant broken: do not recycle
+        else cached_free(ctx->allocs[i], ctx->alloc_bytes[i], ctx->device);
+    }
+    for (size_t i = 0; i < ctx->seed_allocs.size(); i++) cached_free(ctx->seed_allocs[i], ctx->seed_alloc_bytes[i], ctx->device);
+    if (ctx->ev_step0) cudaEventDestroy(ctx->ev_step0);
+    if (ctx->ev_step1) cudaEventDestroy(ctx->ev_step1);
+    if (ctx->h_ctl) cached_free(ctx->h_ctl, sizeof(Control), -1);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -678,9 +732,9 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     lcb_params &p = ctx->prm;
     if (p.phase_size <= 0) p.phase_size = 256;
     if (p.looking_depth <= 0) p.looking_depth = 8;
-    if (p.window_init <= 0) p.window_init = 4096;
-    if (p.window_max <= 0) p.window_max = 32768;
-    p.window_max = std::min(p.window_max, 65536);
+    if (p.window_init <= 0) p.window_init = 16384;
+    if (p.window_max <= 0) p.window_max = 131072;
+    p.window_max = std::min(p.window_max, 1 << 20);
     p.window_max = std::max(p.phase_size, p.window_max / p.phase_size * p.phase_size);
     p.window_init = std::max(p.phase_size, std::min(p.window_init, p.window_max) / p.phase_size * p.phase_size);
     if (v->n_records < 0 || v->n_records >= (int64_t)0x7FFFFFF0 || v->n_vertices >= (int64_t)0x3FFFFFF0 || v->n_chr < 0) {
@@ -708,6 +762,8 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_step0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev_step1));
     CUDA_TRY(cudaEventCreate(&ctx->ev2));
     CUDA_TRY(cudaEventCreate(&ctx->ev3));
     const int64_t N = v->n_records, V = v->n_vertices;
@@ -715,16 +771,30 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     auto t0 = std::chrono::steady_clock::now();
     // ---- pack + upload the index (8 B + 2 B per record, u32 CSR) ----
     {
-        std::vector<int2> rec((size_t)N);
-        std::vector<uchar2> chs((size_t)N);
+        // packed into ONE pinned staging buffer so the copies are true async DMA from page-locked memory
+        const size_t b_rec = sizeof(int2) * (size_t)N, b_chs = sizeof(uchar2) * (size_t)N, b_vo = sizeof(uint32_t) * ((size_t)V + 2),
+                     b_oc = sizeof(uint32_t) * (size_t)N, b_co = sizeof(uint32_t) * ((size_t)C + 1);
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        unsigned char *stage = nullptr;
+        const size_t stage_bytes = up(b_rec) + up(b_chs) + up(b_vo) + up(b_oc) + up(b_co) + 256;
+        CUDA_TRY(cached_alloc((void **)&stage, stage_bytes, -1, nullptr));
+        struct Unpin {
+            unsigned char *p;
+            size_t n;
+            ~Unpin() { cached_free(p, n, -1); }
+        } unpin{stage, stage_bytes};
+        int2 *rec = (int2 *)stage;
+        uchar2 *chs = (uchar2 *)(stage + up(b_rec));
+        uint32_t *vo = (uint32_t *)((unsigned char *)chs + up(b_chs));
+        uint32_t *oc = (uint32_t *)((unsigned char *)vo + up(b_vo));
+        uint32_t *co = (uint32_t *)((unsigned char *)oc + up(b_oc));
         for (int64_t g = 0; g < N; g++) {
             rec[(size_t)g] = make_int2(v->pos_id[g], (int)v->pos_bp[g]);
             chs[(size_t)g] = make_uchar2(v->next_ch[g], v->prev_rc[g]);
+            oc[(size_t)g] = (uint32_t)v->occ_g[g];
         }
-        std::vector<uint32_t> vo((size_t)V + 2, 0), oc((size_t)N), co((size_t)C + 1);
         for (int64_t i = 0; i <= V; i++) vo[(size_t)i] = (uint32_t)v->vtx_off[i];
         vo[(size_t)V + 1] = vo[(size_t)V];
-        for (int64_t i = 0; i < N; i++) oc[(size_t)i] = (uint32_t)v->occ_g[i];
         for (int i = 0; i <= C; i++) co[(size_t)i] = (uint32_t)v->chr_off[i];
         int rc;
         if ((rc = dev_alloc(ctx, &ctx->d_rec, (size_t)N))) return rc;
@@ -734,11 +804,11 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
         if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
         for (int e = 0; e < 3; e++)
             if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, rec.data(), sizeof(int2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_chs, chs.data(), sizeof(uchar2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_vtx_off, vo.data(), sizeof(uint32_t) * ((size_t)V + 2), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, oc.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_chr_off, co.data(), sizeof(uint32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, rec, sizeof(int2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_chs, chs, sizeof(uchar2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_vtx_off, vo, sizeof(uint32_t) * ((size_t)V + 2), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, oc, sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_chr_off, co, sizeof(uint32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->st.h2d_bytes = (uint64_t)N * (8 + 2 + 4) + (uint64_t)(V + 2) * 4 + (uint64_t)(C + 1) * 4;
     }
@@ -774,7 +844,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.rs_pool, (size_t)ctx->win.rs_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_ctl, 1))) return rc;
-    CUDA_TRY(cudaMallocHost((void **)&ctx->h_ctl, sizeof(Control)));
+    CUDA_TRY(cached_alloc((void **)&ctx->h_ctl, sizeof(Control), -1, nullptr));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, kThreads, 0));
@@ -785,8 +855,9 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
                         2 * sizeof(unsigned short) * kInstMax;
     ctx->arena_stride = (ctx->arena_stride + 255) & ~(size_t)255;
     size_t arena_bytes = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock;
-    if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes))) return rc;
-    CUDA_TRY(cudaMemsetAsync(ctx->d_arena, 0, arena_bytes, ctx->stream)); // the spill hash must start all-empty
+    bool arena_cached = false;
+    if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes, &arena_cached))) return rc;
+    if (!arena_cached) CUDA_TRY(cudaMemsetAsync(ctx->d_arena, 0, arena_bytes, ctx->stream)); // the spill hash must start all-empty
     if ((rc = dev_alloc(ctx, &ctx->d_out, (size_t)N + 1))) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return LCB_OK;
@@ -828,6 +899,29 @@ extern "C" int lcb_enumerate_seeds(lcb_ctx *ctx, uint64_t *n_seeds)
         if (n_seeds) *n_seeds = ctx->n_seeds;
         return LCB_OK;
     }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->seed_allocs.size(); i++) cached_free(ctx->seed_allocs[i], ctx->seed_alloc_bytes[i], ctx->device);
+    ctx->seed_allocs.clear();
+    ctx->seed_alloc_bytes.clear();
+    std::vector<void *> keep;
+    std::vector<size_t> keep_b;
+    keep.swap(ctx->allocs); // everything allocated below is seed-scoped
+    keep_b.swap(ctx->alloc_bytes);
+    struct Restore {
+        lcb_ctx *c;
+        std::vector<void *> &k;
+        std::vector<size_t> &kb;
+        ~Restore()
+        {
+            c->seed_allocs.insert(c->seed_allocs.end(), c->allocs.begin(), c->allocs.end());
+            c->seed_alloc_bytes.insert(c->seed_alloc_bytes.end(), c->alloc_bytes.begin(), c->alloc_bytes.end());
+            c->allocs.swap(k);
+            c->alloc_bytes.swap(kb);
+        }
+    } restore{ctx, keep, keep_b};
+    ctx->st.kernel_launches = 0;
+    ctx->st.traverse_launches = 0;
+    CUDA_TRY(cudaEventRecord(ctx->ev_step0, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     const size_t slots = 2 * (size_t)ctx->ix.V;
     unsigned *d_cnt = nullptr, *d_off = nullptr, *d_tile = nullptr, *d_total = nullptr;
@@ -966,6 +1060,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     if (!ctx || !out || !n_out) return LCB_ERR_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     int rc;
+    ctx->step_timed = !ctx->seeds_ready;
     if (!ctx->seeds_ready && (rc = lcb_enumerate_seeds(ctx, nullptr))) return rc;
     auto t_begin = std::chrono::steady_clock::now();
     const unsigned S = (unsigned)ctx->n_seeds;
@@ -980,8 +1075,11 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     const unsigned vgrid = (unsigned)ctx->sms * 8;
     float trav_ms = 0;
     ctx->st.windows = ctx->st.rounds = 0;
+    double prev_rate = 0;
+    int hold = 0;
     for (unsigned w0 = 0; w0 < S;) {
         const unsigned n = std::min(W, S - w0);
+        const auto t_window = std::chrono::steady_clock::now();
         // fresh window: every seed needs its speculative evaluation
         CUDA_TRY(cudaMemsetAsync(ctx->win.conf, 0, n, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(ctx->win.has1, 0, n, ctx->stream));
@@ -1024,6 +1122,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
             trav_ms += ms;
             if (ctx->h_ctl->err) {
+                ctx->arena_dirty = true;
                 ctx->error = "a per-seed device buffer overflowed its hard cap (path, instance or read-set too large)";
                 return (int)ctx->h_ctl->err;
             }
@@ -1065,9 +1164,23 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         }
         ctx->st.windows++;
         w0 += n;
-        // adapt the window: interference inside the window shows up as first-round invalidations
-        if (first_dirty * 5 > n) W = std::max(phase, W / 2 / phase * phase);
-        else if (first_dirty * 20 < n) W = std::min((unsigned)ctx->prm.window_max, W * 2);
+        // Adapt the window by measured throughput (seeds per ms).  The traversal is latency-bound, so wider
+        // windows are nearly free until speculation on stale epochs multiplies the work (repeat-rich seeds);
+        // grow while the rate holds, step back and hold for a few windows when it drops.
+        {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_window).count();
+            const double rate = n / std::max(ms, 1e-3);
+            (void)first_dirty;
+            if (hold > 0) {
+                hold--;
+            } else if (n == W && prev_rate > 0 && rate < 0.7 * prev_rate && W > phase) {
+                W = std::max(phase, W / 2 / phase * phase);
+                hold = 3;
+            } else if (n == W) {
+                W = std::min((unsigned)ctx->prm.window_max, W * 2);
+            }
+            prev_rate = rate;
+        }
     }
     // ---- results ----
     auto t_d2h = std::chrono::steady_clock::now();
@@ -1076,8 +1189,15 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         ctx->error = "out of host memory";
         return LCB_ERR_ARG;
     }
+    CUDA_TRY(cudaEventRecord(ctx->ev_step1, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(host, ctx->d_out, sizeof(lcb_block_instance) * out_done, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->st.ms_step_device = 0;
+    if (ctx->step_timed) {
+        float sm = 0;
+        cudaEventElapsedTime(&sm, ctx->ev_step0, ctx->ev_step1);
+        ctx->st.ms_step_device = sm;
+    }
     auto t_end = std::chrono::steady_clock::now();
     ctx->st.ms_d2h = std::chrono::duration<double, std::milli>(t_end - t_d2h).count();
     ctx->st.d2h_bytes = sizeof(lcb_block_instance) * (uint64_t)out_done;
@@ -1098,6 +1218,26 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
 }
 
 extern "C" void lcb_free_blocks(lcb_block_instance *p) { free(p); }
+
+extern "C" void lcb_trim_cache(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto &b : g_cache) {
+        if (b.device < 0) cudaFreeHost(b.p);
+        else {
+            cudaSetDevice(b.device);
+            cudaFree(b.p);
+        }
+    }
+    g_cache.clear();
+}
+
+extern "C" int lcb_reset_seeds(lcb_ctx *ctx)
+{
+    if (!ctx) return LCB_ERR_ARG;
+    ctx->seeds_ready = false;
+    return LCB_OK;
+}
 
 extern "C" int lcb_get_stats(lcb_ctx *ctx, lcb_stats *stats)
 {
