@@ -66,12 +66,22 @@ def main():
             and np.array_equal(ob["end"], blocks["end"].astype(np.uint64)) and np.array_equal(ob["chr"], blocks["chr"])
         print("PARITY", ok, len(ob["id"]), len(blocks))
     if a.ref:
+        import filecmp
+        import subprocess
         out = os.path.join(d, "refout")
         os.makedirs(out, exist_ok=True)
-        for th in (1, min(32, os.cpu_count() or 1)):
+        for th in ((1,) if a.length <= 20000000 else ()) + (min(32, os.cpu_count() or 1),):
             t = time.time()
-            run_reference_lcb(dbg, fas, a.k, out, threads=th)
+            log = run_reference_lcb(dbg, fas, a.k, out, threads=th)
             print("reference -t %d total %.2fs" % (th, time.time() - t), flush=True)
+        # whole-binary wall clock of the drop-in CLI on the same input, and byte comparison of the GFF
+        mine = os.path.join(d, "myout")
+        t = time.time()
+        r = subprocess.run([sb.CLI_PATH, "--graph", dbg] + fas + ["-k", str(a.k), "-b", "200", "-o", mine, "-m", "50", "-t", "1",
+                            "--abundance", "150", "--noseq", "--stats"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        print("sibeliaz-lcb (B200) whole binary %.2fs rc=%d" % (time.time() - t, r.returncode))
+        print(r.stdout.strip().splitlines()[-2:], r.stderr.strip()[-900:])
+        print("GFF byte-identical to the reference:", filecmp.cmp(os.path.join(mine, "blocks_coords.gff"), os.path.join(out, "blocks_coords.gff"), shallow=False))
 
 
 if __name__ == "__main__":
