@@ -75,6 +75,17 @@ struct Window { // per-window arrays, indexed by j = seed - w0
         }                                                                                                 \
     } while (0)
 
+#ifdef LCB_WITH_NCCL
+#define NCCL_TRY(x)                                                                                       \
+    do {                                                                                                  \
+        ncclResult_t r_ = (x);                                                                            \
+        if (r_ != ncclSuccess) {                                                                          \
+            ctx->error = std::string(#x) + ": " + ncclGetErrorString(r_);                                 \
+            return LCB_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // traversal kernel: persistent warps pull (seed, slot) items from a list
 // ------------------------------------------------------------------------------------------------
@@ -280,24 +291,33 @@ __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__
     }
 }
 
-__global__ void k_iota(unsigned *list, unsigned n)
+__global__ void k_iota(unsigned *list, unsigned n, unsigned first = 0, unsigned stride = 1)
 {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) list[i] = i;
+    if (i < n) list[i] = first + i * stride;
 }
 
 // Finalize (blocksfinder.h:312-332) for a converged window: block ids and output offsets are prefix
 // sums in seed order (one block, W <= 65536)
+// per-seed size of the final result (0 for seeds this rank does not own); summed across ranks before the scan
+__global__ void k_final_counts(unsigned n, Window win, unsigned *cnt_out)
+{
+    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    unsigned off, cnt;
+    final_result(win, j, off, cnt);
+    cnt_out[j] = cnt;
+}
+
 __global__ void __launch_bounds__(1024) k_emit_scan(unsigned n, Window win, Control *ctl, unsigned blocks_before,
-                                                     unsigned out_before)
+                                                     unsigned out_before, const unsigned *__restrict__ counts)
 {
     __shared__ unsigned sb[1024], so[1024];
     const unsigned per = (n + 1023) / 1024;
     const unsigned lo = threadIdx.x * per, hi = min(n, lo + per);
     unsigned nb = 0, no = 0;
     for (unsigned j = lo; j < hi; j++) {
-        unsigned off, cnt;
-        final_result(win, j, off, cnt);
+        const unsigned cnt = counts[j];
         nb += cnt ? 1 : 0;
         no += cnt;
     }
@@ -311,8 +331,7 @@ __global__ void __launch_bounds__(1024) k_emit_scan(unsigned n, Window win, Cont
     }
     unsigned b = blocks_before + sb[threadIdx.x] - nb, o = out_before + so[threadIdx.x] - no;
     for (unsigned j = lo; j < hi; j++) {
-        unsigned off, cnt;
-        final_result(win, j, off, cnt);
+        const unsigned cnt = counts[j];
         win.out_off[j] = o;
         win.blk[j] = cnt ? ++b : 0;
         o += cnt;
@@ -582,6 +601,10 @@ struct lcb_ctx {
     lcb_block_instance *d_out = nullptr;
     lcb_stats st{};
     int rank = 0, n_ranks = 1;
+#ifdef LCB_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+    unsigned *d_counts = nullptr, *d_wnext = nullptr;
     std::vector<void *> allocs, seed_allocs;
     std::vector<size_t> alloc_bytes, seed_alloc_bytes;
     bool arena_dirty = false;
@@ -707,6 +730,9 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+#ifdef LCB_WITH_NCCL
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+#endif
     for (size_t i = 0; i < ctx->allocs.size(); i++) {
         if (ctx->allocs[i] == (void *)ctx->d_arena && ctx->arena_dirty) cudaFree(ctx->allocs[i]); // invariant broken: do not recycle
         else cached_free(ctx->allocs[i], ctx->alloc_bytes[i], ctx->device);
@@ -839,6 +865,8 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if ((rc = dev_alloc(ctx, &ctx->win.out_off, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.list0, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.list1, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_wnext, 4))) return rc;
     ctx->win.inst_cap = 16ull << 20;
     ctx->win.rs_cap = 128ull << 20;
     if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
@@ -880,15 +908,27 @@ extern "C" int lcb_comm_unique_id(void *id_bytes)
 
 extern "C" int lcb_comm_init(lcb_ctx *ctx, int rank, int n_ranks, const void *id_bytes)
 {
-    if (!ctx) return LCB_ERR_ARG;
-    (void)id_bytes;
+    if (!ctx || n_ranks < 1 || rank < 0 || rank >= n_ranks) return LCB_ERR_ARG;
     if (n_ranks == 1) {
         ctx->rank = 0, ctx->n_ranks = 1;
         return LCB_OK;
     }
-    ctx->error = "multi-GPU support is not compiled in";
-    (void)rank;
+#ifdef LCB_WITH_NCCL
+    if (!id_bytes) return LCB_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclResult_t r = ncclCommInitRank(&ctx->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) {
+        ctx->error = std::string("ncclCommInitRank: ") + ncclGetErrorString(r);
+        return LCB_ERR_CUDA;
+    }
+    ctx->rank = rank, ctx->n_ranks = n_ranks;
+    return LCB_OK;
+#else
+    ctx->error = "multi-GPU support is not compiled in (NCCL not found at build time)";
     return LCB_ERR_STATE;
+#endif
 }
 
 extern "C" int lcb_enumerate_seeds(lcb_ctx *ctx, uint64_t *n_seeds)
@@ -1070,6 +1110,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     CUDA_TRY(cudaMemsetAsync(Ebase, 0xFF, (N + 32) * sizeof(uint32_t), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
     memset(ctx->h_ctl, 0, sizeof(Control));
+    if (ctx->n_ranks > 1) CUDA_TRY(cudaMemsetAsync(ctx->d_out, 0, (N + 1) * sizeof(lcb_block_instance), ctx->stream));
     unsigned blocks_done = 0, out_done = 0;
     unsigned W = (unsigned)ctx->prm.window_init;
     const unsigned vgrid = (unsigned)ctx->sms * 8;
@@ -1083,11 +1124,19 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         // fresh window: every seed needs its speculative evaluation
         CUDA_TRY(cudaMemsetAsync(ctx->win.conf, 0, n, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(ctx->win.has1, 0, n, ctx->stream));
-        k_iota<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->win.list0, n);
+        // seeds are dealt round-robin over the ranks; a rank sees the others' seeds as "no result, empty read-set"
+        const unsigned R = (unsigned)ctx->n_ranks, me = (unsigned)ctx->rank;
+        const unsigned n_own = n > me ? (n - me + R - 1) / R : 0;
+        if (R > 1)
+            for (int s = 0; s < 2; s++) {
+                CUDA_TRY(cudaMemsetAsync(ctx->win.res_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
+                CUDA_TRY(cudaMemsetAsync(ctx->win.rs_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
+            }
+        if (n_own) k_iota<<<(n_own + 255) / 256, 256, 0, ctx->stream>>>(ctx->win.list0, n_own, me, R);
         ctx->st.kernel_launches++;
         {
             Control z{};
-            z.n0 = n;
+            z.n0 = n_own;
             z.ct_walk = ctx->h_ctl->ct_walk, z.ct_occ = ctx->h_ctl->ct_occ, z.ct_scan = ctx->h_ctl->ct_scan,
             z.ct_score = ctx->h_ctl->ct_score, z.runs0 = ctx->h_ctl->runs0, z.runs1 = ctx->h_ctl->runs1;
             *ctx->h_ctl = z;
@@ -1111,11 +1160,27 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             // D. new epochs
             CUDA_TRY(cudaMemcpyAsync(Enew, Ebase, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
             k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, w0, n, ctx->win);
+#ifdef LCB_WITH_NCCL
+            // the one real exchange of the path: every rank's claims meet in a min-reduction over NVLink
+            if (R > 1) NCCL_TRY(ncclAllReduce(Enew, Enew, N, ncclUint32, ncclMin, ctx->comm, ctx->stream));
+#endif
             // E. validation + next work lists
             CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream)); // n0, n1, dirty
             k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, w0, n, phase, ctx->win, ctx->d_ctl);
             ctx->st.kernel_launches += 3;
             if ((rc = fetch_control(ctx))) return rc;
+#ifdef LCB_WITH_NCCL
+            if (R > 1) { // agree on termination / failure: {dirty, err, pool_overflow} summed over ranks
+                unsigned local[4] = {ctx->h_ctl->dirty, ctx->h_ctl->err, ctx->h_ctl->pool_overflow, 0};
+                CUDA_TRY(cudaMemcpyAsync(ctx->d_wnext, local, sizeof local, cudaMemcpyHostToDevice, ctx->stream));
+                NCCL_TRY(ncclAllReduce(ctx->d_wnext, ctx->d_wnext, 4, ncclUint32, ncclSum, ctx->comm, ctx->stream));
+                CUDA_TRY(cudaMemcpyAsync(local, ctx->d_wnext, sizeof local, cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                ctx->h_ctl->dirty = local[0];
+                if (local[1] && !ctx->h_ctl->err) ctx->h_ctl->err = LCB_ERR_CAPACITY;
+                ctx->h_ctl->pool_overflow = local[2];
+            }
+#endif
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
             trav_ms += ms;
@@ -1148,9 +1213,13 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             continue;
         }
         // window converged: Ecur holds base + this window's claims
-        k_emit_scan<<<1, 1024, 0, ctx->stream>>>(n, ctx->win, ctx->d_ctl, blocks_done, out_done);
+        k_final_counts<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->win, ctx->d_counts);
+#ifdef LCB_WITH_NCCL
+        if (R > 1) NCCL_TRY(ncclAllReduce(ctx->d_counts, ctx->d_counts, n, ncclUint32, ncclSum, ctx->comm, ctx->stream));
+#endif
+        k_emit_scan<<<1, 1024, 0, ctx->stream>>>(n, ctx->win, ctx->d_ctl, blocks_done, out_done, ctx->d_counts);
         k_emit_write<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ix, ctx->prm.k, n, ctx->win, ctx->d_out);
-        ctx->st.kernel_launches += 2;
+        ctx->st.kernel_launches += 3;
         if ((rc = fetch_control(ctx))) return rc;
         blocks_done += ctx->h_ctl->n_blocks;
         out_done += ctx->h_ctl->n_out;
@@ -1180,6 +1249,14 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
                 W = std::min((unsigned)ctx->prm.window_max, W * 2);
             }
             prev_rate = rate;
+#ifdef LCB_WITH_NCCL
+            if (R > 1) { // every rank must walk the same windows: rank 0's choice wins
+                CUDA_TRY(cudaMemcpyAsync(ctx->d_wnext, &W, sizeof W, cudaMemcpyHostToDevice, ctx->stream));
+                NCCL_TRY(ncclBroadcast(ctx->d_wnext, ctx->d_wnext, 1, ncclUint32, 0, ctx->comm, ctx->stream));
+                CUDA_TRY(cudaMemcpyAsync(&W, ctx->d_wnext, sizeof W, cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            }
+#endif
         }
     }
     // ---- results ----
@@ -1189,6 +1266,11 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         ctx->error = "out of host memory";
         return LCB_ERR_ARG;
     }
+#ifdef LCB_WITH_NCCL
+    // every rank wrote only its own seeds' records (the rest is zero): one sum yields the full commit-ordered list everywhere
+    if (ctx->n_ranks > 1 && out_done)
+        NCCL_TRY(ncclAllReduce(ctx->d_out, ctx->d_out, (size_t)out_done * 4, ncclUint32, ncclSum, ctx->comm, ctx->stream));
+#endif
     CUDA_TRY(cudaEventRecord(ctx->ev_step1, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(host, ctx->d_out, sizeof(lcb_block_instance) * out_done, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
