@@ -109,6 +109,10 @@ typedef struct lcb_stats {
 
 void lcb_default_params(lcb_params *p);
 
+/* Optional: create the CUDA context on `device` and pre-allocate the index-independent scratch, e.g. on a
+ * thread while the host parses its inputs. */
+int lcb_warmup(int device);
+
 /* Uploads the index (arrays are caller-owned and may be freed once this returns). */
 int lcb_create(const lcb_index_view *index, const lcb_params *params, lcb_ctx **out);
 

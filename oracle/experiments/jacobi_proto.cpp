@@ -46,7 +46,8 @@ int main(int argc, char **argv)
     L->order.assign(L->C, std::vector<int>());
     const uint32_t INF = 0xFFFFFFFFu;
     std::vector<uint32_t> Ebase(L->N, INF), Enew;
-    L->epoch = Ebase;
+    std::vector<uint32_t> Ecur = Ebase;
+    L->epoch = Ecur.data();
     std::vector<int64_t> log;
     L->readlog = &log;
     uint64_t runs0 = 0, runs1 = 0, total_rounds = 0, windows = 0, max_rounds = 0, rs_intervals = 0, rs_len = 0, val_reads = 0;
@@ -57,7 +58,8 @@ int main(int argc, char **argv)
         std::vector<std::vector<Inst>> r0(n), r1(n);
         std::vector<Intervals> R0(n), R1(n);
         std::vector<char> need0(n, 1), need1(n, 0), has1(n, 0), conf(n, 0);
-        L->epoch = Ebase; // E_cur
+        Ecur = Ebase; // E_cur
+        L->epoch = Ecur.data();
         int rounds = 0;
         while (true) {
             rounds++;
@@ -74,7 +76,7 @@ int main(int argc, char **argv)
                 if (r0[j].size() > 1)
                     for (auto &in : r0[j]) {
                         int64_t lo, hi; Marks(in, lo, hi);
-                        for (int64_t f = lo; f <= hi && !c; f++) c = L->epoch[f] < (uint32_t)i;
+                        for (int64_t f = lo; f <= hi && !c; f++) c = Ecur[f] < (uint32_t)i;
                     }
                 conf[j] = c;
                 if (c && (!has1[j] || need1[j])) {
@@ -100,7 +102,7 @@ int main(int argc, char **argv)
                 uint32_t i = (uint32_t)(w0 + j), T = i / 256 * 256;
                 bool d0 = false;
                 for (auto &iv : R0[j]) {
-                    for (int64_t f = iv.first; f <= iv.second && !d0; f++) { val_reads++; d0 = (L->epoch[f] < T) != (Enew[f] < T); }
+                    for (int64_t f = iv.first; f <= iv.second && !d0; f++) { val_reads++; d0 = (Ecur[f] < T) != (Enew[f] < T); }
                     if (d0) break;
                 }
                 if (d0) { need0[j] = 1; has1[j] = 0; dirty++; continue; }
@@ -114,18 +116,19 @@ int main(int argc, char **argv)
                 if (c && has1[j]) {
                     bool d1 = false;
                     for (auto &iv : R1[j]) {
-                        for (int64_t f = iv.first; f <= iv.second && !d1; f++) { val_reads++; d1 = (L->epoch[f] < i) != (Enew[f] < i); }
+                        for (int64_t f = iv.first; f <= iv.second && !d1; f++) { val_reads++; d1 = (Ecur[f] < i) != (Enew[f] < i); }
                         if (d1) break;
                     }
                     if (d1) { need1[j] = 1; dirty++; }
                 }
             }
             if (rounds <= 12 || dirty == 0) fprintf(stderr, "  window %lld round %d dirty %lld\n", (long long)(w0 / W), rounds, (long long)dirty);
-            L->epoch.swap(Enew);
+            Ecur.swap(Enew);
+            L->epoch = Ecur.data();
             if (!dirty) break;
         }
         total_rounds += rounds; windows++; max_rounds = std::max<uint64_t>(max_rounds, rounds);
-        Ebase = L->epoch;
+        Ebase = Ecur;
         for (int64_t j = 0; j < n; j++) {
             for (auto &iv : R0[j]) { rs_intervals++; rs_len += iv.second - iv.first + 1; }
             const std::vector<Inst> &fin = conf[j] ? r1[j] : r0[j];

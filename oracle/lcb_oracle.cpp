@@ -135,7 +135,7 @@ struct lcbo {
     int64_t blocks_found = 0;
     uint64_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #ifdef LCBO_EPOCH
-    std::vector<uint32_t> epoch;
+    const uint32_t *epoch = nullptr; // caller-owned epoch array (see lcb_oracle_epoch API below)
     uint32_t thresh = 0;
     mutable std::vector<int64_t> *readlog = nullptr;
 #endif
@@ -956,6 +956,60 @@ extern "C" int lcbo_generate_output(lcbo *L, const char *outdir, int gen_seq, in
     }
     return 0;
 }
+
+
+#ifdef LCBO_EPOCH
+// -------------------------------------------------------------------------------------------------
+// Epoch-threshold evaluation of one seed (test infrastructure for the speculative-round protocol used by the
+// CUDA path): edge e is "used" iff epoch[e] < thresh.  Returns the best instances as
+// (front g | strand bit 62, back g) pairs and the read-set as sorted, merged [lo, hi] intervals.
+// -------------------------------------------------------------------------------------------------
+extern "C" void lcbo_epoch_prepare(lcbo *L, int min_block, int max_branch, int max_flank, int looking_depth)
+{
+    if (L->seed.empty()) lcbo_enumerate_seeds(L);
+    L->min_block = min_block;
+    L->max_branch = max_branch;
+    L->max_flank = max_flank;
+    L->looking_depth = looking_depth;
+    L->distance.assign((size_t)L->V * 2 + 2, INT_MAX);
+    L->count.assign((size_t)L->V * 2 + 2, 0);
+    L->order.assign(L->C, std::vector<int>());
+}
+
+extern "C" int lcbo_epoch_process(lcbo *L, int64_t seed_index, uint32_t thresh, const uint32_t *epoch, int64_t *inst_out,
+                                  int inst_cap, int64_t *rs_out, int rs_cap, int *n_rs)
+{
+    std::vector<int64_t> log;
+    std::vector<Inst> best;
+    L->epoch = epoch;
+    L->thresh = thresh;
+    L->readlog = &log;
+    L->Process(L->seed[(size_t)seed_index], best);
+    L->readlog = nullptr;
+    std::sort(log.begin(), log.end());
+    int m = 0;
+    for (size_t i = 0; i < log.size();) {
+        size_t j = i;
+        while (j + 1 < log.size() && log[j + 1] <= log[j] + 1) j++;
+        if (m < rs_cap) {
+            rs_out[2 * m] = log[i];
+            rs_out[2 * m + 1] = log[j];
+        }
+        m++;
+        i = j + 1;
+    }
+    *n_rs = m;
+    int n = 0;
+    for (const Inst &a : best) {
+        if (n < inst_cap) {
+            inst_out[2 * n] = a.fg | (a.pos ? (int64_t)1 << 62 : 0);
+            inst_out[2 * n + 1] = a.bg;
+        }
+        n++;
+    }
+    return n;
+}
+#endif
 
 #ifdef LCB_ORACLE_MAIN
 // Minimal CLI used by tests and by hand: lcb_oracle <graph> <k> <b> <m> <a> <outdir> <noseq 0|1> <chunks> <fasta...>

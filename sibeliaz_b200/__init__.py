@@ -24,7 +24,7 @@ LCB_OK = 0
 ERR_NAMES = {1: "LCB_ERR_ARG", 2: "LCB_ERR_IO", 3: "LCB_ERR_FORMAT", 4: "LCB_ERR_CUDA", 5: "LCB_ERR_CAPACITY",
              6: "LCB_ERR_STATE"}
 
-EXPORTS = ["lcb_trim_cache", "lcb_reset_seeds", "lcb_index_load", "lcb_index_get_view", "lcb_index_num_chr", "lcb_index_chr_name", "lcb_index_chr_length",
+EXPORTS = ["lcb_warmup", "lcb_trim_cache", "lcb_reset_seeds", "lcb_index_load", "lcb_index_get_view", "lcb_index_num_chr", "lcb_index_chr_name", "lcb_index_chr_length",
            "lcb_index_free", "lcb_default_params", "lcb_create", "lcb_comm_unique_id", "lcb_comm_init",
            "lcb_enumerate_seeds", "lcb_get_seeds", "lcb_find_blocks", "lcb_free_blocks", "lcb_get_stats",
            "lcb_last_error", "lcb_destroy", "lcb_write_output", "lcb_version"]

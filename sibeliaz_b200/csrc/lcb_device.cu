@@ -626,6 +626,10 @@ struct CachedBlock {
 };
 std::mutex g_cache_mu;
 std::vector<CachedBlock> g_cache;
+#ifdef LCB_WITH_NCCL
+ncclComm_t g_comm = nullptr; // reused by every context of this process (lcb_comm_init), freed by lcb_trim_cache
+int g_comm_dev = -1, g_comm_rank = -1, g_comm_size = 0;
+#endif
 
 cudaError_t cached_alloc(void **p, size_t bytes, int device, bool *was_cached)
 {
@@ -653,6 +657,15 @@ void cached_free(void *p, size_t bytes, int device)
     bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
     std::lock_guard<std::mutex> lk(g_cache_mu);
     g_cache.push_back(CachedBlock{p, bytes, device, false});
+}
+
+constexpr unsigned long long kInstPoolCap = 16ull << 20, kRsPoolCap = 128ull << 20;
+
+size_t arena_stride_bytes()
+{
+    size_t s = sizeof(Inst) * kInstMax + sizeof(int4) * kInstMax + sizeof(int2) * kHashMax + sizeof(int4) * kPathMax +
+               sizeof(int2) * kVoteMax + sizeof(int2) * kReadSetMax + sizeof(int) * kPathMax + 2 * sizeof(unsigned short) * kInstMax;
+    return (s + 255) & ~(size_t)255;
 }
 
 template <typename T>
@@ -723,6 +736,34 @@ extern "C" void lcb_default_params(lcb_params *p)
     p->collect_counters = 0;
 }
 
+// Creates the CUDA context on `device` and parks the index-independent scratch (arena, pools) in the block cache,
+// so a host can overlap it with parsing its inputs (the CLI does).  Optional; lcb_create works without it.
+extern "C" int lcb_warmup(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return LCB_ERR_CUDA;
+    if (cudaFree(nullptr) != cudaSuccess) return LCB_ERR_CUDA;
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const size_t stride = arena_stride_bytes();
+    const size_t arena_bytes = stride * (size_t)per_sm * (size_t)sms * kWarpsPerBlock;
+    void *arena = nullptr, *ip = nullptr, *rp = nullptr;
+    bool cached = false;
+    if (cached_alloc(&arena, arena_bytes, device, &cached) != cudaSuccess) return LCB_ERR_CUDA;
+    if (!cached && cudaMemset(arena, 0, arena_bytes) != cudaSuccess) return LCB_ERR_CUDA;
+    if (cached_alloc(&ip, sizeof(int4) * kInstPoolCap, device, nullptr) != cudaSuccess) return LCB_ERR_CUDA;
+    if (cached_alloc(&rp, sizeof(int2) * kRsPoolCap, device, nullptr) != cudaSuccess) return LCB_ERR_CUDA;
+    cudaDeviceSynchronize();
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        size_t ab = (arena_bytes + 511) & ~(size_t)511;
+        g_cache.push_back(CachedBlock{arena, ab, device, true});
+    }
+    cached_free(ip, sizeof(int4) * kInstPoolCap, device);
+    cached_free(rp, sizeof(int2) * kRsPoolCap, device);
+    return LCB_OK;
+}
+
 extern "C" const char *lcb_last_error(lcb_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 
 extern "C" void lcb_destroy(lcb_ctx *ctx)
@@ -730,9 +771,6 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-#ifdef LCB_WITH_NCCL
-    if (ctx->comm) ncclCommDestroy(ctx->comm);
-#endif
     for (size_t i = 0; i < ctx->allocs.size(); i++) {
         if (ctx->allocs[i] == (void *)ctx->d_arena && ctx->arena_dirty) cudaFree(ctx->allocs[i]); // invariant broken: do not recycle
         else cached_free(ctx->allocs[i], ctx->alloc_bytes[i], ctx->device);
@@ -867,8 +905,8 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if ((rc = dev_alloc(ctx, &ctx->win.list1, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_wnext, 4))) return rc;
-    ctx->win.inst_cap = 16ull << 20;
-    ctx->win.rs_cap = 128ull << 20;
+    ctx->win.inst_cap = kInstPoolCap;
+    ctx->win.rs_cap = kRsPoolCap;
     if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.rs_pool, (size_t)ctx->win.rs_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_ctl, 1))) return rc;
@@ -878,10 +916,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
     ctx->grid_traverse = per_sm * ctx->sms;
-    ctx->arena_stride = sizeof(Inst) * kInstMax + sizeof(int4) * kInstMax + sizeof(int2) * kHashMax + sizeof(int4) * kPathMax +
-                        sizeof(int2) * kVoteMax + sizeof(int2) * kReadSetMax + sizeof(int) * kPathMax +
-                        2 * sizeof(unsigned short) * kInstMax;
-    ctx->arena_stride = (ctx->arena_stride + 255) & ~(size_t)255;
+    ctx->arena_stride = arena_stride_bytes();
     size_t arena_bytes = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock;
     bool arena_cached = false;
     if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes, &arena_cached))) return rc;
@@ -916,13 +951,29 @@ extern "C" int lcb_comm_init(lcb_ctx *ctx, int rank, int n_ranks, const void *id
 #ifdef LCB_WITH_NCCL
     if (!id_bytes) return LCB_ERR_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    {
+        // communicators are expensive (seconds) and independent of the index: keep one per (device, rank, size)
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_comm && g_comm_dev == ctx->device && g_comm_rank == rank && g_comm_size == n_ranks) {
+            ctx->comm = g_comm;
+            ctx->rank = rank, ctx->n_ranks = n_ranks;
+            return LCB_OK;
+        }
+    }
     ncclUniqueId id;
     memcpy(&id, id_bytes, sizeof id);
-    ncclResult_t r = ncclCommInitRank(&ctx->comm, n_ranks, id, rank);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = ncclCommInitRank(&comm, n_ranks, id, rank);
     if (r != ncclSuccess) {
         ctx->error = std::string("ncclCommInitRank: ") + ncclGetErrorString(r);
         return LCB_ERR_CUDA;
     }
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_comm) ncclCommDestroy(g_comm);
+        g_comm = comm, g_comm_dev = ctx->device, g_comm_rank = rank, g_comm_size = n_ranks;
+    }
+    ctx->comm = comm;
     ctx->rank = rank, ctx->n_ranks = n_ranks;
     return LCB_OK;
 #else
@@ -1312,6 +1363,10 @@ extern "C" void lcb_trim_cache(void)
         }
     }
     g_cache.clear();
+#ifdef LCB_WITH_NCCL
+    if (g_comm) ncclCommDestroy(g_comm);
+    g_comm = nullptr;
+#endif
 }
 
 extern "C" int lcb_reset_seeds(lcb_ctx *ctx)

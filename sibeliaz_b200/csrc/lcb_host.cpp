@@ -98,45 +98,6 @@ struct FastaRecords {
     std::vector<std::string> seq;
 };
 
-void ParseFasta(const char *path, FastaRecords &out)
-{
-    MappedFile f;
-    if (!f.open(path)) throw Failure(LCB_ERR_IO, std::string("Can't open file ") + path);
-    const uint8_t *p = f.data, *end = f.data + f.size;
-    std::string header;
-    while (p < end) {
-        if (*p != '>')
-            throw Failure(LCB_ERR_FORMAT, std::string("The FASTA header should start with a '>', started with '") + (char)*p + "'");
-        ++p;
-        const uint8_t *nl = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
-        const uint8_t *line_end = nl ? nl : end;
-        if (nl) { // header := first blank-delimited token; an empty header line keeps the previous name
-            const uint8_t *a = p;
-            while (a < line_end && isspace(*a)) ++a;
-            const uint8_t *b = a;
-            while (b < line_end && !isspace(*b)) ++b;
-            if (b > a) header.assign((const char *)a, (size_t)(b - a));
-        }
-        p = nl ? nl + 1 : end;
-        out.name.push_back(header);
-        out.seq.emplace_back();
-        std::string &s = out.seq.back();
-        // size the record first so the bases land with one allocation
-        const uint8_t *q = (const uint8_t *)memchr(p, '>', (size_t)(end - p));
-        const uint8_t *rec_end = q ? q : end;
-        s.resize((size_t)(rec_end - p));
-        char *w = &s[0];
-        for (const uint8_t *r = p; r < rec_end; ++r) {
-            uint8_t c = kFasta.t[*r];
-            if (c > 2) *w++ = (char)c;
-            else if (c == 0)
-                throw Failure(LCB_ERR_FORMAT, std::string("Found an invalid character '") + (char)*r + "' in sequence " + header);
-        }
-        s.resize((size_t)(w - s.data()));
-        p = rec_end;
-    }
-}
-
 } // namespace
 
 struct lcb_index {
@@ -151,6 +112,90 @@ struct lcb_index {
     std::string error;
 };
 
+namespace {
+
+unsigned WorkerCount()
+{
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    return std::min(hw, 32u);
+}
+
+// runs fn(t, T) on T threads and joins
+template <class F>
+void Parallel(unsigned T, F fn)
+{
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < T; t++) pool.emplace_back([&fn, t, T]() { fn(t, T); });
+    fn(0, T);
+    for (auto &th : pool) th.join();
+}
+
+// FASTA with the sequence bodies filtered in parallel: count kept characters per 4 MiB slice, then write
+void ParseFastaParallel(const char *path, FastaRecords &out, unsigned T)
+{
+    MappedFile f;
+    if (!f.open(path)) throw Failure(LCB_ERR_IO, std::string("Can't open file ") + path);
+    const uint8_t *p = f.data, *end = f.data + f.size;
+    std::string header;
+    while (p < end) {
+        if (*p != '>')
+            throw Failure(LCB_ERR_FORMAT, std::string("The FASTA header should start with a '>', started with '") + (char)*p + "'");
+        ++p;
+        const uint8_t *nl = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
+        const uint8_t *line_end = nl ? nl : end;
+        if (nl) {
+            const uint8_t *a = p;
+            while (a < line_end && isspace(*a)) ++a;
+            const uint8_t *b = a;
+            while (b < line_end && !isspace(*b)) ++b;
+            if (b > a) header.assign((const char *)a, (size_t)(b - a));
+        }
+        p = nl ? nl + 1 : end;
+        const uint8_t *q = (const uint8_t *)memchr(p, '>', (size_t)(end - p));
+        const uint8_t *rec_end = q ? q : end;
+        const size_t body = (size_t)(rec_end - p);
+        const size_t slice = 4u << 20;
+        const size_t ns = (body + slice - 1) / slice;
+        std::vector<size_t> kept(ns + 1, 0);
+        std::vector<const uint8_t *> bad(ns, nullptr);
+        const unsigned Tn = (unsigned)std::max<size_t>(1, std::min<size_t>(T, ns));
+        Parallel(Tn, [&](unsigned t, unsigned TT) {
+            for (size_t s = t; s < ns; s += TT) {
+                const uint8_t *a = p + s * slice, *b = std::min(rec_end, a + slice);
+                size_t n = 0;
+                for (const uint8_t *r = a; r < b; ++r) {
+                    uint8_t c = kFasta.t[*r];
+                    n += c > 2;
+                    if (c == 0 && !bad[s]) bad[s] = r;
+                }
+                kept[s + 1] = n;
+            }
+        });
+        for (size_t s = 0; s < ns; s++)
+            if (bad[s])
+                throw Failure(LCB_ERR_FORMAT, std::string("Found an invalid character '") + (char)*bad[s] + "' in sequence " + header);
+        for (size_t s = 0; s < ns; s++) kept[s + 1] += kept[s];
+        out.name.push_back(header);
+        out.seq.emplace_back();
+        std::string &str = out.seq.back();
+        str.resize(kept[ns]);
+        char *base = str.empty() ? nullptr : &str[0];
+        Parallel(Tn, [&](unsigned t, unsigned TT) {
+            for (size_t s = t; s < ns; s += TT) {
+                const uint8_t *a = p + s * slice, *b = std::min(rec_end, a + slice);
+                char *w = base + kept[s];
+                for (const uint8_t *r = a; r < b; ++r) {
+                    uint8_t c = kFasta.t[*r];
+                    if (c > 2) *w++ = (char)c;
+                }
+            }
+        });
+        p = rec_end;
+    }
+}
+
+} // namespace
+
 extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_files, int n_fasta, int k, int abundance,
                               lcb_index **out, char *err, size_t errlen)
 {
@@ -158,116 +203,181 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
     lcb_index *ix = new lcb_index;
     try {
         ix->k = k;
-        // FASTA files parse concurrently with the junction stream (one thread per file, capped)
+        const unsigned T = WorkerCount();
+        // ---- FASTA files on their own threads (each splits its bodies further), concurrently with the junction stream
         std::vector<FastaRecords> per_file((size_t)n_fasta);
         std::vector<std::string> fasta_err((size_t)n_fasta);
         std::vector<int> fasta_code((size_t)n_fasta, LCB_OK);
-        {
-            unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-            unsigned workers = std::min<unsigned>(hw, (unsigned)std::max(1, n_fasta));
-            std::vector<std::thread> pool;
-            for (unsigned w = 0; w < workers; w++)
-                pool.emplace_back([&, w]() {
-                    for (int i = (int)w; i < n_fasta; i += (int)workers) {
-                        try {
-                            ParseFasta(fasta_files[i], per_file[(size_t)i]);
-                        } catch (Failure &e) {
-                            fasta_code[(size_t)i] = e.code;
-                            fasta_err[(size_t)i] = e.what();
-                        }
-                    }
-                });
-
-            // ---- junction records: {u32 pos; i64 id} packed little-endian, 12 bytes ----
-            MappedFile g;
-            if (!g.open(graph_file)) {
-                for (auto &t : pool) t.join();
-                throw Failure(LCB_ERR_IO, "Can't read the input file");
+        const unsigned per_fasta_threads = std::max(1u, T / (unsigned)std::max(1, n_fasta));
+        std::vector<std::thread> fasta_pool;
+        for (int i = 0; i < n_fasta; i++)
+            fasta_pool.emplace_back([&, i]() {
+                try {
+                    ParseFastaParallel(fasta_files[i], per_file[(size_t)i], per_fasta_threads);
+                } catch (Failure &e) {
+                    fasta_code[(size_t)i] = e.code;
+                    fasta_err[(size_t)i] = e.what();
+                } catch (std::exception &e) {
+                    fasta_code[(size_t)i] = LCB_ERR_IO;
+                    fasta_err[(size_t)i] = e.what();
+                }
+            });
+        struct Joiner {
+            std::vector<std::thread> &p;
+            ~Joiner()
+            {
+                for (auto &t : p)
+                    if (t.joinable()) t.join();
             }
-            const size_t nrec = g.size / 12;
-            std::vector<uint32_t> rec_chr;
-            std::vector<uint32_t> occ_count; // occurrences per |id| before filtering
-            rec_chr.reserve(nrec);
-            ix->pos_id.reserve(nrec);
-            ix->pos_bp.reserve(nrec);
-            uint32_t chr = 0, max_chr = 0;
-            int64_t max_abs = -1;
-            for (size_t i = 0; i < nrec; i++) {
+        } joiner{fasta_pool};
+
+        // ---- junction records: {u32 pos; i64 id} packed little-endian, 12 bytes; separators bump the chromosome
+        MappedFile g;
+        if (!g.open(graph_file)) throw Failure(LCB_ERR_IO, "Can't read the input file");
+        const size_t nrec = g.size / 12;
+        auto rd = [&g](size_t i, uint32_t &pos, int64_t &id) {
+            memcpy(&pos, g.data + i * 12, 4);
+            memcpy(&id, g.data + i * 12 + 4, 8);
+        };
+        auto chunk = [nrec](unsigned t, unsigned TT, size_t &lo, size_t &hi) {
+            lo = nrec * t / TT;
+            hi = nrec * (t + 1) / TT;
+        };
+        std::vector<size_t> seps(T + 1, 0), recs(T + 1, 0);
+        std::vector<int64_t> tmax(T, -1);
+        Parallel(T, [&](unsigned t, unsigned TT) {
+            size_t lo, hi, ns = 0, nr = 0;
+            int64_t mx = -1;
+            chunk(t, TT, lo, hi);
+            for (size_t i = lo; i < hi; i++) {
                 uint32_t pos;
                 int64_t id;
-                memcpy(&pos, g.data + i * 12, 4);
-                memcpy(&id, g.data + i * 12 + 4, 8);
-                if (pos == UINT32_MAX || id == INT64_MAX) { // chromosome separator
+                rd(i, pos, id);
+                if (pos == UINT32_MAX || id == INT64_MAX) ++ns;
+                else {
+                    ++nr;
+                    int64_t a = id < 0 ? -id : id;
+                    if (a > mx) mx = a;
+                }
+            }
+            seps[t + 1] = ns, recs[t + 1] = nr, tmax[t] = mx;
+        });
+        int64_t max_abs = -1;
+        for (unsigned t = 0; t < T; t++) {
+            seps[t + 1] += seps[t];
+            recs[t + 1] += recs[t];
+            max_abs = std::max(max_abs, tmax[t]);
+        }
+        const size_t M = recs[T]; // records before the abundance filter
+        ix->V = max_abs + 1;
+        std::vector<int32_t> id_all(M);
+        std::vector<uint32_t> bp_all(M), chr_all(M);
+        std::vector<uint32_t> occ_count((size_t)ix->V + 1, 0);
+        Parallel(T, [&](unsigned t, unsigned TT) {
+            size_t lo, hi;
+            chunk(t, TT, lo, hi);
+            uint32_t chr = (uint32_t)seps[t];
+            size_t w = recs[t];
+            for (size_t i = lo; i < hi; i++) {
+                uint32_t pos;
+                int64_t id;
+                rd(i, pos, id);
+                if (pos == UINT32_MAX || id == INT64_MAX) {
                     ++chr;
                     continue;
                 }
-                int64_t a = id < 0 ? -id : id;
-                if (a > max_abs) {
-                    max_abs = a;
-                    if ((size_t)a >= occ_count.size()) occ_count.resize((size_t)a + 1 + occ_count.size() / 2, 0);
-                }
-                ++occ_count[(size_t)a];
-                ix->pos_id.push_back((int32_t)id); // int32 truncation as in Position/Vertex
-                ix->pos_bp.push_back(pos);
-                rec_chr.push_back(chr);
-                max_chr = chr;
+                id_all[w] = (int32_t)id; // int32 truncation as in Position/Vertex (junctionstorage.h:129,148)
+                bp_all[w] = pos;
+                chr_all[w] = chr;
+                ++w;
+                __atomic_fetch_add(&occ_count[(size_t)(id < 0 ? -id : id)], 1u, __ATOMIC_RELAXED);
             }
-            ix->V = max_abs + 1;
-            ix->C = rec_chr.empty() ? 0 : (int32_t)max_chr + 1;
-            // ---- abundance filter (strict <), compaction in place, per-chromosome offsets ----
-            ix->chr_off.assign((size_t)ix->C + 1, 0);
-            std::vector<int64_t> kept_per_vertex((size_t)ix->V + 1, 0);
-            size_t w = 0;
-            for (size_t i = 0; i < rec_chr.size(); i++) {
-                int64_t id = ix->pos_id[i];
-                // the filter uses the 64-bit |id|; ids beyond int32 would already have broken the reference
-                size_t a = (size_t)(id < 0 ? -id : id);
-                if (occ_count[a] < (size_t)abundance) {
-                    ix->pos_id[w] = ix->pos_id[i];
-                    ix->pos_bp[w] = ix->pos_bp[i];
-                    rec_chr[w] = rec_chr[i];
-                    ++ix->chr_off[(size_t)rec_chr[i] + 1];
-                    ++kept_per_vertex[a];
+        });
+        ix->C = M ? (int32_t)chr_all[M - 1] + 1 : 0;
+        // ---- abundance filter (strict <, junctionstorage.h:610) + compaction
+        auto rchunk = [M](unsigned t, unsigned TT, size_t &lo, size_t &hi) {
+            lo = M * t / TT;
+            hi = M * (t + 1) / TT;
+        };
+        auto vabs = [&id_all](size_t i) { return (size_t)(id_all[i] < 0 ? -(int64_t)id_all[i] : (int64_t)id_all[i]); };
+        std::vector<size_t> kept(T + 1, 0);
+        Parallel(T, [&](unsigned t, unsigned TT) {
+            size_t lo, hi, n = 0;
+            rchunk(t, TT, lo, hi);
+            for (size_t i = lo; i < hi; i++) n += occ_count[vabs(i)] < (uint32_t)abundance;
+            kept[t + 1] = n;
+        });
+        for (unsigned t = 0; t < T; t++) kept[t + 1] += kept[t];
+        const size_t N = kept[T];
+        ix->N = (int64_t)N;
+        ix->pos_id.resize(N);
+        ix->pos_bp.resize(N);
+        std::vector<uint32_t> rec_chr(N);
+        Parallel(T, [&](unsigned t, unsigned TT) {
+            size_t lo, hi;
+            rchunk(t, TT, lo, hi);
+            size_t w = kept[t];
+            for (size_t i = lo; i < hi; i++)
+                if (occ_count[vabs(i)] < (uint32_t)abundance) {
+                    ix->pos_id[w] = id_all[i];
+                    ix->pos_bp[w] = bp_all[i];
+                    rec_chr[w] = chr_all[i];
                     ++w;
                 }
-            }
-            ix->N = (int64_t)w;
-            ix->pos_id.resize(w);
-            ix->pos_bp.resize(w);
-            rec_chr.resize(w);
-            for (int32_t c = 0; c < ix->C; c++) ix->chr_off[(size_t)c + 1] += ix->chr_off[(size_t)c];
-            // ---- CSR of occurrences; counting sort keeps genome order == (chr, idx) order ----
-            ix->vtx_off.assign((size_t)ix->V + 1, 0);
-            for (int64_t v = 0; v < ix->V; v++) ix->vtx_off[(size_t)v + 1] = ix->vtx_off[(size_t)v] + kept_per_vertex[(size_t)v];
-            ix->occ_g.resize(w);
-            {
-                std::vector<int64_t> cursor(ix->vtx_off.begin(), ix->vtx_off.end() - (ix->V ? 1 : 0));
-                for (size_t gi = 0; gi < w; gi++) {
-                    int64_t id = ix->pos_id[gi];
-                    ix->occ_g[(size_t)cursor[(size_t)(id < 0 ? -id : id)]++] = (int64_t)gi;
+        });
+        ix->chr_off.assign((size_t)ix->C + 1, 0);
+        for (size_t gi = 0; gi < N; gi++) ++ix->chr_off[(size_t)rec_chr[gi] + 1];
+        for (int32_t c = 0; c < ix->C; c++) ix->chr_off[(size_t)c + 1] += ix->chr_off[(size_t)c];
+        // ---- CSR of occurrences: every thread owns a vertex range and scans the records in genome order, so each
+        //      occurrence list comes out sorted by (chr, idx) like std::sort leaves it at junctionstorage.h:646-649
+        ix->vtx_off.assign((size_t)ix->V + 1, 0);
+        for (int64_t v = 0; v < ix->V; v++)
+            ix->vtx_off[(size_t)v + 1] = ix->vtx_off[(size_t)v] + (occ_count[(size_t)v] < (uint32_t)abundance ? occ_count[(size_t)v] : 0);
+        ix->occ_g.resize(N);
+        {
+            std::vector<int64_t> cursor(ix->vtx_off.begin(), ix->vtx_off.end());
+            Parallel(T, [&](unsigned t, unsigned TT) {
+                // balance by occurrences: vertex range [va, vb) holding ~N/T of them
+                auto split = [&](unsigned q) -> int64_t {
+                    int64_t target = (int64_t)(N * q / TT);
+                    return (int64_t)(std::lower_bound(ix->vtx_off.begin(), ix->vtx_off.end(), target) - ix->vtx_off.begin());
+                };
+                int64_t va = t == 0 ? 0 : split(t), vb = t + 1 == TT ? ix->V + 1 : split(t + 1);
+                for (size_t gi = 0; gi < N; gi++) {
+                    int64_t a = ix->pos_id[gi] < 0 ? -(int64_t)ix->pos_id[gi] : (int64_t)ix->pos_id[gi];
+                    if (a >= va && a < vb) ix->occ_g[(size_t)cursor[(size_t)a]++] = (int64_t)gi;
                 }
+            });
+        }
+        // ---- sequences
+        for (auto &th : fasta_pool) th.join();
+        for (int i = 0; i < n_fasta; i++)
+            if (fasta_code[(size_t)i] != LCB_OK) throw Failure(fasta_code[(size_t)i], fasta_err[(size_t)i]);
+        for (auto &pf : per_file)
+            for (size_t r = 0; r < pf.seq.size(); r++) {
+                ix->fasta.name.push_back(std::move(pf.name[r]));
+                ix->fasta.seq.push_back(std::move(pf.seq[r]));
             }
-            for (auto &t : pool) t.join();
-            for (int i = 0; i < n_fasta; i++)
-                if (fasta_code[(size_t)i] != LCB_OK) throw Failure(fasta_code[(size_t)i], fasta_err[(size_t)i]);
-            for (auto &pf : per_file)
-                for (size_t r = 0; r < pf.seq.size(); r++) {
-                    ix->fasta.name.push_back(std::move(pf.name[r]));
-                    ix->fasta.seq.push_back(std::move(pf.seq[r]));
-                }
-            if ((int64_t)ix->fasta.seq.size() < ix->C)
-                throw Failure(LCB_ERR_FORMAT, "the graph refers to more sequences than the FASTA files contain");
-            // ---- the two characters the traversal needs per junction ----
-            ix->next_ch.resize(w);
-            ix->prev_rc.resize(w);
-            for (size_t gi = 0; gi < w; gi++) {
+        if ((int64_t)ix->fasta.seq.size() < ix->C)
+            throw Failure(LCB_ERR_FORMAT, "the graph refers to more sequences than the FASTA files contain");
+        // ---- the two characters the traversal needs per junction (junctionstorage.h:641-642)
+        ix->next_ch.resize(N);
+        ix->prev_rc.resize(N);
+        std::vector<int> bad(T, 0);
+        Parallel(T, [&](unsigned t, unsigned TT) {
+            for (size_t gi = N * t / TT; gi < N * (t + 1) / TT; gi++) {
                 const std::string &s = ix->fasta.seq[rec_chr[gi]];
                 size_t p = ix->pos_bp[gi];
-                if (p + (size_t)k > s.size()) throw Failure(LCB_ERR_FORMAT, "junction position beyond the end of its sequence (wrong -k or FASTA?)");
+                if (p + (size_t)k > s.size()) {
+                    bad[t] = 1;
+                    continue;
+                }
                 ix->next_ch[gi] = p + (size_t)k < s.size() ? (uint8_t)s[p + (size_t)k] : 0;
                 ix->prev_rc[gi] = p > 0 ? Complement((uint8_t)s[p - 1]) : (uint8_t)'N';
             }
-        }
+        });
+        for (unsigned t = 0; t < T; t++)
+            if (bad[t]) throw Failure(LCB_ERR_FORMAT, "junction position beyond the end of its sequence (wrong -k or FASTA?)");
     } catch (Failure &e) {
         if (err && errlen) snprintf(err, errlen, "%s", e.what());
         int code = e.code;

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -154,10 +155,13 @@ int main(int argc, char **argv)
     auto t0 = std::chrono::steady_clock::now();
     printf("Loading the graph...\n");
     fflush(stdout);
+    std::thread warm([&o]() { lcb_warmup(o.gpu); }); // CUDA context + scratch while the files are parsed
     std::vector<const char *> files;
     for (auto &f : o.fasta) files.push_back(f.c_str());
     lcb_index *index = nullptr;
-    if (lcb_index_load(o.graph.c_str(), files.data(), (int)files.size(), (int)o.k, (int)o.a, &index, err, sizeof err)) {
+    int load_rc = lcb_index_load(o.graph.c_str(), files.data(), (int)files.size(), (int)o.k, (int)o.a, &index, err, sizeof err);
+    warm.join();
+    if (load_rc) {
         fprintf(stderr, "error: %s\n", err);
         return 1;
     }

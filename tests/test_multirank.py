@@ -1,0 +1,163 @@
+"""World-size-2 (gloo, CPU) test of the multi-rank protocol of DESIGN.md section 7, the one lcb_device.cu runs over
+NCCL: seeds of a window dealt round-robin over ranks, every rank evaluates / validates only its own seeds against a
+replicated epoch array, claims meet in an all-reduce(MIN), dirty counters in an all-reduce(SUM), block ids are a prefix
+sum over all-reduced per-seed counts.  Seed evaluation itself is the oracle's epoch-threshold Process
+(oracle/liblcb_oracle_epoch.so), so the test checks the PROTOCOL -- sharding, reductions, termination, ordered emit --
+independently of CUDA.  The result must equal the sequential oracle's blocksInstance_ list."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INF = 0xFFFFFFFF
+PHASE = 256
+
+
+def _worker(rank, world, port, graph, fastas, k, W, out_queue):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "liblcb_oracle_epoch.so"))
+    L.lcbo_load.restype = C.c_void_p
+    L.lcbo_load.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    L.lcbo_num_records.restype = C.c_int64
+    L.lcbo_num_records.argtypes = [C.c_void_p]
+    L.lcbo_enumerate_seeds.restype = C.c_int64
+    L.lcbo_enumerate_seeds.argtypes = [C.c_void_p]
+    L.lcbo_epoch_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.lcbo_epoch_process.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.lcbo_get_index.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+    err = C.create_string_buffer(256)
+    files = (C.c_char_p * len(fastas))(*[f.encode() for f in fastas])
+    h = L.lcbo_load(graph.encode(), files, len(fastas), k, 150, err, 256)
+    N = L.lcbo_num_records(h)
+    S = L.lcbo_enumerate_seeds(h)
+    L.lcbo_epoch_prepare(h, 50, 200, 200, 8)
+    pos_bp = np.zeros(N, np.uint32)
+    L.lcbo_get_index(h, None, None, pos_bp.ctypes.data, None, None, None, None, None)
+    inst_buf, rs_buf, n_rs = np.zeros(2 * 4096, np.int64), np.zeros(2 * 65536, np.int64), C.c_int()
+
+    def process(i, thresh, E):
+        n = L.lcbo_epoch_process(h, i, thresh, E.ctypes.data, inst_buf.ctypes.data, 4096, rs_buf.ctypes.data, 65536, C.byref(n_rs))
+        assert n <= 4096 and n_rs.value <= 65536
+        return inst_buf[:2 * n].reshape(-1, 2).copy(), rs_buf[:2 * n_rs.value].reshape(-1, 2).copy()
+
+    def edges(inst):
+        fg = inst[:, 0] & ((1 << 62) - 1)
+        lo, hi = np.minimum(fg, inst[:, 1]), np.maximum(fg, inst[:, 1]) - 1
+        return [np.arange(a, b + 1) for a, b in zip(lo, hi)]
+
+    def conflicts(inst, E, limit):
+        return len(inst) > 1 and any((E[e] < limit).any() for e in edges(inst))
+
+    def changed(rs, Ea, Eb, limit):
+        for lo, hi in rs:
+            if ((Ea[lo:hi + 1] < limit) != (Eb[lo:hi + 1] < limit)).any():
+                return True
+        return False
+
+    Ebase = np.full(N, INF, np.uint32)
+    out, blocks_before, rounds_total = [], 0, 0
+    for w0 in range(0, S, W):
+        n = min(W, S - w0)
+        own = list(range(rank, n, world))
+        r0, R0, r1, R1, conf = {}, {}, {}, {}, {j: False for j in own}
+        need0, need1 = set(own), set()
+        Ecur = Ebase.copy()
+        while True:
+            rounds_total += 1
+            for j in sorted(need0):
+                i = w0 + j
+                r0[j], R0[j] = process(i, i // PHASE * PHASE, Ecur)
+                conf[j] = conflicts(r0[j], Ecur, i)
+                if conf[j] and j not in r1:
+                    need1.add(j)
+                if not conf[j]:
+                    r1.pop(j, None)
+            for j in sorted(need1):
+                r1[j], R1[j] = process(w0 + j, w0 + j, Ecur)
+            need0, need1 = set(), set()
+            fin = {j: (r1[j] if conf[j] else r0[j]) for j in own}
+            Enew = Ebase.astype(np.int64)
+            for j in own:
+                if len(fin[j]) > 1:
+                    for e in edges(fin[j]):
+                        Enew[e] = np.minimum(Enew[e], w0 + j)
+            t = torch.from_numpy(Enew)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # <- the exchange step (ncclAllReduce(min) on the device)
+            Enew = t.numpy().astype(np.uint32)
+            dirty = 0
+            for j in own:
+                i = w0 + j
+                if changed(R0[j], Ecur, Enew, i // PHASE * PHASE):
+                    need0.add(j)
+                    r1.pop(j, None)
+                    dirty += 1
+                    continue
+                c = conflicts(r0[j], Enew, i)
+                dirty += c != conf[j]
+                conf[j] = c
+                if c and (j not in r1 or changed(R1[j], Ecur, Enew, i)):
+                    need1.add(j)
+                    dirty += 1
+                if not c:
+                    r1.pop(j, None)
+            d = torch.tensor([dirty])
+            dist.all_reduce(d, op=dist.ReduceOp.SUM)
+            Ecur = Enew
+            if d.item() == 0:
+                break
+        Ebase = Ecur
+        counts = np.zeros(n, np.int64)
+        for j in own:
+            f = r1[j] if conf[j] else r0[j]
+            counts[j] = len(f) if len(f) > 1 else 0
+        t = torch.from_numpy(counts)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ids = blocks_before + np.cumsum(counts > 0)
+        for j in own:
+            f = r1[j] if conf[j] else r0[j]
+            if len(f) > 1:
+                for fgs, bg in f:
+                    pos, fg = bool(fgs >> 62), int(fgs & ((1 << 62) - 1))
+                    if pos:
+                        out.append((w0 + j, int(ids[j]), int(pos_bp[fg]), int(pos_bp[bg]) + k))
+                    else:
+                        out.append((w0 + j, -int(ids[j]), int(pos_bp[bg]), int(pos_bp[fg]) + k))
+        blocks_before = int(ids[-1]) if n else blocks_before
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        out_queue.put((sum(gathered, []), rounds_total))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("window", [1024, 4096])
+def test_two_rank_protocol_matches_sequential_oracle(star_small, window):
+    import torch.multiprocessing as mp
+    from oracle_binding import Oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29620 + window % 97
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, star_small.graph, star_small.fastas, star_small.k, window, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rows, rounds = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ob = Oracle(star_small.graph, star_small.fastas, star_small.k, star_small.a).find_blocks(star_small.m, star_small.b)
+    # stable sort by seed index keeps each rank's instance order, i.e. the commit order
+    rows.sort(key=lambda r: r[0])
+    assert len(rows) == len(ob["id"]) > 1000
+    assert [r[1] for r in rows] == ob["id"].tolist()
+    assert [r[2] for r in rows] == ob["start"].tolist()
+    assert [r[3] for r in rows] == ob["end"].tolist()
+    assert rounds >= 2
