@@ -28,6 +28,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lcb_traverse.cuh"
@@ -401,13 +402,16 @@ __global__ void k_seed_enum(Index ix, unsigned *__restrict__ per_vertex, const u
     unsigned emitted = 0;
     unsigned w = FILL ? offset[t] : 0;
     for (unsigned a = o0; a < o1; a++) {
-        const int ga = (int)ix.occ[a];
-        const bool pa = ix.rec[ga].x == v;
-        const unsigned char ca = pa ? ix.chs[ga].x : ix.chs[ga].y;
+        const int2 oa = ix.occ[a];
+        const int ga = oa.x & 0x7FFFFFFF;
+        const bool pa = (oa.x < 0) == (v < 0);
+        const int4 ra = ix.rec[ga];
+        const unsigned char ca = pa ? rec_next_ch(ra) : rec_prev_rc(ra);
         bool first = true;
         for (unsigned b = o0; b < a && first; b++) {
-            const int gb = (int)ix.occ[b];
-            const unsigned char cb = ix.rec[gb].x == v ? ix.chs[gb].x : ix.chs[gb].y;
+            const int2 ob = ix.occ[b];
+            const int4 rb = ix.rec[ob.x & 0x7FFFFFFF];
+            const unsigned char cb = ((ob.x < 0) == (v < 0)) ? rec_next_ch(rb) : rec_prev_rc(rb);
             first = cb != ca;
         }
         if (!first) continue;
@@ -416,10 +420,11 @@ __global__ void k_seed_enum(Index ix, unsigned *__restrict__ per_vertex, const u
         unsigned long long rank = 0, base = 1;
         unsigned long long best = ~0ULL; // (pos, chr) packed for the lexicographic min
         for (unsigned b = a; b < o1; b++) {
-            const int gb = (int)ix.occ[b];
-            const int2 rb = ix.rec[gb];
-            const bool pb = rb.x == v;
-            const unsigned char cb = pb ? ix.chs[gb].x : ix.chs[gb].y;
+            const int2 ob = ix.occ[b];
+            const int gb = ob.x & 0x7FFFFFFF;
+            const int4 rb = ix.rec[gb];
+            const bool pb = (ob.x < 0) == (v < 0);
+            const unsigned char cb = pb ? rec_next_ch(rb) : rec_prev_rc(rb);
             if (cb != ca) continue;
             count++;
             int lo = 0, hi = ix.C;
@@ -580,9 +585,9 @@ struct lcb_ctx {
     cudaStream_t stream = nullptr;
     // index
     Index ix{};
-    int2 *d_rec = nullptr;
-    uchar2 *d_chs = nullptr;
-    uint32_t *d_vtx_off = nullptr, *d_occ = nullptr, *d_chr_off = nullptr;
+    int4 *d_rec = nullptr;
+    int2 *d_occ = nullptr;
+    uint32_t *d_vtx_off = nullptr, *d_chr_off = nullptr;
     uint32_t *d_E[3] = {nullptr, nullptr, nullptr};
     // seeds
     uint64_t n_seeds = 0;
@@ -836,49 +841,64 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     // ---- pack + upload the index (8 B + 2 B per record, u32 CSR) ----
     {
         // packed into ONE pinned staging buffer so the copies are true async DMA from page-locked memory
-        const size_t b_rec = sizeof(int2) * (size_t)N, b_chs = sizeof(uchar2) * (size_t)N, b_vo = sizeof(uint32_t) * ((size_t)V + 2),
-                     b_oc = sizeof(uint32_t) * (size_t)N, b_co = sizeof(uint32_t) * ((size_t)C + 1);
+        const size_t b_rec = sizeof(int4) * (size_t)N, b_occ = sizeof(int2) * (size_t)N, b_vo = sizeof(uint32_t) * ((size_t)V + 2),
+                     b_co = sizeof(uint32_t) * ((size_t)C + 1);
         auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
         unsigned char *stage = nullptr;
-        const size_t stage_bytes = up(b_rec) + up(b_chs) + up(b_vo) + up(b_oc) + up(b_co) + 256;
+        const size_t stage_bytes = up(b_rec) + up(b_occ) + up(b_vo) + up(b_co) + 256;
         CUDA_TRY(cached_alloc((void **)&stage, stage_bytes, -1, nullptr));
         struct Unpin {
             unsigned char *p;
             size_t n;
             ~Unpin() { cached_free(p, n, -1); }
         } unpin{stage, stage_bytes};
-        int2 *rec = (int2 *)stage;
-        uchar2 *chs = (uchar2 *)(stage + up(b_rec));
-        uint32_t *vo = (uint32_t *)((unsigned char *)chs + up(b_chs));
-        uint32_t *oc = (uint32_t *)((unsigned char *)vo + up(b_vo));
-        uint32_t *co = (uint32_t *)((unsigned char *)oc + up(b_oc));
-        for (int64_t g = 0; g < N; g++) {
-            rec[(size_t)g] = make_int2(v->pos_id[g], (int)v->pos_bp[g]);
-            chs[(size_t)g] = make_uchar2(v->next_ch[g], v->prev_rc[g]);
-            oc[(size_t)g] = (uint32_t)v->occ_g[g];
-        }
+        int4 *rec = (int4 *)stage;
+        int2 *oc = (int2 *)(stage + up(b_rec));
+        uint32_t *vo = (uint32_t *)((unsigned char *)oc + up(b_occ));
+        uint32_t *co = (uint32_t *)((unsigned char *)vo + up(b_vo));
         for (int64_t i = 0; i <= V; i++) vo[(size_t)i] = (uint32_t)v->vtx_off[i];
         vo[(size_t)V + 1] = vo[(size_t)V];
         for (int i = 0; i <= C; i++) co[(size_t)i] = (uint32_t)v->chr_off[i];
+        {
+            unsigned T = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+            std::vector<std::thread> pool;
+            std::vector<int> too_many(T, 0);
+            for (unsigned t = 0; t < T; t++)
+                pool.emplace_back([&, t]() {
+                    for (int64_t g = N * t / T; g < N * (t + 1) / T; g++) {
+                        const int32_t id = v->pos_id[g];
+                        const int64_t a = id < 0 ? -(int64_t)id : (int64_t)id;
+                        const int64_t o0 = v->vtx_off[a], cnt = v->vtx_off[a + 1] - o0;
+                        if (cnt > 65535) too_many[t] = 1;
+                        rec[(size_t)g] = make_int4(id, (int)v->pos_bp[g], (int)o0,
+                                                   (int)(((unsigned)cnt << 16) | ((unsigned)v->next_ch[g] << 8) | (unsigned)v->prev_rc[g]));
+                        const int64_t og = v->occ_g[g]; // occurrence slot g of the CSR (not record g)
+                        oc[(size_t)g] = make_int2((int)((unsigned)og | (v->pos_id[og] < 0 ? 0x80000000u : 0u)), (int)v->pos_bp[og]);
+                    }
+                });
+            for (auto &th : pool) th.join();
+            for (unsigned t = 0; t < T; t++)
+                if (too_many[t]) {
+                    ctx->error = "a junction occurs more than 65535 times: lower the abundance threshold (-a)";
+                    return LCB_ERR_ARG;
+                }
+        }
         int rc;
         if ((rc = dev_alloc(ctx, &ctx->d_rec, (size_t)N))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_chs, (size_t)N))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_occ, (size_t)N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
         for (int e = 0; e < 3; e++)
             if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, rec, sizeof(int2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_chs, chs, sizeof(uchar2) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_vtx_off, vo, sizeof(uint32_t) * ((size_t)V + 2), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, oc, sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_chr_off, co, sizeof(uint32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, rec, b_rec, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, oc, b_occ, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_vtx_off, vo, b_vo, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_chr_off, co, b_co, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        ctx->st.h2d_bytes = (uint64_t)N * (8 + 2 + 4) + (uint64_t)(V + 2) * 4 + (uint64_t)(C + 1) * 4;
+        ctx->st.h2d_bytes = (uint64_t)(b_rec + b_occ + b_vo + b_co);
     }
     ctx->st.ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     ctx->ix.rec = ctx->d_rec;
-    ctx->ix.chs = ctx->d_chs;
     ctx->ix.vtx_off = ctx->d_vtx_off;
     ctx->ix.occ = ctx->d_occ;
     ctx->ix.chr_off = ctx->d_chr_off;

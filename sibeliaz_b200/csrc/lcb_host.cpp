@@ -8,6 +8,7 @@
 #include "sibeliaz_lcb.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -204,6 +205,11 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
     try {
         ix->k = k;
         const unsigned T = WorkerCount();
+        const bool trace = getenv("LCB_LOAD_TRACE") != nullptr;
+        auto t_start = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (trace) fprintf(stderr, "[load] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+        };
         // ---- FASTA files on their own threads (each splits its bodies further), concurrently with the junction stream
         std::vector<FastaRecords> per_file((size_t)n_fasta);
         std::vector<std::string> fasta_err((size_t)n_fasta);
@@ -262,6 +268,7 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
             }
             seps[t + 1] = ns, recs[t + 1] = nr, tmax[t] = mx;
         });
+        lap("junction pass 1");
         int64_t max_abs = -1;
         for (unsigned t = 0; t < T; t++) {
             seps[t + 1] += seps[t];
@@ -293,6 +300,7 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
                 __atomic_fetch_add(&occ_count[(size_t)(id < 0 ? -id : id)], 1u, __ATOMIC_RELAXED);
             }
         });
+        lap("junction pass 2");
         ix->C = M ? (int32_t)chr_all[M - 1] + 1 : 0;
         // ---- abundance filter (strict <, junctionstorage.h:610) + compaction
         auto rchunk = [M](unsigned t, unsigned TT, size_t &lo, size_t &hi) {
@@ -325,6 +333,7 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
                     ++w;
                 }
         });
+        lap("filter + compaction");
         ix->chr_off.assign((size_t)ix->C + 1, 0);
         for (size_t gi = 0; gi < N; gi++) ++ix->chr_off[(size_t)rec_chr[gi] + 1];
         for (int32_t c = 0; c < ix->C; c++) ix->chr_off[(size_t)c + 1] += ix->chr_off[(size_t)c];
@@ -349,8 +358,10 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
                 }
             });
         }
+        lap("CSR");
         // ---- sequences
         for (auto &th : fasta_pool) th.join();
+        lap("FASTA joined");
         for (int i = 0; i < n_fasta; i++)
             if (fasta_code[(size_t)i] != LCB_OK) throw Failure(fasta_code[(size_t)i], fasta_err[(size_t)i]);
         for (auto &pf : per_file)
@@ -376,6 +387,7 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
                 ix->prev_rc[gi] = p > 0 ? Complement((uint8_t)s[p - 1]) : (uint8_t)'N';
             }
         });
+        lap("junction chars");
         for (unsigned t = 0; t < T; t++)
             if (bad[t]) throw Failure(LCB_ERR_FORMAT, "junction position beyond the end of its sequence (wrong -k or FASTA?)");
     } catch (Failure &e) {

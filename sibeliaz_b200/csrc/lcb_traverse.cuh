@@ -47,14 +47,20 @@ struct Inst { // Path::Instance (path.h:53-181) with cached end-point data; 56 b
 };
 constexpr unsigned kPos = 1u, kFFin = 2u, kBFin = 4u;
 
-struct Index { // device view of the SoA junction index
-    const int2 *rec;        // {id, bp} per record
-    const uchar2 *chs;      // {next_ch, prev_rc} per record
+struct Index { // device view of the junction index
+    // rec[g] = {id, bp, first occurrence slot of |id|, (#occurrences << 16) | (next_ch << 8) | prev_rc}: one 16-byte
+    // load per walk step yields the vertex, its position, where its occurrence list lives and both edge characters
+    const int4 *rec;
+    // occ[o] = {g | (stored id < 0 ? 1<<31 : 0), bp}: an occurrence's strand and position without touching rec[g]
+    const int2 *occ;
     const uint32_t *vtx_off;
-    const uint32_t *occ;
     const uint32_t *chr_off;
     int C, N, V;
 };
+
+__device__ __forceinline__ unsigned char rec_next_ch(const int4 &r) { return (unsigned char)((unsigned)r.w >> 8); }
+__device__ __forceinline__ unsigned char rec_prev_rc(const int4 &r) { return (unsigned char)r.w; }
+__device__ __forceinline__ unsigned rec_occ_count(const int4 &r) { return (unsigned)r.w >> 16; }
 
 struct Params {
     int k, b, m, flank, depth;
@@ -342,11 +348,11 @@ struct Occ {
 __device__ __forceinline__ Occ load_occurrence(const Ctx &c, unsigned o, int vertex)
 {
     Occ r;
-    r.g = (int)__ldg(c.ix.occ + o);
-    int2 rc = __ldg(c.ix.rec + r.g);
-    r.v_id = rc.x;
-    r.bp = (unsigned)rc.y;
-    r.pos = rc.x == vertex; // JunctionIterator::IsPositiveStrand, junctionstorage.h:408-411
+    const int2 oc = __ldg(c.ix.occ + o);
+    r.g = oc.x & 0x7FFFFFFF;
+    r.bp = (unsigned)oc.y;
+    r.pos = (oc.x < 0) == (vertex < 0); // JunctionIterator::IsPositiveStrand: stored id == vertex (junctionstorage.h:408-411)
+    r.v_id = 0;
     chr_bounds(c.ix, r.g, r.clo, r.chi);
     bool has = r.pos || r.g > r.clo; // IsUsed on the - strand at idx 0 is false (junctionstorage.h:277-282)
     r.flag = has ? (r.pos ? r.g : r.g - 1) : -1;
@@ -368,8 +374,8 @@ __device__ __forceinline__ void path_init(Ctx &c, int vid, unsigned char ch)
         bool match = false;
         if (o < o1) {
             q = load_occurrence(c, o, vid);
-            uchar2 cc = __ldg(c.ix.chs + q.g);
-            match = (q.pos ? cc.x : cc.y) == ch; // seqIt.GetChar(), junctionstorage.h:234-243
+            const int4 rr = __ldg(c.ix.rec + q.g);
+            match = (q.pos ? rec_next_ch(rr) : rec_prev_rc(rr)) == ch; // seqIt.GetChar(), junctionstorage.h:234-243
         }
         unsigned mm = __ballot_sync(kFull, match);
         while (mm) { // occurrences in (chr, idx) order
@@ -408,16 +414,155 @@ __device__ __forceinline__ bool scan_used(Ctx &c, int lo, int hi)
 // Path::PointPushBack / PointPushFront with their workers (path.h:430-602).  BACK: `v` = e.GetEndVertex(),
 // FRONT: `v` = e.GetStartVertex().  e_ch_g/e_ch_pos locate the junction whose char is e.GetChar();
 // e_other is e.GetEndVertex() for FRONT (the far-branch test `start1.GetVertexId() != e.GetEndVertex()`).
-__device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int len, int e_ch_g, bool e_ch_pos, int e_other)
+// Fast path of the PointPush* workers: all occurrences of the pushed vertex (<= 32) lie on distinct chromosomes,
+// so they cannot see each other's effects inside this push; every lane evaluates one occurrence against the
+// pre-push state (multiset neighbours, Within, Compatible incl. its epoch scan), then the effects are applied in
+// occurrence order (goodInstance_ appends, new instances).  Returns false when the precondition does not hold.
+__device__ __forceinline__ bool push_parallel(Ctx &c, const bool BACK, int v, int dist, unsigned o0, unsigned cnt, int e_ch_g,
+                                              bool e_ch_pos, int e_other)
+{
+    const bool live = (unsigned)c.lane < cnt;
+    Occ q;
+    q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = -1 - c.lane, q.chi = 0, q.v_id = 0;
+    if (live) q = load_occurrence(c, o0 + (unsigned)c.lane, v);
+    {
+        const unsigned peers = __match_any_sync(kFull, q.clo);
+        if (__any_sync(kFull, live && (peers & (peers - 1)) != 0)) return false;
+    }
+    int outcome = 0, cand = -1, scan_lo = 0, scan_hi = -1; // 0 skip, 1 extend, 2 new instance, 3 found used
+    if (live) {
+        const int n = c.ninst;
+        int ub = n;
+        for (int p = 0; p < n; p++)
+            if (c.inst[c.ord[p]].key > q.g) {
+                ub = p;
+                break;
+            }
+        int hi_id = -1, lo_id = -1;
+        if (ub < n) {
+            int id = c.ord[ub];
+            if (c.inst[id].key < q.chi) hi_id = id;
+        }
+        if (ub > 0) {
+            int id = c.ord[ub - 1];
+            if (c.inst[id].key >= q.clo) lo_id = id;
+        }
+        bool within = false;
+        if (hi_id >= 0) {
+            int a = c.inst[hi_id].fg, b = c.inst[hi_id].bg;
+            within = q.g >= min(a, b) && q.g <= max(a, b);
+        }
+        if (!within) {
+            cand = (q.pos == BACK) ? lo_id : hi_id;
+            bool extend = false;
+            int cend_v = 0;
+            if (cand >= 0) {
+                const Inst &I = c.inst[cand];
+                const bool cpos = (I.flags & kPos) != 0;
+                const int cg = BACK ? I.bg : I.fg;
+                const unsigned cbp = BACK ? I.bbp : I.fbp;
+                const int cdist = BACK ? I.bdist : I.fdist;
+                cend_v = BACK ? I.bv : I.fv;
+                if (cpos == q.pos) {
+                    long long rd = BACK ? (long long)q.bp - (long long)cbp : (long long)cbp - (long long)q.bp;
+                    if (!q.pos) rd = -rd;
+                    const long long ad = BACK ? (long long)dist - cdist : (long long)cdist - dist;
+                    bool ok = rd >= 0;
+                    if (ok && (rd > c.pr.b || ad > c.pr.b)) {
+                        const int step = q.pos ? 1 : -1;
+                        ok = BACK ? (q.g == cg + step) : (cg == q.g + step);
+                        if (ok) {
+                            const int4 ce = __ldg(c.ix.rec + e_ch_g), cs = __ldg(c.ix.rec + (BACK ? cg : q.g));
+                            ok = (q.pos ? rec_next_ch(cs) : rec_prev_rc(cs)) == (e_ch_pos ? rec_next_ch(ce) : rec_prev_rc(ce));
+                            if (!BACK) ok = ok && I.fv == e_other;
+                        }
+                    }
+                    if (ok) {
+                        scan_lo = min(cg, q.g);
+                        scan_hi = max(cg, q.g) - 1;
+                        for (int f = scan_lo; f <= scan_hi && ok; f++) ok = !(__ldg(c.E + f) < c.thresh);
+                    }
+                    extend = ok;
+                }
+            }
+            outcome = (extend && cend_v != v) ? 1 : (!q.used ? 2 : 3);
+        }
+    }
+    c.ct.scan += (unsigned long long)__reduce_add_sync(kFull, scan_lo <= scan_hi ? (unsigned)(scan_hi - scan_lo + 1) : 0u);
+    // ---- apply.  Candidates of different lanes are different instances (different chromosomes).
+    bool newly_good = false;
+    if (live && cand >= 0 && scan_lo <= scan_hi) inst_extend_reads(c.inst[cand], scan_lo, scan_hi);
+    if (outcome == 1) {
+        Inst &I = c.inst[cand];
+        const unsigned fin = BACK ? kBFin : kFFin;
+        if (!(I.flags & fin)) {
+            unsigned a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
+            const bool prev_good = (long long)a >= c.pr.m;
+            if (BACK) {
+                I.bg = q.g, I.bv = v, I.bbp = q.bp, I.bdist = dist;
+                if (q.pos) I.key = q.g;
+            } else {
+                I.fg = q.g, I.fv = v, I.fbp = q.bp, I.fdist = dist;
+                if (!q.pos) I.key = q.g;
+            }
+            a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
+            newly_good = !prev_good && (long long)a >= c.pr.m;
+            if (q.flag >= 0) inst_extend_reads(I, q.flag, q.flag);
+            if (q.used) I.flags |= fin;
+        }
+    }
+    const unsigned lt = (1u << c.lane) - 1u;
+    const unsigned gm = __ballot_sync(kFull, newly_good);
+    if (newly_good) c.good[c.ngood + __popc(gm & lt)] = (unsigned short)cand;
+    c.ngood += __popc(gm);
+    const unsigned om = __ballot_sync(kFull, outcome == 3);
+    if (om) {
+        if (c.nrs + __popc(om) > kReadSetMax) {
+            c.err = LCB_ERR_CAPACITY;
+            return true;
+        }
+        if (outcome == 3) c.ar.rs[c.nrs + __popc(om & lt)] = make_int2(q.flag, q.flag);
+        c.nrs += __popc(om);
+    }
+    __syncwarp();
+    unsigned nm = __ballot_sync(kFull, outcome == 2);
+    while (nm) { // allInstance_ order == occurrence order
+        const int src = ffs_lane(nm);
+        nm &= nm - 1;
+        const int g = __shfl_sync(kFull, q.g, src);
+        const bool pos = __shfl_sync(kFull, (int)q.pos, src);
+        const unsigned bp = __shfl_sync(kFull, q.bp, src);
+        const int flag = __shfl_sync(kFull, q.flag, src);
+        const int clo = __shfl_sync(kFull, q.clo, src), chi = __shfl_sync(kFull, q.chi, src);
+        const int at = ord_upper_bound(c, g);
+        inst_insert(c, at, g, pos, v, bp, dist, flag, clo, chi);
+        if (c.err) return true;
+    }
+    return true;
+}
+
+// occ_first/occ_count: the pushed vertex's occurrence range when the caller already holds it (rec[g].z/.w), else -1
+__device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int len, int e_ch_g, bool e_ch_pos, int e_other,
+                                          int occ_first, int occ_count)
 {
     if (hash_find(c.hash, c.hmask, v) != kNotSet) return false; // vertex already in the path
     const int dist = BACK ? c.right_flank + len : c.left_flank - len;
     hash_insert(c, v, dist);
     if (c.err) return true;
-    int av = v < 0 ? -v : v;
-    unsigned o0 = __ldg(c.ix.vtx_off + av), o1 = __ldg(c.ix.vtx_off + av + 1);
+    unsigned o0, o1;
+    if (occ_count >= 0) {
+        o0 = (unsigned)occ_first, o1 = o0 + (unsigned)occ_count;
+    } else {
+        int av = v < 0 ? -v : v;
+        o0 = __ldg(c.ix.vtx_off + av), o1 = __ldg(c.ix.vtx_off + av + 1);
+    }
     c.ct.occ += o1 - o0;
-    for (unsigned base = o0; base < o1; base += 32) {
+    bool handled = false;
+    if (o1 - o0 <= 32u) {
+        handled = push_parallel(c, BACK, v, dist, o0, o1 - o0, e_ch_g, e_ch_pos, e_other);
+        if (c.err) return true;
+    }
+    for (unsigned base = o0; base < o1 && !handled; base += 32) {
         unsigned o = base + (unsigned)c.lane;
         Occ q;
         q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = 0, q.chi = 0;
@@ -465,10 +610,9 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
                         const bool adjacent = BACK ? (g == cg + step) : (cg == g + step);
                         ok = adjacent;
                         if (ok) {
-                            uchar2 ce = __ldg(c.ix.chs + e_ch_g);
-                            unsigned char ech = e_ch_pos ? ce.x : ce.y;
-                            uchar2 cs = __ldg(c.ix.chs + (BACK ? cg : g));
-                            unsigned char sch = pos ? cs.x : cs.y;
+                            const int4 ce = __ldg(c.ix.rec + e_ch_g), cs = __ldg(c.ix.rec + (BACK ? cg : g));
+                            unsigned char ech = e_ch_pos ? rec_next_ch(ce) : rec_prev_rc(ce);
+                            unsigned char sch = pos ? rec_next_ch(cs) : rec_prev_rc(cs);
                             ok = sch == ech;
                             if (!BACK) ok = ok && I.fv == e_other;
                         }
@@ -599,7 +743,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
             int vid = 0, flag = -1;
             bool used = false, inpath = false;
             if (in_range) {
-                int2 rc = __ldg(c.ix.rec + g);
+                const int4 rc = __ldg(c.ix.rec + g);
                 vid = pos ? rc.x : -rc.x;
                 long long dp = (long long)(unsigned)rc.y - (long long)obp;
                 if (dp < 0) dp = -dp;
@@ -673,34 +817,164 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
     return best;
 }
 
+struct Staged { // per-lane copy of the look-ahead walks of the last MostPopularVertex (fast path)
+    int vid, o0;
+    unsigned bp, w;
+    int base; // first lane of the winning walk (uniform)
+    unsigned obp;
+    bool valid;
+};
+
+// MostPopularVertex when <= 4 instances sit on the path end and every look-ahead fits its lane segment: all walks are
+// fetched at once (one lane per (instance, depth)) and the vote is evaluated in closed form instead of being replayed:
+// counts are order-independent sums; the running arg-max of the reference ends on -- among the vertices whose FINAL
+// count is the maximum M -- the one whose last increment came from the smallest origin (strand, chr, idx), earliest
+// such event on ties (proof sketch in DESIGN.md section 4).  Returns 0 when the general path must be taken.
+__device__ __forceinline__ int mpv_fast(Ctx &c, bool forward, bool try_used, Next &best, Staged &sg)
+{
+    const int start_vid = forward ? c.right_vertex : c.left_vertex;
+    const bool use_good = c.ngood >= 2;
+    const int n = use_good ? c.ngood : c.ninst;
+    best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
+    sg.valid = false;
+    if (n > 32) return 0;
+    int my_id = 0;
+    bool elig = false;
+    if (c.lane < n) {
+        my_id = use_good ? (int)c.good[c.lane] : c.lane;
+        elig = (forward ? c.inst[my_id].bv : c.inst[my_id].fv) == start_vid;
+    }
+    const unsigned em = __ballot_sync(kFull, elig);
+    const int E = __popc(em);
+    if (E == 0) return 1;
+    if (E > 4) return 0;
+    const int L = 32 / E; // 32, 16, 10, 8 lanes (= depths) per instance
+    const int slot = c.lane / L, d = c.lane % L + 1;
+    const bool lane_on = slot < E;
+    const int src = lane_on ? (int)__fns(em, 0, slot + 1) : 0;
+    const int id = __shfl_sync(kFull, my_id, src);
+    const Inst &I = c.inst[id];
+    const bool pos = (I.flags & kPos) != 0;
+    const int og = forward ? I.bg : I.fg;
+    const unsigned obp = forward ? I.bbp : I.fbp;
+    const unsigned weight = (I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp) + 1u;
+    const int clo = I.clo, chi = I.chi;
+    const int step = (forward == pos) ? 1 : -1;
+    const int g = og + step * d;
+    bool in_range = lane_on && g >= clo && g < chi;
+    int vid = 0, flag = -1, o0 = 0;
+    unsigned bp = 0, w = 0;
+    bool used = false, inpath = false;
+    if (in_range) {
+        const int4 rc = __ldg(c.ix.rec + g);
+        vid = pos ? rc.x : -rc.x;
+        bp = (unsigned)rc.y, o0 = rc.z, w = (unsigned)rc.w;
+        long long dp = (long long)bp - (long long)obp;
+        if (dp < 0) dp = -dp;
+        in_range = d < c.pr.depth || dp <= c.pr.b;
+        if (in_range) {
+            const bool has = pos || g > clo;
+            flag = has ? (pos ? g : g - 1) : -1;
+            if (has && !try_used) used = __ldg(c.E + flag) < c.thresh;
+            inpath = hash_find(c.hash, c.hmask, vid) != kNotSet;
+        }
+    }
+    const bool ok = in_range && !inpath && !used;
+    const unsigned seg = !lane_on ? 0u : (L == 32 ? kFull : (((1u << L) - 1u) << (slot * L)));
+    const unsigned fail = __ballot_sync(kFull, lane_on && !ok) & seg;
+    const int nok = fail ? ffs_lane(fail) - slot * L : L;
+    if (__any_sync(kFull, lane_on && nok == L)) return 0; // a walk needs more depth than its segment offers
+    const bool active = lane_on && d - 1 < nok;
+    { // loop-body executions (walk steps) and the epochs each walk depended on
+        const bool stop_in_body = lane_on && d - 1 == nok && in_range;
+        c.ct.walk += (unsigned long long)__popc(__ballot_sync(kFull, active || stop_in_body));
+        const bool dep = flag >= 0 && !try_used && (active || (lane_on && d - 1 == nok && in_range && !inpath));
+        for (int s = 0; s < E; s++) {
+            const int lo = __reduce_min_sync(kFull, dep && slot == s ? flag : 0x7FFFFFFF);
+            const int hi = __reduce_max_sync(kFull, dep && slot == s ? flag : -1);
+            const int sid = __shfl_sync(kFull, id, s * L);
+            if (lo <= hi && c.lane == 0) inst_extend_reads(c.inst[sid], lo, hi);
+        }
+        __syncwarp();
+    }
+    const unsigned long long key = active ? (unsigned long long)(unsigned)vid : (0x100000000ull | (unsigned)c.lane);
+    const unsigned peers = __match_any_sync(kFull, key);
+    unsigned total = 0;
+    for (int s = 0; s < E; s++) {
+        const unsigned segs = L == 32 ? kFull : (((1u << L) - 1u) << (s * L));
+        total += (unsigned)__popc(peers & segs) * __shfl_sync(kFull, weight, s * L);
+    }
+    const bool is_last = active && c.lane == 31 - __clz((int)peers);
+    const unsigned M = __reduce_max_sync(kFull, active ? total : 0u);
+    const bool cand = is_last && total == M;
+    const unsigned okey = (pos ? 0x80000000u : 0u) | (unsigned)og; // origin order: - strand first, then (chr, idx)
+    const unsigned kmin = __reduce_min_sync(kFull, cand ? okey : 0xFFFFFFFFu);
+    const unsigned win = __ballot_sync(kFull, cand && okey == kmin);
+    if (!win) return 1;
+    const int wl = ffs_lane(win);
+    best.vid = __shfl_sync(kFull, vid, wl);
+    best.og = __shfl_sync(kFull, og, wl);
+    best.opos = __shfl_sync(kFull, (int)pos, wl) != 0;
+    best.d = __shfl_sync(kFull, d, wl);
+    sg.vid = vid, sg.o0 = o0, sg.bp = bp, sg.w = w;
+    sg.base = (wl / L) * L;
+    sg.obp = __shfl_sync(kFull, obp, wl);
+    sg.valid = true;
+    return 1;
+}
+
 // ExtendPathForward / ExtendPathBackward (blocksfinder.h:770-895)
 __device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &best_size, long long &best_score, long long &now_score)
 {
     Next nx;
+    Staged sg;
     nx.vid = 0;
+    sg.valid = false;
     for (int attempt = 0; attempt < 2 && nx.vid == 0 && !c.err; attempt++) { // forward retries with tryUsed (:782-785)
         if (attempt == 1 && !FORWARD) break;
-        nx = most_popular_vertex(c, FORWARD, attempt == 1);
+        if (!mpv_fast(c, FORWARD, attempt == 1, nx, sg)) {
+            sg.valid = false;
+            nx = most_popular_vertex(c, FORWARD, attempt == 1);
+        }
     }
     if (c.err || nx.vid == 0) return false;
     bool success = false;
     const int step = (FORWARD == nx.opos) ? 1 : -1;
-    int prev_v = 0;
+    int prev_v = FORWARD ? c.right_vertex : c.left_vertex; // vertex of the origin junction
     unsigned prev_bp = 0;
-    for (int j0 = 0; j0 <= nx.d; j0 += 32) { // junctions og .. og+step*d, re-read (cache-hot)
-        int j = j0 + c.lane;
-        int2 rc = make_int2(0, 0);
-        if (j <= nx.d) rc = __ldg(c.ix.rec + (nx.og + step * j));
-        int cnt = min(32, nx.d - j0 + 1);
-        for (int t = 0; t < cnt; t++) {
-            int idv = __shfl_sync(kFull, rc.x, t);
-            unsigned bp = (unsigned)__shfl_sync(kFull, rc.y, t);
-            int v = nx.opos ? idv : -idv;
-            int jj = j0 + t;
-            if (jj > 0) {
-                int len = (int)(bp > prev_bp ? bp - prev_bp : prev_bp - bp);
-                int g_prev = nx.og + step * (jj - 1), g_now = nx.og + step * jj;
-                bool ok = path_push(c, FORWARD, v, len, FORWARD ? g_prev : g_now, nx.opos, prev_v);
+    bool have_prev_bp = false;
+    if (sg.valid) prev_bp = sg.obp, have_prev_bp = true;
+    // `for (it = origin; it.GetVertexId() != next; ++it) push(it.Outgoing/IngoingEdge())`: stops at the FIRST junction
+    // of the walk that carries the chosen vertex (blocksfinder.h:789, :852)
+    for (int j0 = sg.valid ? 1 : 0; j0 <= nx.d; j0 += 32) {
+        int4 rc = make_int4(0, 0, 0, 0);
+        if (!sg.valid) { // general path: re-read the junctions og .. og+step*d (cache-hot)
+            int j = j0 + c.lane;
+            if (j <= nx.d) rc = __ldg(c.ix.rec + (nx.og + step * j));
+        }
+        const int cnt = sg.valid ? nx.d : min(32, nx.d - j0 + 1);
+        bool done = false;
+        for (int t = 0; t < cnt && !done; t++) {
+            const int jj = j0 + t;
+            int v, o_first, o_count;
+            unsigned bp;
+            if (sg.valid) {
+                const int ln = sg.base + jj - 1;
+                v = __shfl_sync(kFull, sg.vid, ln);
+                bp = __shfl_sync(kFull, sg.bp, ln);
+                o_first = __shfl_sync(kFull, sg.o0, ln);
+                o_count = (int)(__shfl_sync(kFull, sg.w, ln) >> 16);
+            } else {
+                const int idv = __shfl_sync(kFull, rc.x, t);
+                bp = (unsigned)__shfl_sync(kFull, rc.y, t);
+                o_first = __shfl_sync(kFull, rc.z, t);
+                o_count = (int)((unsigned)__shfl_sync(kFull, rc.w, t) >> 16);
+                v = nx.opos ? idv : -idv;
+            }
+            if (jj > 0 && have_prev_bp) {
+                const int len = (int)(bp > prev_bp ? bp - prev_bp : prev_bp - bp);
+                const int g_prev = nx.og + step * (jj - 1), g_now = nx.og + step * jj;
+                const bool ok = path_push(c, FORWARD, v, len, FORWARD ? g_prev : g_now, nx.opos, prev_v, o_first, o_count);
                 if (c.err) return false;
                 success = ok;
                 if (ok) {
@@ -711,10 +985,13 @@ __device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &bes
                         if (now_score > 0) snapshot_best(c);
                     }
                 }
+                done = v == nx.vid;
             }
             prev_v = v;
             prev_bp = bp;
+            have_prev_bp = true;
         }
+        if (done || sg.valid) break;
     }
     return success;
 }
@@ -747,7 +1024,7 @@ __device__ __forceinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
         if (c.ninst == 0) break; // a seed without live instances cannot move (MostPopularVertex finds nothing)
         for (int i = 0; i < replay && !c.err; i++) { // re-play the best right part (blocksfinder.h:271-284)
             int4 e = c.ar.redge[i];
-            path_push(c, true, e.x, e.y, e.z, e.w != 0, 0);
+            path_push(c, true, e.x, e.y, e.z, e.w != 0, 0, -1, -1);
         }
         if (c.err) return;
         while (true) {
