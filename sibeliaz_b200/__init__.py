@@ -227,7 +227,7 @@ class BlocksFinder:
         p.k, p.min_block, p.max_branch, p.max_flank, p.looking_depth = self.k, min_block, max_branch, max_flank, looking_depth
         p.device = self.device
         p.window_init, p.window_max = self._window
-        p.collect_counters = 1 if self._collect else 0
+        p.collect_counters = int(self._collect) if not isinstance(self._collect, bool) else (1 if self._collect else 0)
         rc = self._lib.lcb_create(C.byref(self.storage.view), C.byref(p), C.byref(self._ctx))
         if rc:
             msg = self._lib.lcb_last_error(self._ctx).decode() if self._ctx else "lcb_create failed"

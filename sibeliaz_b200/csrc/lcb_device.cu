@@ -54,6 +54,7 @@ struct Control { // device-resident round state, mirrored to pinned host memory 
     unsigned long long ct_walk, ct_occ, ct_scan, ct_score;
     unsigned long long runs0, runs1;
     unsigned n_blocks, n_out; // emit: blocks / instances of the current window
+    unsigned long long dbg[5];
 };
 
 struct Window { // per-window arrays, indexed by j = seed - w0
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kThreads) k_traverse(Index ix, Params pr, cons
     c.sm = &smem[wib];
     c.err = 0;
     c.ct.walk = c.ct.occ = c.ct.scan = c.ct.score = 0;
+    c.ct.pushes = c.ct.mpv_fast = c.ct.mpv_slow = c.ct.push_par = c.ct.push_ser = 0;
     {
         unsigned char *p = arena_base + warp_global * arena_stride;
         c.ar.inst = (Inst *)p, p += sizeof(Inst) * kInstMax;
@@ -130,7 +132,16 @@ __global__ void __launch_bounds__(kThreads) k_traverse(Index ix, Params pr, cons
         const unsigned j = list[idx];
         const unsigned i = w0 + j;
         c.thresh = slot == 0 ? (i / phase) * phase : i;
+        const long long t_begin = collect == 2 ? clock64() : 0;
+        const unsigned p_begin = c.ct.pushes, s_begin = c.ct.mpv_slow + c.ct.push_ser;
         process_seed(c, seed_vid[i], seed_ch[i]);
+        if (collect == 2 && lane == 0 && slot == 0) {
+            unsigned cyc = (unsigned)min((long long)0xFFFFFFFFll, clock64() - t_begin);
+            if (cyc > win.blk[j]) {
+                win.blk[j] = cyc;
+                win.out_off[j] = ((c.ct.pushes - p_begin) << 12) | min(4095u, c.ct.mpv_slow + c.ct.push_ser - s_begin);
+            }
+        }
         if (c.err) {
             if (lane == 0) atomicCAS(&ctl->err, 0u, (unsigned)c.err);
             break;
@@ -164,6 +175,11 @@ __global__ void __launch_bounds__(kThreads) k_traverse(Index ix, Params pr, cons
             atomicAdd(&ctl->ct_occ, c.ct.occ);
             atomicAdd(&ctl->ct_scan, c.ct.scan);
             atomicAdd(&ctl->ct_score, c.ct.score);
+            atomicAdd(&ctl->dbg[0], (unsigned long long)c.ct.pushes);
+            atomicAdd(&ctl->dbg[1], (unsigned long long)c.ct.mpv_fast);
+            atomicAdd(&ctl->dbg[2], (unsigned long long)c.ct.mpv_slow);
+            atomicAdd(&ctl->dbg[3], (unsigned long long)c.ct.push_par);
+            atomicAdd(&ctl->dbg[4], (unsigned long long)c.ct.push_ser);
         }
     }
 }
@@ -1189,12 +1205,17 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     ctx->st.windows = ctx->st.rounds = 0;
     double prev_rate = 0;
     int hold = 0;
+    const bool trace_rounds = getenv("LCB_TRACE_ROUNDS") != nullptr;
     for (unsigned w0 = 0; w0 < S;) {
         const unsigned n = std::min(W, S - w0);
         const auto t_window = std::chrono::steady_clock::now();
         // fresh window: every seed needs its speculative evaluation
         CUDA_TRY(cudaMemsetAsync(ctx->win.conf, 0, n, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(ctx->win.has1, 0, n, ctx->stream));
+        if (ctx->prm.collect_counters == 2) {
+            CUDA_TRY(cudaMemsetAsync(ctx->win.blk, 0, n * sizeof(unsigned), ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(ctx->win.out_off, 0, n * sizeof(unsigned), ctx->stream));
+        }
         // seeds are dealt round-robin over the ranks; a rank sees the others' seeds as "no result, empty read-set"
         const unsigned R = (unsigned)ctx->n_ranks, me = (unsigned)ctx->rank;
         const unsigned n_own = n > me ? (n - me + R - 1) / R : 0;
@@ -1210,6 +1231,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             z.n0 = n_own;
             z.ct_walk = ctx->h_ctl->ct_walk, z.ct_occ = ctx->h_ctl->ct_occ, z.ct_scan = ctx->h_ctl->ct_scan,
             z.ct_score = ctx->h_ctl->ct_score, z.runs0 = ctx->h_ctl->runs0, z.runs1 = ctx->h_ctl->runs1;
+            for (int q = 0; q < 5; q++) z.dbg[q] = ctx->h_ctl->dbg[q];
             *ctx->h_ctl = z;
             CUDA_TRY(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Control), cudaMemcpyHostToDevice, ctx->stream));
         }
@@ -1255,8 +1277,12 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
             trav_ms += ms;
-            cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3);
-            trav_ms += ms;
+            float ms1 = 0;
+            cudaEventElapsedTime(&ms1, ctx->ev2, ctx->ev3);
+            trav_ms += ms1;
+            if (trace_rounds)
+                fprintf(stderr, "[round] w0=%u n=%u round=%u speculative=%.3f ms rerun=%.3f ms next: n0=%u n1=%u dirty=%u\n", w0, n, round, ms, ms1,
+                        ctx->h_ctl->n0, ctx->h_ctl->n1, ctx->h_ctl->dirty);
             if (ctx->h_ctl->err) {
                 ctx->arena_dirty = true;
                 ctx->error = "a per-seed device buffer overflowed its hard cap (path, instance or read-set too large)";
@@ -1274,6 +1300,24 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
                 std::swap(Ecur, Enew);
             }
             if (ctx->h_ctl->dirty == 0) break;
+        }
+        if (trace_rounds && ctx->prm.collect_counters == 2) { // developer aid: slowest seeds of the window
+            std::vector<unsigned> c0(n), c1(n), rc0(n), rs0(n);
+            std::vector<int> vids(n);
+            cudaMemcpy(c0.data(), ctx->win.blk, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(c1.data(), ctx->win.out_off, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(rc0.data(), ctx->win.res_cnt[0], n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(rs0.data(), ctx->win.rs_cnt[0], n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(vids.data(), ctx->d_seed_vid + w0, n * 4, cudaMemcpyDeviceToHost);
+            std::vector<unsigned> idx(n);
+            for (unsigned q = 0; q < n; q++) idx[q] = q;
+            std::partial_sort(idx.begin(), idx.begin() + std::min(n, 6u), idx.end(), [&](unsigned a, unsigned b) { return c0[a] > c0[b]; });
+            unsigned long long sum = 0;
+            for (unsigned q = 0; q < n; q++) sum += c0[q];
+            fprintf(stderr, "[slow] window w0=%u: mean speculative %.1f kcycles; top:", w0, sum / 1e3 / n);
+            for (unsigned q = 0; q < std::min(n, 6u); q++)
+                fprintf(stderr, " (seed %u vid %d: %u kcyc, %u pushes, %u slow-path calls, %u inst, %u reads)", w0 + idx[q], vids[idx[q]], c0[idx[q]] / 1000, c1[idx[q]] >> 12, c1[idx[q]] & 4095, rc0[idx[q]], rs0[idx[q]]);
+            fprintf(stderr, "\n[slow] cumulative pushes %llu mpv fast/slow %llu/%llu push parallel/serial %llu/%llu\n", ctx->h_ctl->dbg[0], ctx->h_ctl->dbg[1], ctx->h_ctl->dbg[2], ctx->h_ctl->dbg[3], ctx->h_ctl->dbg[4]);
         }
         if (retry) {
             if (W <= phase) {

@@ -89,6 +89,7 @@ struct WarpArena { // per-warp HBM scratch (spill + variable-length logs)
 
 struct Counters {
     unsigned long long walk, occ, scan, score;
+    unsigned pushes, mpv_fast, mpv_slow, push_par, push_ser; // developer diagnostics
 };
 
 struct Ctx { // warp-uniform traversal state (registers)
@@ -557,10 +558,13 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
         o0 = __ldg(c.ix.vtx_off + av), o1 = __ldg(c.ix.vtx_off + av + 1);
     }
     c.ct.occ += o1 - o0;
+    c.ct.pushes++;
     bool handled = false;
     if (o1 - o0 <= 32u) {
         handled = push_parallel(c, BACK, v, dist, o0, o1 - o0, e_ch_g, e_ch_pos, e_other);
         if (c.err) return true;
+        if (handled) c.ct.push_par++;
+        else c.ct.push_ser++;
     }
     for (unsigned base = o0; base < o1 && !handled; base += 32) {
         unsigned o = base + (unsigned)c.lane;
@@ -932,7 +936,10 @@ __device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &bes
     sg.valid = false;
     for (int attempt = 0; attempt < 2 && nx.vid == 0 && !c.err; attempt++) { // forward retries with tryUsed (:782-785)
         if (attempt == 1 && !FORWARD) break;
-        if (!mpv_fast(c, FORWARD, attempt == 1, nx, sg)) {
+        if (mpv_fast(c, FORWARD, attempt == 1, nx, sg)) {
+            c.ct.mpv_fast++;
+        } else {
+            c.ct.mpv_slow++;
             sg.valid = false;
             nx = most_popular_vertex(c, FORWARD, attempt == 1);
         }

@@ -43,7 +43,7 @@ def main():
     st = sb.JunctionStorage(dbg, fas, a.k, 150)
     print("load %.2fs  records %d vertices %d" % (time.time() - t, st.n_records, st.n_vertices), flush=True)
     for rep in range(a.reps):
-        bf = sb.BlocksFinder(st, a.k, window_init=a.window, window_max=a.wmax or a.window, collect_counters=True)
+        bf = sb.BlocksFinder(st, a.k, window_init=a.window, window_max=a.wmax or a.window, collect_counters=(2 if os.environ.get('LCB_TRACE_ROUNDS') else True))
         t = time.time()
         bf.create(50, 200)
         t_create = time.time() - t
