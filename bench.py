@@ -272,10 +272,15 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:  # dram__bytes_read+write per launch from the committed ncu --set full captures of this kernel
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))["mean_dram_bytes_per_launch"]
+    except Exception:
+        pass
     achieved = (alg_bytes * steps / 1e9) / (trav_ms / 1000.0) if trav_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_traverse", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
-                "algorithmic_bytes_per_step": alg_bytes, "launches_per_step": trav_launches / steps,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/ncu_traffic_r1.json)", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes * steps / max(1, trav_launches), "launches_per_step": trav_launches / steps,
                 "kernel_ms_per_step": trav_ms / steps, "kernel_share_of_step": trav_ms / dev_ms if dev_ms else None,
                 "note": "latency-bound dependent random walk: see DESIGN.md section 5"}
     cpu = None
