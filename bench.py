@@ -141,8 +141,7 @@ def main():
     host_threads = min(32, os.cpu_count() or 1)  # the sibeliaz wrapper caps sibeliaz-lcb at 32 threads (sibeliaz:139)
     config = {"workload": "synthetic star 4x10 Mbp, 0.05 subs/site, seed 1, k=21, -b 200 -m 50 -a 150 (BASELINE configs[1])"
               if a.workload == "star4x10M_k21" else a.workload, "name": a.workload,
-              "l2_policy": "index + epochs + per-seed state are re-created/re-written every step and the traversal is a dependent "
-                           "random walk; no L2 flush is issued between steps (working set 35 MB < L2: cache-resident by nature)"}
+              "l2_flush": "a 256 MiB device buffer is overwritten before every timed step (outside the timed region)"}
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
@@ -214,6 +213,12 @@ def main():
         alg_bytes = 13 * counters["t_walk"] + 17 * counters["t_occ"] + counters["t_scan"] + 32 * counters["t_score"]
         orc.close()
 
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.add_(1)  # read+write of 256 MiB > 126 MB L2
+        torch.cuda.synchronize()
+
     # ---- value: index resident in HBM, whole FindBlocks equivalent per step, device-timed
     for _ in range(warmup):
         bf.reset_seeds()
@@ -224,6 +229,7 @@ def main():
     step_ms, trav_ms, trav_launches, launches = [], 0.0, 0, 0
     t0 = time.perf_counter()
     for _ in range(steps):
+        flush_l2()
         bf.reset_seeds()
         bf.find_blocks(M, B)
         step_ms.append(bf.stats["ms_step_device"])
@@ -246,13 +252,19 @@ def main():
     # ---- e2e: host arrays -> lcb_create (H2D) -> enumerate -> find (D2H) -> destroy, every step
     e2e_t, h2d, d2h = 0.0, 0, 0
     for it in range(1 + steps):
+        flush_l2()
         sync()
         t0 = time.perf_counter()
         f = make_finder()
+        t1 = time.perf_counter()
         blk = f.find_blocks(M, B)
+        t2 = time.perf_counter()
         h2d, d2h = f.stats["h2d_bytes"], f.stats["d2h_bytes"]
+        e2e_parts = {"create_ms": 1000 * (t1 - t0), "pack_h2d_ms": f.stats["ms_h2d"], "find_call_ms": 1000 * (t2 - t1),
+                     "enumerate_ms": f.stats["ms_enumerate"], "find_ms": f.stats["ms_find"], "d2h_ms": f.stats["ms_d2h"]}
         f.close()
         sync()
+        e2e_parts["destroy_ms"] = 1000 * (time.perf_counter() - t2)
         if it > 0:
             e2e_t += time.perf_counter() - t0
     if dist is not None:
@@ -299,7 +311,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "detail": {"records": int(n_records), "seeds": int(stats["n_seeds"]), "block_instances": int(stats["n_block_instances"]),
                        "windows": int(stats["windows"]), "rounds": int(stats["rounds"]), "traversals": int(stats["traversals_first"] + stats["traversals_rerun"]),
-                       "wall_ms_per_step": wall_ms / steps, "ms_enumerate": stats["ms_enumerate"], "oracle_counters": counters}}
+                       "wall_ms_per_step": wall_ms / steps, "e2e_last_step_parts": e2e_parts, "ms_enumerate": stats["ms_enumerate"], "oracle_counters": counters}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

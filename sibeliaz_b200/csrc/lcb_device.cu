@@ -91,7 +91,7 @@ struct Window { // per-window arrays, indexed by j = seed - w0
 // ------------------------------------------------------------------------------------------------
 // traversal kernel: persistent warps pull (seed, slot) items from a list
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
+__global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
                                                         const int *__restrict__ seed_vid,
                                                         const unsigned char *__restrict__ seed_ch, unsigned w0,
                                                         unsigned phase, int slot, const unsigned *__restrict__ list,
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kThreads) k_traverse(Index ix, Params pr, cons
         c.ar.hash = (int2 *)p, p += sizeof(int2) * kHashMax;
         c.ar.redge = (int4 *)p, p += sizeof(int4) * kPathMax;
         c.ar.vote = (int2 *)p, p += sizeof(int2) * kVoteMax;
+        c.ar.vlast = (unsigned *)p, p += sizeof(unsigned) * kVoteMax;
         c.ar.rs = (int2 *)p, p += sizeof(int2) * kReadSetMax;
         c.ar.hslot = (int *)p, p += sizeof(int) * kPathMax;
         c.ar.ord = (unsigned short *)p, p += sizeof(unsigned short) * kInstMax;
@@ -685,7 +686,7 @@ constexpr unsigned long long kInstPoolCap = 16ull << 20, kRsPoolCap = 128ull << 
 size_t arena_stride_bytes()
 {
     size_t s = sizeof(Inst) * kInstMax + sizeof(int4) * kInstMax + sizeof(int2) * kHashMax + sizeof(int4) * kPathMax +
-               sizeof(int2) * kVoteMax + sizeof(int2) * kReadSetMax + sizeof(int) * kPathMax + 2 * sizeof(unsigned short) * kInstMax;
+               sizeof(int2) * kVoteMax + sizeof(unsigned) * kVoteMax + sizeof(int2) * kReadSetMax + sizeof(int) * kPathMax + 2 * sizeof(unsigned short) * kInstMax;
     return (s + 255) & ~(size_t)255;
 }
 

@@ -31,7 +31,7 @@ constexpr int kInstMax = 4096;     // hard cap (HBM arena)
 constexpr int kHashSmem = 256;     // path hash slots in shared memory (<=128 vertices)
 constexpr int kHashMax = 65536;    // hard cap: 32768 path vertices
 constexpr int kPathMax = 32768;
-constexpr int kVoteSmem = 64;      // vote candidates in shared memory
+constexpr int kVoteSmem = 128;     // vote table slots in shared memory
 constexpr int kVoteMax = 8192;
 constexpr int kReadSetMax = 65536; // read-set intervals per traversal
 
@@ -71,6 +71,7 @@ struct WarpSmem { // ~5 KB per warp
     int4 best[kInstSmem];
     int2 hash[kHashSmem];
     int2 vote[kVoteSmem];
+    unsigned vlast[kVoteSmem];
     unsigned short ord[kInstSmem];
     unsigned short good[kInstSmem];
 };
@@ -84,6 +85,7 @@ struct WarpArena { // per-warp HBM scratch (spill + variable-length logs)
     int *hslot;           // kPathMax: slots occupied in the HBM hash (for O(path) clearing)
     int4 *redge;          // kPathMax: successful right edges {end vertex, length, source g, source strand}
     int2 *vote;           // kVoteMax
+    unsigned *vlast;      // kVoteMax
     int2 *rs;             // kReadSetMax: read-set intervals [lo, hi] over epoch indices
 };
 
@@ -719,105 +721,163 @@ struct Next { // result of MostPopularVertex
     bool opos;
 };
 
-// BlocksFinder::MostPopularVertex (blocksfinder.h:708-768).  Lanes = look-ahead depths of one instance;
-// the vote itself is replayed in reference order (running arg-max with the origin tie-break).
+// BlocksFinder::MostPopularVertex (blocksfinder.h:708-768), general path.  Up to four look-ahead walks share the warp per
+// pass (one lane per (walk, depth)); walks that run out of lanes continue in the next pass.  The vote is accumulated
+// order-independently in a small hash table (count += weight, last event = max (list position, depth)) and resolved in
+// closed form: among the vertices whose final count is the maximum, the one whose last increment came from the
+// smallest origin (strand, chr, idx) wins, earliest event on ties -- exactly where the reference's running arg-max
+// with its `origin < ret.origin` tie-break ends (blocksfinder.h:733-741).
 __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool try_used)
 {
     Next best;
     best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
-    long long best_count = 0;
-    int nvote = 0;
     const int start_vid = forward ? c.right_vertex : c.left_vertex;
     const bool use_good = c.ngood >= 2;
     const int n = use_good ? c.ngood : c.ninst;
-    for (int q = 0; q < n; q++) {
-        const int id = use_good ? (int)c.good[q] : q;
-        const Inst I = c.inst[id];
-        const int og = forward ? I.bg : I.fg;
-        if ((forward ? I.bv : I.fv) != start_vid) continue;
-        const bool pos = (I.flags & kPos) != 0;
-        const unsigned weight = (I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp) + 1u;
-        const unsigned obp = forward ? I.bbp : I.fbp;
-        const int step = (forward == pos) ? 1 : -1;
-        int read_lo = 0x7FFFFFFF, read_hi = -1;
-        for (int d0 = 0;; d0 += 16) {
-            const int d = d0 + c.lane + 1;
-            const int g = og + step * d;
-            bool in_range = c.lane < 16 && g >= I.clo && g < I.chi; // it.Valid()
-            int vid = 0, flag = -1;
-            bool used = false, inpath = false;
-            if (in_range) {
-                const int4 rc = __ldg(c.ix.rec + g);
-                vid = pos ? rc.x : -rc.x;
-                long long dp = (long long)(unsigned)rc.y - (long long)obp;
-                if (dp < 0) dp = -dp;
-                in_range = d < c.pr.depth || dp <= c.pr.b;
-                if (in_range) {
-                    bool has = pos || g > I.clo;
-                    flag = has ? (pos ? g : g - 1) : -1;
-                    if (has && !try_used) used = __ldg(c.E + flag) < c.thresh;
-                    inpath = hash_find(c.hash, c.hmask, vid) != kNotSet;
-                }
+    int2 *tab = c.sm->vote;
+    unsigned *last = c.sm->vlast;
+    int cap = kVoteSmem;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        for (int i = c.lane; i < cap; i += 32) tab[i] = make_int2(0, 0), last[i] = 0u;
+        __syncwarp();
+        int distinct = 0;
+        bool overflow = false;
+        for (int lb = 0; lb < n && !overflow; lb += 32) {
+            const int qi = lb + c.lane;
+            int my_id = 0;
+            bool elig = false;
+            if (qi < n) {
+                my_id = use_good ? (int)c.good[qi] : qi;
+                elig = (forward ? c.inst[my_id].bv : c.inst[my_id].fv) == start_vid;
             }
-            const bool ok = in_range && !inpath && !used;
-            const unsigned fail = __ballot_sync(kFull, !ok);
-            const int nok = ffs_lane(fail); // lanes >= 16 always fail, so fail != 0
-            // loop-body executions: the ok steps plus the step that hit `break`
-            const bool stop_in_body = nok < 16 && __shfl_sync(kFull, (int)in_range, nok & 31);
-            c.ct.walk += (unsigned long long)(nok + (stop_in_body ? 1 : 0));
-            // epochs this walk depended on: the ok steps, and the stopping step when it stopped on `used`
-            if (!try_used) {
-                bool dep = flag >= 0 && (c.lane < nok || (c.lane == nok && in_range && !inpath));
-                int lo = dep ? flag : 0x7FFFFFFF, hi = dep ? flag : -1;
-#pragma unroll
-                for (int s = 8; s; s >>= 1) {
-                    lo = min(lo, __shfl_xor_sync(kFull, lo, s));
-                    hi = max(hi, __shfl_xor_sync(kFull, hi, s));
-                }
-                lo = __shfl_sync(kFull, lo, 0), hi = __shfl_sync(kFull, hi, 0);
-                read_lo = min(read_lo, lo), read_hi = max(read_hi, hi);
-            }
-            for (int j = 0; j < nok; j++) { // the vote, in walk order
-                const int cv = __shfl_sync(kFull, vid, j);
-                int slot = -1;
-                for (int base = 0; base < nvote && slot < 0; base += 32) {
-                    int i = base + c.lane;
-                    unsigned m = __ballot_sync(kFull, i < nvote && c.vote[i].x == cv);
-                    if (m) slot = base + ffs_lane(m);
-                }
-                unsigned cnt;
-                if (slot < 0) {
-                    if (nvote >= c.vcap) {
-                        if (c.vcap == kVoteSmem) {
-                            for (int i = c.lane; i < nvote; i += 32) c.ar.vote[i] = c.vote[i];
-                            __syncwarp();
-                            c.vote = c.ar.vote, c.vcap = kVoteMax;
-                        } else {
-                            c.err = LCB_ERR_CAPACITY;
-                            return best;
+            const unsigned em = __ballot_sync(kFull, elig);
+            const int E = __popc(em);
+            for (int gb = 0; gb < E && !overflow; gb += 4) {
+                unsigned pend = E - gb >= 4 ? 0xFu : ((1u << (E - gb)) - 1u);
+                int d0 = 0;
+                while (pend && !overflow) {
+                    if (distinct + 32 >= cap) { // a pass inserts at most 32 keys; probing needs one empty slot to terminate
+                        overflow = true;
+                        break;
+                    }
+                    const int K = __popc(pend), L = 32 / K;
+                    const int k = c.lane / L, dd = c.lane % L + 1;
+                    const bool lane_on = k < K;
+                    const int wi = lane_on ? (int)__fns(pend, 0, k + 1) : 0;
+                    const int src = (int)__fns(em, 0, gb + wi + 1);
+                    const int id = __shfl_sync(kFull, my_id, src & 31);
+                    const unsigned qord = (unsigned)(lb + (src & 31));
+                    const Inst &I = c.inst[id];
+                    const bool pos = (I.flags & kPos) != 0;
+                    const int og = forward ? I.bg : I.fg;
+                    const unsigned obp = forward ? I.bbp : I.fbp;
+                    const unsigned weight = (I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp) + 1u;
+                    const int clo = I.clo, chi = I.chi;
+                    const int step = (forward == pos) ? 1 : -1;
+                    const int d = d0 + dd;
+                    const int g = og + step * d;
+                    bool in_range = lane_on && g >= clo && g < chi; // it.Valid()
+                    int vid = 0, flag = -1;
+                    bool used = false, inpath = false;
+                    if (in_range) {
+                        const int4 rc = __ldg(c.ix.rec + g);
+                        vid = pos ? rc.x : -rc.x;
+                        long long dp = (long long)(unsigned)rc.y - (long long)obp;
+                        if (dp < 0) dp = -dp;
+                        in_range = d < c.pr.depth || dp <= c.pr.b;
+                        if (in_range) {
+                            const bool has = pos || g > clo;
+                            flag = has ? (pos ? g : g - 1) : -1;
+                            if (has && !try_used) used = __ldg(c.E + flag) < c.thresh;
+                            inpath = hash_find(c.hash, c.hmask, vid) != kNotSet;
                         }
                     }
-                    slot = nvote++;
-                    cnt = weight;
-                } else {
-                    cnt = (unsigned)c.vote[slot].y + weight;
-                }
-                __syncwarp();
-                if (c.lane == 0) c.vote[slot] = make_int2(cv, (int)cnt);
-                __syncwarp();
-                // origin < ret.origin: (strand, chr, idx), - strand first (junctionstorage.h:349-362)
-                bool less = (pos != best.opos) ? (!pos && best.opos) : (og < best.og);
-                if ((long long)cnt > best_count || ((long long)cnt == best_count && less)) {
-                    best_count = cnt;
-                    best.vid = cv, best.og = og, best.opos = pos, best.d = d0 + j + 1;
+                    const bool ok = in_range && !inpath && !used;
+                    const unsigned seg = !lane_on ? 0u : (L == 32 ? kFull : (((1u << L) - 1u) << (k * L)));
+                    const unsigned failm = __ballot_sync(kFull, lane_on && !ok);
+                    const unsigned fail = failm & seg;
+                    const int nok = fail ? ffs_lane(fail) - k * L : L;
+                    const bool active = lane_on && dd - 1 < nok;
+                    bool fresh = false;
+                    if (active) { // count[vid] += weight; remember the last (list position, depth) that touched it
+                        unsigned sl = (hash_of(vid) >> 12) & (unsigned)(cap - 1);
+                        while (true) {
+                            const int old = atomicCAS(&tab[sl].x, 0, vid);
+                            if (old == 0 || old == vid) {
+                                fresh = old == 0;
+                                break;
+                            }
+                            sl = (sl + 1) & (unsigned)(cap - 1);
+                        }
+                        atomicAdd((unsigned *)&tab[sl].y, weight);
+                        atomicMax(&last[sl], (qord << 20) | (unsigned)d);
+                    }
+                    distinct += __popc(__ballot_sync(kFull, fresh));
+                    { // loop-body executions and the epochs each walk depended on
+                        const bool stop_in_body = lane_on && dd - 1 == nok && in_range;
+                        if (attempt == 0) c.ct.walk += (unsigned long long)__popc(__ballot_sync(kFull, active || stop_in_body));
+                        const bool dep = flag >= 0 && !try_used && (active || (stop_in_body && !inpath));
+                        for (int kk = 0; kk < K; kk++) {
+                            const int lo = __reduce_min_sync(kFull, dep && k == kk ? flag : 0x7FFFFFFF);
+                            const int hi = __reduce_max_sync(kFull, dep && k == kk ? flag : -1);
+                            const int sid = __shfl_sync(kFull, id, kk * L);
+                            if (lo <= hi && c.lane == 0) inst_extend_reads(c.inst[sid], lo, hi);
+                        }
+                    }
+                    // walks that found their end leave; the others go on from depth d0 + L
+                    unsigned next_pend = 0;
+                    for (int kk = 0; kk < K; kk++) {
+                        const unsigned segk = L == 32 ? kFull : (((1u << L) - 1u) << (kk * L));
+                        if (!(failm & segk)) next_pend |= 1u << __fns(pend, 0, kk + 1);
+                    }
+                    pend = next_pend;
+                    d0 += L;
+                    __syncwarp();
                 }
             }
-            if (nok < 16) break;
         }
-        if (read_lo <= read_hi && c.lane == 0) inst_extend_reads(c.inst[id], read_lo, read_hi);
-        __syncwarp();
+        if (!overflow) break;
+        if (attempt == 1 || cap == kVoteMax) {
+            c.err = LCB_ERR_CAPACITY;
+            return best;
+        }
+        tab = c.ar.vote, last = c.ar.vlast, cap = kVoteMax; // start over with the big table
     }
-    c.vote = c.sm->vote, c.vcap = kVoteSmem;
+    __syncwarp();
+    // ---- resolve
+    unsigned M = 0;
+    for (int base = 0; base < cap; base += 32) {
+        const int2 e = tab[base + c.lane];
+        M = max(M, __reduce_max_sync(kFull, e.x ? (unsigned)e.y : 0u));
+    }
+    if (M == 0) return best;
+    unsigned best_okey = 0xFFFFFFFFu, best_ev = 0xFFFFFFFFu;
+    for (int base = 0; base < cap; base += 32) {
+        const int2 e = tab[base + c.lane];
+        const bool cand = e.x != 0 && (unsigned)e.y == M;
+        unsigned okey = 0xFFFFFFFFu, ev = 0xFFFFFFFFu;
+        int og = 0;
+        bool pos = false;
+        if (cand) {
+            ev = last[base + c.lane];
+            const int q = (int)(ev >> 20);
+            const Inst &I = c.inst[use_good ? (int)c.good[q] : q];
+            pos = (I.flags & kPos) != 0;
+            og = forward ? I.bg : I.fg;
+            okey = (pos ? 0x80000000u : 0u) | (unsigned)og; // origin order: - strand first, then (chr, idx)
+        }
+        if (!__any_sync(kFull, cand)) continue;
+        const unsigned kmin = __reduce_min_sync(kFull, okey);
+        const unsigned emin = __reduce_min_sync(kFull, cand && okey == kmin ? ev : 0xFFFFFFFFu);
+        if (kmin < best_okey || (kmin == best_okey && emin < best_ev)) {
+            const int wl = ffs_lane(__ballot_sync(kFull, cand && okey == kmin && ev == emin));
+            best_okey = kmin, best_ev = emin;
+            best.vid = __shfl_sync(kFull, e.x, wl);
+            best.og = __shfl_sync(kFull, og, wl);
+            best.opos = __shfl_sync(kFull, (int)pos, wl) != 0;
+            best.d = (int)(emin & 0xFFFFFu);
+        }
+    }
     return best;
 }
 
@@ -851,8 +911,8 @@ __device__ __forceinline__ int mpv_fast(Ctx &c, bool forward, bool try_used, Nex
     const unsigned em = __ballot_sync(kFull, elig);
     const int E = __popc(em);
     if (E == 0) return 1;
-    if (E > 4) return 0;
-    const int L = 32 / E; // 32, 16, 10, 8 lanes (= depths) per instance
+    if (E > 2) return 0; // three or more: the general path shares the warp between walks and continues them
+    const int L = 32 / E; // 32 or 16 lanes (= depths) per instance
     const int slot = c.lane / L, d = c.lane % L + 1;
     const bool lane_on = slot < E;
     const int src = lane_on ? (int)__fns(em, 0, slot + 1) : 0;
