@@ -103,3 +103,89 @@ def test_examples_k25_golden(examples, tmp_path):
     _check_seeds(orc, bf)
     _check_blocks(orc, bf, case)
     _check_gff(bf, case, tmp_path)
+
+
+def _fresh_case(tmp_path, kind, genomes, length, k, seed, rate=0.03):
+    from conftest import Case
+    from oracle_binding import REF_TWOPACO, run_twopaco
+    from tools.gen_synthetic import generate
+    if not os.path.exists(REF_TWOPACO):
+        pytest.skip("oracle/_ref/twopaco (input producer) not built")
+    d = str(tmp_path / kind)
+    fas = generate(d, kind, genomes, length, rate, seed)
+    dbg = run_twopaco(fas, k, os.path.join(d, "g.dbg"), threads=8)
+    return Case("%s_%dx%d_k%d" % (kind, genomes, length, k), dbg, fas, k)
+
+
+@pytest.mark.parametrize("kind,genomes,length,k,seed", [("mammal", 8, 1500000, 25, 3), ("pangenome", 16, 500000, 15, 4)])
+def test_synthetic_kinds_blocks_and_gff(tmp_path, kind, genomes, length, k, seed):
+    """Scaled-down BASELINE configs[2] (mammalian-like with repeats, indels, inversions) and configs[3] (pan-genome)."""
+    case = _fresh_case(tmp_path, kind, genomes, length, k, seed)
+    orc, st, bf = _oracle_and_product(case, tmp_path)
+    _check_index(orc, st)
+    bf.create(case.m, case.b)
+    _check_seeds(orc, bf)
+    _check_blocks(orc, bf, case)
+    out_o, out_p = str(tmp_path / "o"), str(tmp_path / "p")
+    orc.generate_output(out_o, False, 0, case.m)
+    bf.generate_output(out_p, False, 0)
+    assert filecmp.cmp(os.path.join(out_o, "blocks_coords.gff"), os.path.join(out_p, "blocks_coords.gff"), shallow=False)
+
+
+def test_cli_drop_in(star_small, tmp_path):
+    """The sibeliaz-lcb binary with the wrapper's flags (SibeliaZ-LCB/sibeliaz:146) writes the reference's files."""
+    import subprocess
+    import sibeliaz_b200 as sb
+    out = str(tmp_path / "cli")
+    cmd = [sb.CLI_PATH, "--graph", star_small.graph] + star_small.fastas + ["-k", "21", "-b", "200", "-o", out, "-m", "50", "-t", "4",
+                                                                          "--abundance", "150", "--chunks", "4"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == "Loading the graph..." and lines[1] == "Analyzing the graph..." and lines[2].startswith("[") and lines[2].endswith("]")
+    assert lines[3] == "Generating the output..." and lines[4].startswith("Blocks found: ") and lines[5].startswith("Coverage: ")
+    assert filecmp.cmp(os.path.join(out, "blocks_coords.gff"), star_small.ref_gff, shallow=False)
+    got = b""
+    for i in range(4):
+        got += b"== %d.tmp\n" % i + open(os.path.join(out, "%d.tmp" % i), "rb").read()
+    assert got == open(star_small.ref_chunks, "rb").read()
+
+
+def test_two_gpus_match_one(star_small, tmp_path):
+    """Seed-sharded 2-GPU run (NCCL min-allreduce of the epoch claims) must return the identical commit-ordered list."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "two.py"
+    script.write_text('''
+import os, sys, ctypes, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import sibeliaz_b200 as sb
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+st = sb.JunctionStorage(%r, %r, 21, 150)
+bf = sb.BlocksFinder(st, 21, device=rank, window_init=2048, window_max=2048).create(50, 200)
+idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    buf = ctypes.create_string_buffer(128); sb.load_library().lcb_comm_unique_id(buf)
+    idb = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+dist.broadcast(idb, 0)
+bf.comm_init(rank, world, bytes(idb.cpu().tolist()))
+b = bf.find_blocks(50, 200)
+np.save(%r + "/blocks_%%d.npy" %% rank, b)
+dist.destroy_process_group()
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), star_small.graph,
+       star_small.fastas, str(tmp_path)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import sibeliaz_b200 as sb
+    from oracle_binding import Oracle
+    ob = Oracle(star_small.graph, star_small.fastas, 21, 150).find_blocks(50, 200)
+    for rank in range(2):
+        b = np.load(str(tmp_path / ("blocks_%d.npy" % rank)))
+        assert len(b) == len(ob["id"]) and np.array_equal(b["id"], ob["id"]) and np.array_equal(b["start"].astype(np.uint64), ob["start"])
+        assert np.array_equal(b["end"].astype(np.uint64), ob["end"]) and np.array_equal(b["chr"], ob["chr"])
