@@ -74,6 +74,11 @@ struct WarpSmem { // ~5 KB per warp
     unsigned vlast[kVoteSmem];
     unsigned short ord[kInstSmem];
     unsigned short good[kInstSmem];
+    // shadow copy of the path state at the best forward point (restored instead of Clear + Init + re-push)
+    Inst s_inst[kInstSmem];
+    int2 s_hash[kHashSmem];
+    unsigned short s_ord[kInstSmem];
+    unsigned short s_good[kInstSmem];
 };
 
 struct WarpArena { // per-warp HBM scratch (spill + variable-length logs)
@@ -116,6 +121,9 @@ struct Ctx { // warp-uniform traversal state (registers)
     int nright, nleft;           // successful pushes
     int ninst, ngood, nbest, hcount, nrs;
     int err; // 0 or LCB_ERR_CAPACITY
+    // shadow state (WarpSmem::s_*)
+    bool snap_valid;
+    int snap_ninst, snap_ngood, snap_hcount, snap_right_flank, snap_right_vertex, snap_nright;
     Counters ct;
 };
 
@@ -338,6 +346,46 @@ __device__ __forceinline__ void path_clear(Ctx &c)
     }
     c.ninst = c.ngood = 0;
     c.nright = c.nleft = 0;
+    __syncwarp();
+}
+
+// Shadow copy of everything Path holds after the current number of right pushes; only while the state is still in
+// shared memory (small paths -- the common case).  Replaces blocksfinder.h:271-284 (Clear, Init, re-push best edges),
+// which recomputes exactly this state.
+__device__ __forceinline__ void snapshot_state(Ctx &c)
+{
+    if (c.icap != kInstSmem || c.hbig) {
+        c.snap_valid = false;
+        return;
+    }
+    WarpSmem *sm = c.sm;
+    const int *src = (const int *)sm->inst;
+    int *dst = (int *)sm->s_inst;
+    const int words = c.ninst * (int)(sizeof(Inst) / sizeof(int));
+    for (int i = c.lane; i < words; i += 32) dst[i] = src[i];
+    for (int i = c.lane; i < kHashSmem; i += 32) sm->s_hash[i] = sm->hash[i];
+    if (c.lane < c.ninst) sm->s_ord[c.lane] = sm->ord[c.lane];
+    if (c.lane < c.ngood) sm->s_good[c.lane] = sm->good[c.lane];
+    c.snap_ninst = c.ninst, c.snap_ngood = c.ngood, c.snap_hcount = c.hcount;
+    c.snap_right_flank = c.right_flank, c.snap_right_vertex = c.right_vertex, c.snap_nright = c.nright;
+    c.snap_valid = true;
+    __syncwarp();
+}
+
+// after path_clear(): bring the shadow state back (storage is in shared memory again, hash table zeroed)
+__device__ __forceinline__ void restore_state(Ctx &c)
+{
+    WarpSmem *sm = c.sm;
+    const int *src = (const int *)sm->s_inst;
+    int *dst = (int *)sm->inst;
+    const int words = c.snap_ninst * (int)(sizeof(Inst) / sizeof(int));
+    for (int i = c.lane; i < words; i += 32) dst[i] = src[i];
+    for (int i = c.lane; i < kHashSmem; i += 32) sm->hash[i] = sm->s_hash[i];
+    if (c.lane < c.snap_ninst) sm->ord[c.lane] = sm->s_ord[c.lane];
+    if (c.lane < c.snap_ngood) sm->good[c.lane] = sm->s_good[c.lane];
+    c.ninst = c.snap_ninst, c.ngood = c.snap_ngood, c.hcount = c.snap_hcount;
+    c.right_flank = c.snap_right_flank, c.right_vertex = c.snap_right_vertex, c.nright = c.snap_nright;
+    c.left_flank = 0, c.left_vertex = c.origin, c.nleft = 0;
     __syncwarp();
 }
 
@@ -1050,6 +1098,7 @@ __device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &bes
                         best_score = now_score;
                         best_size = (FORWARD ? c.nright : c.nleft) + 1;
                         if (now_score > 0) snapshot_best(c);
+                        if (FORWARD) snapshot_state(c);
                     }
                 }
                 done = v == nx.vid;
@@ -1078,22 +1127,29 @@ __device__ __forceinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
     long long best_score = 0, score = 0;
     int best_size[2] = {1, 1}; // bestLeftSize, bestRightSize
     const int min_run = c.pr.b * 2;
+    c.snap_valid = false;
     for (int phase = 1; phase >= 0; phase--) { // 1: forward, 0: backward
         const bool forward = phase == 1;
-        int replay = 0;
-        if (!forward) {
-            replay = best_size[1] - 1;
+        if (forward) {
+            path_init(c, vid, ch);
+            if (c.err) return;
+            if (c.ninst == 0) break; // a seed without live instances cannot move (MostPopularVertex finds nothing)
+            snapshot_state(c);       // bestRightSize == 1: the state right after Init
+        } else {
+            const int replay = best_size[1] - 1;
             path_clear(c);
             if (c.err) return;
+            if (c.snap_valid && c.snap_nright == replay && c.icap == kInstSmem) {
+                restore_state(c);
+            } else { // big paths: re-play the best right part (blocksfinder.h:271-284)
+                path_init(c, vid, ch);
+                for (int i = 0; i < replay && !c.err; i++) {
+                    int4 e = c.ar.redge[i];
+                    path_push(c, true, e.x, e.y, e.z, e.w != 0, 0, -1, -1);
+                }
+                if (c.err) return;
+            }
         }
-        path_init(c, vid, ch);
-        if (c.err) return;
-        if (c.ninst == 0) break; // a seed without live instances cannot move (MostPopularVertex finds nothing)
-        for (int i = 0; i < replay && !c.err; i++) { // re-play the best right part (blocksfinder.h:271-284)
-            int4 e = c.ar.redge[i];
-            path_push(c, true, e.x, e.y, e.z, e.w != 0, 0, -1, -1);
-        }
-        if (c.err) return;
         while (true) {
             bool ret = true, positive = false;
             const int prev_len = c.right_flank - c.left_flank;
