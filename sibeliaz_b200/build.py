@@ -72,8 +72,8 @@ def build(force=False, verbose=False):
         cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", LIB] + srcs
         nccl = _nccl()
         if nccl:
-            cmd += ["-DLCB_WITH_NCCL", "-I", nccl[0], "-L", os.path.dirname(nccl[1]), "-Xlinker", "-l:" + os.path.basename(nccl[1]),
-                    "-Xlinker", "-rpath," + os.path.dirname(nccl[1])]
+            # NCCL is dlopen'ed on first multi-GPU use: headers for the types, no link-time dependency
+            cmd += ["-DLCB_WITH_NCCL", "-I", nccl[0], '-DLCB_NCCL_PATH="%s"' % nccl[1], "-ldl"]
         cmd += ["-cudart", "shared"]
         out = _run(cmd)
         if verbose:

@@ -34,7 +34,8 @@
 #include "lcb_traverse.cuh"
 
 #ifdef LCB_WITH_NCCL
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library itself is dlopen'ed on first multi-GPU use (single-GPU hosts never load it)
 #endif
 
 using namespace lcb;
@@ -78,6 +79,45 @@ struct Window { // per-window arrays, indexed by j = seed - w0
     } while (0)
 
 #ifdef LCB_WITH_NCCL
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi *nccl_api()
+{
+    static NcclApi api = []() {
+        NcclApi a;
+        const char *cands[] = {getenv("LCB_NCCL_LIB"), "libnccl.so.2",
+#ifdef LCB_NCCL_PATH
+                               LCB_NCCL_PATH,
+#endif
+                               "libnccl.so"};
+        void *h = nullptr;
+        for (const char *c : cands)
+            if (c && (h = dlopen(c, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!h) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+        a.Broadcast = (decltype(a.Broadcast))dlsym(h, "ncclBroadcast");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.GetErrorString;
+        return a;
+    }();
+    return &api;
+}
+#define ncclGetUniqueId nccl_api()->GetUniqueId
+#define ncclCommInitRank nccl_api()->CommInitRank
+#define ncclCommDestroy nccl_api()->CommDestroy
+#define ncclAllReduce nccl_api()->AllReduce
+#define ncclBroadcast nccl_api()->Broadcast
+#define ncclGetErrorString nccl_api()->GetErrorString
 #define NCCL_TRY(x)                                                                                       \
     do {                                                                                                  \
         ncclResult_t r_ = (x);                                                                            \
@@ -762,8 +802,14 @@ extern "C" void lcb_default_params(lcb_params *p)
 // so a host can overlap it with parsing its inputs (the CLI does).  Optional; lcb_create works without it.
 extern "C" int lcb_warmup(int device)
 {
+    const bool trace = getenv("LCB_LOAD_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace) fprintf(stderr, "[warmup] %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     if (cudaSetDevice(device) != cudaSuccess) return LCB_ERR_CUDA;
     if (cudaFree(nullptr) != cudaSuccess) return LCB_ERR_CUDA;
+    lap("context");
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -772,10 +818,12 @@ extern "C" int lcb_warmup(int device)
     void *arena = nullptr, *ip = nullptr, *rp = nullptr;
     bool cached = false;
     if (cached_alloc(&arena, arena_bytes, device, &cached) != cudaSuccess) return LCB_ERR_CUDA;
+    lap("arena malloc");
     if (!cached && cudaMemset(arena, 0, arena_bytes) != cudaSuccess) return LCB_ERR_CUDA;
     if (cached_alloc(&ip, sizeof(int4) * kInstPoolCap, device, nullptr) != cudaSuccess) return LCB_ERR_CUDA;
     if (cached_alloc(&rp, sizeof(int2) * kRsPoolCap, device, nullptr) != cudaSuccess) return LCB_ERR_CUDA;
     cudaDeviceSynchronize();
+    lap("pools + memset");
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         size_t ab = (arena_bytes + 511) & ~(size_t)511;
@@ -966,6 +1014,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
 extern "C" int lcb_comm_unique_id(void *id_bytes)
 {
 #ifdef LCB_WITH_NCCL
+    if (!nccl_api()->ok) return LCB_ERR_STATE;
     ncclUniqueId id;
     if (ncclGetUniqueId(&id) != ncclSuccess) return LCB_ERR_CUDA;
     static_assert(sizeof(id) <= LCB_COMM_ID_BYTES, "id size");
@@ -987,6 +1036,10 @@ extern "C" int lcb_comm_init(lcb_ctx *ctx, int rank, int n_ranks, const void *id
     }
 #ifdef LCB_WITH_NCCL
     if (!id_bytes) return LCB_ERR_ARG;
+    if (!nccl_api()->ok) {
+        ctx->error = "libnccl.so.2 could not be loaded (set LCB_NCCL_LIB)";
+        return LCB_ERR_STATE;
+    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     {
         // communicators are expensive (seconds) and independent of the index: keep one per (device, rank, size)

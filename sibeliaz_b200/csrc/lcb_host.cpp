@@ -445,6 +445,27 @@ struct OutBlock {
     int32_t abs_id() const { return id < 0 ? -id : id; }
 };
 
+// per-base coverage flags (the reference's std::vector<bool> covered[chr], blocksfinder.h:607-611) on raw words
+struct Bitmap {
+    std::vector<uint64_t> w;
+    void reset(size_t bits) { w.assign((bits + 63) / 64, 0); }
+    bool test(uint64_t i) const { return (w[i >> 6] >> (i & 63)) & 1; }
+    void fill(uint64_t lo, uint64_t hi, bool v) // [lo, hi)
+    {
+        if (lo >= hi) return;
+        uint64_t a = lo >> 6, b = (hi - 1) >> 6;
+        uint64_t ma = ~0ULL << (lo & 63), mb = ~0ULL >> (63 - ((hi - 1) & 63));
+        if (a == b) {
+            uint64_t m = ma & mb;
+            w[a] = v ? (w[a] | m) : (w[a] & ~m);
+            return;
+        }
+        w[a] = v ? (w[a] | ma) : (w[a] & ~ma);
+        for (uint64_t i = a + 1; i < b; i++) w[i] = v ? ~0ULL : 0;
+        w[b] = v ? (w[b] | mb) : (w[b] & ~mb);
+    }
+};
+
 struct TextBuffer {
     std::string s;
     void put(const char *p, size_t n) { s.append(p, n); }
@@ -479,6 +500,11 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
     if (!ix || (!blocks && n) || !out_dir) return LCB_ERR_ARG;
     try {
         if (gen_seq && chunks <= 0) throw Failure(LCB_ERR_ARG, "--chunks must be positive when block sequences are written");
+        const bool trace = getenv("LCB_LOAD_TRACE") != nullptr;
+        auto t_start = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (trace) fprintf(stderr, "[output] %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+        };
         const int32_t C = ix->C;
         int32_t max_id = 0;
         for (uint64_t i = 0; i < n; i++) {
@@ -497,10 +523,12 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
             if (ma != mb) return ma > mb;
             return a.abs_id() < b.abs_id();
         };
+        lap("copy + count");
         std::sort(inst.begin(), inst.end(), by_multiplicity);
+        lap("sort by multiplicity");
         // trimming against per-base coverage bitmaps, blocksfinder.h:607-656
-        std::vector<std::vector<bool>> covered((size_t)C);
-        for (int32_t c = 0; c < C; c++) covered[(size_t)c].assign(ix->fasta.seq[(size_t)c].size() + 1, false);
+        std::vector<Bitmap> covered((size_t)C);
+        for (int32_t c = 0; c < C; c++) covered[(size_t)c].reset(ix->fasta.seq[(size_t)c].size() + 1);
         std::vector<OutBlock> kept, group;
         int64_t next_id = 1;
         for (size_t lo = 0; lo < inst.size();) {
@@ -508,24 +536,24 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
             while (hi < inst.size() && !by_multiplicity(inst[lo], inst[hi])) ++hi;
             group.clear();
             for (size_t i = lo; i < hi; i++) {
-                std::vector<bool> &cov = covered[inst[i].chr];
+                Bitmap &cov = covered[inst[i].chr];
                 uint64_t s = inst[i].start, e = inst[i].end;
-                while (cov[s] && s < e) ++s;
-                while (cov[e] && e > s) --e;
+                while (cov.test(s) && s < e) ++s;
+                while (cov.test(e) && e > s) --e;
                 if (e - s >= (uint64_t)min_block) {
                     group.push_back(OutBlock{(int32_t)(inst[i].id > 0 ? next_id : -next_id), inst[i].chr, s, e});
-                    std::fill(cov.begin() + (ptrdiff_t)s, cov.begin() + (ptrdiff_t)e, true);
+                    cov.fill(s, e, true);
                 }
             }
             if (group.size() > 1) {
                 ++next_id;
                 kept.insert(kept.end(), group.begin(), group.end());
             } else {
-                for (const OutBlock &b : group)
-                    std::fill(covered[b.chr].begin() + (ptrdiff_t)b.start, covered[b.chr].begin() + (ptrdiff_t)b.end, false);
+                for (const OutBlock &b : group) covered[b.chr].fill(b.start, b.end, false);
             }
             lo = hi;
         }
+        lap("trim against coverage");
         uint64_t total = 0, in_blocks = 0;
         for (int32_t c = 0; c < C; c++) total += ix->fasta.seq[(size_t)c].size();
         for (const OutBlock &b : kept) in_blocks += b.end - b.start;
@@ -537,6 +565,7 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
             if (a.chr != b.chr) return a.chr < b.chr;
             return a.start < b.start;
         });
+        lap("sort kept");
         if (mkdir(out_dir, 0755) != 0 && errno != EEXIST) throw Failure(LCB_ERR_IO, std::string("Cannot create dir ") + out_dir);
         auto by_id = [](const OutBlock &a, const OutBlock &b) { return a.abs_id() < b.abs_id(); };
         {
@@ -544,7 +573,6 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
             std::vector<OutBlock> rows(kept);
             std::sort(rows.begin(), rows.end(), by_id);
             TextBuffer t;
-            t.s.reserve(64 + rows.size() * 64);
             t.put("##gff-version 3.1.26\n", 21);
             for (int32_t c = 0; c < C; c++) {
                 t.put("##sequence-region ", 18);
@@ -553,19 +581,34 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
                 t.num(ix->fasta.seq[(size_t)c].size());
                 t.put('\n');
             }
-            for (const OutBlock &b : rows) {
-                t.put(ix->fasta.name[b.chr]);
-                t.put("\tSibeliaZ\tSO:0000856\t", 21);
-                t.num(b.start + 1);
-                t.put('\t');
-                t.num(b.end);
-                t.put("\t.\t", 3);
-                t.put(b.id > 0 ? '+' : '-');
-                t.put("\t.\tID=", 6);
-                t.num((uint64_t)b.abs_id());
-                t.put('\n');
-            }
+            // rows are formatted by several threads into private buffers and concatenated in order
+            const unsigned T = std::max(1u, std::min(WorkerCount(), (unsigned)(rows.size() / 65536 + 1)));
+            std::vector<TextBuffer> part(T);
+            Parallel(T, [&](unsigned tt, unsigned TT) {
+                TextBuffer &p = part[tt];
+                const size_t lo = rows.size() * tt / TT, hi = rows.size() * (tt + 1) / TT;
+                p.s.reserve((hi - lo) * 56 + 64);
+                for (size_t i = lo; i < hi; i++) {
+                    const OutBlock &b = rows[i];
+                    p.put(ix->fasta.name[b.chr]);
+                    p.put("\tSibeliaZ\tSO:0000856\t", 21);
+                    p.num(b.start + 1);
+                    p.put('\t');
+                    p.num(b.end);
+                    p.put("\t.\t", 3);
+                    p.put(b.id > 0 ? '+' : '-');
+                    p.put("\t.\tID=", 6);
+                    p.num((uint64_t)b.abs_id());
+                    p.put('\n');
+                }
+            });
+            size_t total_len = t.s.size();
+            for (auto &p : part) total_len += p.s.size();
+            t.s.reserve(total_len);
+            for (auto &p : part) t.s.append(p.s);
+            lap("sort rows + format");
             WriteFile(std::string(out_dir) + "/blocks_coords.gff", t.s);
+            lap("write gff");
         }
         if (gen_seq) {
             // blocksfinder.h:533-582: one line per block, blocks dealt round-robin over `chunks` files

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 namespace {
@@ -155,11 +156,17 @@ int main(int argc, char **argv)
     auto t0 = std::chrono::steady_clock::now();
     printf("Loading the graph...\n");
     fflush(stdout);
-    std::thread warm([&o]() { lcb_warmup(o.gpu); }); // CUDA context + scratch while the files are parsed
+    double ms_warm = 0;
+    std::thread warm([&o, &ms_warm]() { // CUDA context + scratch while the files are parsed
+        auto a = std::chrono::steady_clock::now();
+        lcb_warmup(o.gpu);
+        ms_warm = Ms(a, std::chrono::steady_clock::now());
+    });
     std::vector<const char *> files;
     for (auto &f : o.fasta) files.push_back(f.c_str());
     lcb_index *index = nullptr;
     int load_rc = lcb_index_load(o.graph.c_str(), files.data(), (int)files.size(), (int)o.k, (int)o.a, &index, err, sizeof err);
+    auto t_parsed = std::chrono::steady_clock::now();
     warm.join();
     if (load_rc) {
         fprintf(stderr, "error: %s\n", err);
@@ -180,6 +187,7 @@ int main(int argc, char **argv)
     if (o.window > 0) p.window_init = p.window_max = o.window;
     lcb_ctx *ctx = nullptr;
     int rc = lcb_create(&view, &p, &ctx);
+    auto t_created = std::chrono::steady_clock::now();
     uint64_t n_seeds = 0;
     if (!rc) rc = lcb_enumerate_seeds(ctx, &n_seeds);
     lcb_block_instance *blocks = nullptr;
@@ -222,17 +230,17 @@ int main(int argc, char **argv)
         fprintf(stderr,
                 "{\"records\": %llu, \"vertices\": %llu, \"seeds\": %llu, \"block_instances\": %llu, \"windows\": %llu, "
                 "\"rounds\": %llu, \"traversals_first\": %llu, \"traversals_rerun\": %llu, \"kernel_launches\": %llu, "
-                "\"ms_load\": %.3f, \"ms_create_enumerate_find\": %.3f, \"ms_enumerate\": %.3f, \"ms_find\": %.3f, "
+                "\"ms_parse\": %.3f, \"ms_warmup_thread\": %.3f, \"ms_load\": %.3f, \"ms_create\": %.3f, \"ms_create_enumerate_find\": %.3f, \"ms_enumerate\": %.3f, \"ms_find\": %.3f, "
                 "\"ms_traverse_kernels\": %.3f, \"ms_output\": %.3f, \"junctions_per_sec\": %.1f}\n",
                 (unsigned long long)st.n_records, (unsigned long long)st.n_vertices, (unsigned long long)st.n_seeds,
                 (unsigned long long)st.n_block_instances, (unsigned long long)st.windows, (unsigned long long)st.rounds,
                 (unsigned long long)st.traversals_first, (unsigned long long)st.traversals_rerun,
-                (unsigned long long)st.kernel_launches, Ms(t0, t1), Ms(t1, t2), st.ms_enumerate, st.ms_find,
+                (unsigned long long)st.kernel_launches, Ms(t0, t_parsed), ms_warm, Ms(t0, t1), Ms(t1, t_created), Ms(t1, t2), st.ms_enumerate, st.ms_find,
                 st.ms_traverse_kernels, Ms(t2, t3),
                 (st.ms_enumerate + st.ms_find) > 0 ? 1000.0 * (double)st.n_records / (st.ms_enumerate + st.ms_find) : 0.0);
     }
-    lcb_free_blocks(blocks);
-    lcb_destroy(ctx);
-    lcb_index_free(index);
-    return 0;
+    // the files are written and flushed: skip the (slow) teardown of multi-GB host/device state
+    fflush(stdout);
+    fflush(stderr);
+    _exit(0);
 }
