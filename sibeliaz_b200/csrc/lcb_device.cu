@@ -134,7 +134,7 @@ NcclApi *nccl_api()
 __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
                                                         const int *__restrict__ seed_vid,
                                                         const unsigned char *__restrict__ seed_ch, unsigned w0,
-                                                        unsigned phase, int slot, const unsigned *__restrict__ list,
+                                                        unsigned phase, int force_slot, const unsigned *__restrict__ list,
                                                         const unsigned *__restrict__ n_ptr, Window win, Control *ctl,
                                                         unsigned char *arena_base, size_t arena_stride, int collect)
 {
@@ -164,13 +164,15 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
         c.ar.good = (unsigned short *)p, p += sizeof(unsigned short) * kInstMax;
     }
     const unsigned n = *n_ptr;
-    unsigned done = 0;
+    unsigned done = 0, done1 = 0;
     while (true) {
         unsigned idx = 0;
         if (lane == 0) idx = atomicAdd(&ctl->head, 1u);
         idx = __shfl_sync(kFull, idx, 0);
         if (idx >= n) break;
-        const unsigned j = list[idx];
+        const unsigned item = list[idx];
+        const unsigned j = item & 0x7FFFFFFFu;
+        const int slot = force_slot >= 0 ? force_slot : (int)(item >> 31); // bit 31: commit-time re-run
         const unsigned i = w0 + j;
         c.thresh = slot == 0 ? (i / phase) * phase : i;
         const long long t_begin = collect == 2 ? clock64() : 0;
@@ -207,10 +209,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
             win.rs_off[slot][j] = (unsigned)ro;
             win.rs_cnt[slot][j] = (unsigned)c.nrs;
         }
-        done++;
+        if (slot == 0) done++;
+        else done1++;
     }
     if (lane == 0) {
-        if (done) atomicAdd(slot == 0 ? &ctl->runs0 : &ctl->runs1, (unsigned long long)done);
+        if (done) atomicAdd(&ctl->runs0, (unsigned long long)done);
+        if (done1) atomicAdd(&ctl->runs1, (unsigned long long)done1);
         if (collect) {
             atomicAdd(&ctl->ct_walk, c.ct.walk);
             atomicAdd(&ctl->ct_occ, c.ct.occ);
@@ -257,6 +261,7 @@ __global__ void k_conflict(const uint32_t *__restrict__ E, unsigned w0, const un
     const int lane = threadIdx.x & 31;
     const unsigned n = *n_ptr;
     for (unsigned idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += gridDim.x * (blockDim.x >> 5)) {
+        if (list[idx] >> 31) continue; // a commit-time re-run queued by the last validation: nothing to test
         const unsigned j = list[idx];
         bool conf = false;
         if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, E, w0 + j, lane);
@@ -339,7 +344,7 @@ __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__
                 win.conf[j] = conf;
                 if (rerun) {
                     win.has1[j] = 1;
-                    win.list1[atomicAdd(&ctl->n1, 1u)] = j;
+                    win.list0[atomicAdd(&ctl->n0, 1u)] = j | 0x80000000u; // evaluated together with the speculative work
                 }
                 if (!conf) win.has1[j] = 0;
             }
@@ -1294,13 +1299,13 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         unsigned first_dirty = 0;
         for (unsigned round = 1;; round++) {
             ctx->st.rounds++;
-            // A. speculative evaluations
+            // A. speculative evaluations, plus the commit-time re-runs the last validation queued (tagged items)
             CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-            if ((rc = launch_traverse(ctx, Ecur, w0, 0, ctx->win.list0, &ctx->d_ctl->n0))) return rc;
+            if ((rc = launch_traverse(ctx, Ecur, w0, -1, ctx->win.list0, &ctx->d_ctl->n0))) return rc;
             CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
             // B. commit-time conflicts of the freshly evaluated seeds
             k_conflict<<<vgrid, 256, 0, ctx->stream>>>(Ecur, w0, ctx->win.list0, &ctx->d_ctl->n0, ctx->win, ctx->d_ctl);
-            // C. commit-time re-runs
+            // C. commit-time re-runs of the conflicts found in B
             CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
             if ((rc = launch_traverse(ctx, Ecur, w0, 1, ctx->win.list1, &ctx->d_ctl->n1))) return rc;
             CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));

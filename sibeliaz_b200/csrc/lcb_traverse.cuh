@@ -730,27 +730,41 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
     return true;
 }
 
-// Path::Score (path.h:604-628): any flank penalty >= maxFlankingSize makes the whole score -INT32_MAX
+// Path::Score (path.h:604-628): any flank penalty >= maxFlankingSize makes the whole score -INT32_MAX.
+// With flank <= 32767 every squared penalty fits 32 bits and sum(real) is split in 16-bit halves, so four 32-bit warp
+// reductions are exact; larger -b values take 64-bit shuffles.
 __device__ __forceinline__ long long path_score(Ctx &c)
 {
-    long long sum = 0;
+    long long total = 0;
     bool bad = false;
+    const bool small = c.pr.flank <= 32767;
     for (int base = 0; base < c.ngood; base += 32) {
-        int i = base + c.lane;
+        const int i = base + c.lane;
+        unsigned real = 0;
+        long long pen = 0;
         if (i < c.ngood) {
             const Inst &I = c.inst[c.good[i]];
-            long long real = I.fbp > I.bbp ? (long long)(I.fbp - I.bbp) : (long long)(I.bbp - I.fbp);
-            long long rp = (long long)c.right_flank - I.bdist;
-            long long lp = (long long)(-c.left_flank) + I.fdist;
+            real = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
+            const long long rp = (long long)c.right_flank - I.bdist;
+            const long long lp = (long long)(-c.left_flank) + I.fdist;
             if (lp >= c.pr.flank || rp >= c.pr.flank) bad = true;
-            sum += real - (rp + lp) * (rp + lp);
+            else pen = rp + lp;
+        }
+        if (small) {
+            const unsigned pen2 = (unsigned)(pen * pen);
+            const unsigned lo = __reduce_add_sync(kFull, real & 0xFFFFu), hi = __reduce_add_sync(kFull, real >> 16);
+            const unsigned pp = __reduce_add_sync(kFull, pen2 >> 5), pr = __reduce_add_sync(kFull, pen2 & 31u);
+            total += (long long)lo + ((long long)hi << 16) - (((long long)pp << 5) + pr);
+        } else {
+            long long term = (long long)real - pen * pen;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) term += __shfl_xor_sync(kFull, term, d);
+            total += term;
         }
     }
     c.ct.score += (unsigned long long)c.ngood;
     bad = __any_sync(kFull, bad);
-#pragma unroll
-    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
-    return bad ? -(long long)0x7FFFFFFF : sum;
+    return bad ? -(long long)0x7FFFFFFF : total;
 }
 
 // bestInstance = copies of *goodInstance_[i] in list order (blocksfinder.h:818-825, :881-888)
