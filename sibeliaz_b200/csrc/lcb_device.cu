@@ -198,8 +198,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
         io = __shfl_sync(kFull, io, 0);
         ro = __shfl_sync(kFull, ro, 0);
         if (io + c.nbest > win.inst_cap || ro + c.nrs > win.rs_cap) {
-            if (lane == 0) atomicExch(&ctl->pool_overflow, 1u);
-            break;
+            // the host halves the window and starts it again; until it notices, the kernels queued behind this one
+            // must see a harmless (empty) entry for this seed
+            if (lane == 0) {
+                atomicExch(&ctl->pool_overflow, 1u);
+                win.res_cnt[slot][j] = 0;
+                win.rs_cnt[slot][j] = 0;
+            }
+            continue;
         }
         for (int t = lane; t < c.nbest; t += 32) win.inst_pool[io + t] = c.best[t];
         for (int t = lane; t < c.nrs; t += 32) win.rs_pool[ro + t] = c.ar.rs[t];
@@ -997,6 +1003,10 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if ((rc = dev_alloc(ctx, &ctx->d_wnext, 4))) return rc;
     ctx->win.inst_cap = kInstPoolCap;
     ctx->win.rs_cap = kRsPoolCap;
+    if (const char *e = getenv("LCB_TEST_POOL_ENTRIES")) { // testing aid: tiny result pools force the window-halving retry
+        unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 1024) ctx->win.inst_cap = std::min(ctx->win.inst_cap, v), ctx->win.rs_cap = std::min(ctx->win.rs_cap, v);
+    }
     if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.rs_pool, (size_t)ctx->win.rs_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_ctl, 1))) return rc;
@@ -1278,11 +1288,10 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         // seeds are dealt round-robin over the ranks; a rank sees the others' seeds as "no result, empty read-set"
         const unsigned R = (unsigned)ctx->n_ranks, me = (unsigned)ctx->rank;
         const unsigned n_own = n > me ? (n - me + R - 1) / R : 0;
-        if (R > 1)
-            for (int s = 0; s < 2; s++) {
-                CUDA_TRY(cudaMemsetAsync(ctx->win.res_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
-                CUDA_TRY(cudaMemsetAsync(ctx->win.rs_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
-            }
+        for (int s = 0; s < 2; s++) { // every seed starts as "no result, empty read-set" (other ranks' seeds stay that way)
+            CUDA_TRY(cudaMemsetAsync(ctx->win.res_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(ctx->win.rs_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
+        }
         if (n_own) k_iota<<<(n_own + 255) / 256, 256, 0, ctx->stream>>>(ctx->win.list0, n_own, me, R);
         ctx->st.kernel_launches++;
         {

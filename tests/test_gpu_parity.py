@@ -189,3 +189,29 @@ dist.destroy_process_group()
         b = np.load(str(tmp_path / ("blocks_%d.npy" % rank)))
         assert len(b) == len(ob["id"]) and np.array_equal(b["id"], ob["id"]) and np.array_equal(b["start"].astype(np.uint64), ob["start"])
         assert np.array_equal(b["end"].astype(np.uint64), ob["end"]) and np.array_equal(b["chr"], ob["chr"])
+
+
+@pytest.mark.parametrize("m,b", [(100, 100), (30, 500), (200, 50)])
+def test_star_small_other_parameters(star_small, tmp_path, m, b):
+    """-m / -b other than the wrapper's defaults (min block, max branch = max flank)."""
+    from conftest import Case
+    case = Case(star_small.name, star_small.graph, star_small.fastas, star_small.k, b=b, m=m)
+    orc, st, bf = _oracle_and_product(case, tmp_path)
+    _check_blocks(orc, bf, case)
+
+
+def test_abundance_threshold(star_small, tmp_path):
+    from conftest import Case
+    case = Case(star_small.name, star_small.graph, star_small.fastas, star_small.k, a=4)
+    orc, st, bf = _oracle_and_product(case, tmp_path)
+    bf.create(case.m, case.b)
+    _check_seeds(orc, bf)
+    _check_blocks(orc, bf, case)
+
+
+def test_pool_overflow_retries_with_smaller_window(star_small, tmp_path, monkeypatch):
+    """Result pools too small for the window: the driver must halve the window and still return the exact result."""
+    monkeypatch.setenv("LCB_TEST_POOL_ENTRIES", "4096")
+    orc, st, bf = _oracle_and_product(star_small, tmp_path, window=8192)
+    _check_blocks(orc, bf, star_small)
+    assert bf.stats["windows"] > 2
