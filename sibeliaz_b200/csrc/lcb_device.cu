@@ -804,7 +804,7 @@ extern "C" void lcb_default_params(lcb_params *p)
     p->looking_depth = 8;
     p->phase_size = 256;
     p->window_init = 16384;
-    p->window_max = 131072;
+    p->window_max = 262144;
     p->device = 0;
     p->collect_counters = 0;
 }
@@ -878,7 +878,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if (p.phase_size <= 0) p.phase_size = 256;
     if (p.looking_depth <= 0) p.looking_depth = 8;
     if (p.window_init <= 0) p.window_init = 16384;
-    if (p.window_max <= 0) p.window_max = 131072;
+    if (p.window_max <= 0) p.window_max = 262144;
     p.window_max = std::min(p.window_max, 1 << 20);
     p.window_max = std::max(p.phase_size, p.window_max / p.phase_size * p.phase_size);
     p.window_init = std::max(p.phase_size, std::min(p.window_init, p.window_max) / p.phase_size * p.phase_size);
