@@ -131,6 +131,7 @@ NcclApi *nccl_api()
 // ------------------------------------------------------------------------------------------------
 // traversal kernel: persistent warps pull (seed, slot) items from a list
 // ------------------------------------------------------------------------------------------------
+template <bool COLLECT>
 __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
                                                         const int *__restrict__ seed_vid,
                                                         const unsigned char *__restrict__ seed_ch, unsigned w0,
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
     c.lane = lane;
     c.sm = &smem[wib];
     c.err = 0;
+    c.collect = COLLECT;
     c.ct.walk = c.ct.occ = c.ct.scan = c.ct.score = 0;
     c.ct.pushes = c.ct.mpv_fast = c.ct.mpv_slow = c.ct.push_par = c.ct.push_ser = 0;
     {
@@ -823,7 +825,7 @@ extern "C" int lcb_warmup(int device)
     lap("context");
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     const size_t stride = arena_stride_bytes();
     const size_t arena_bytes = stride * (size_t)per_sm * (size_t)sms * kWarpsPerBlock;
     void *arena = nullptr, *ip = nullptr, *rp = nullptr;
@@ -1013,7 +1015,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     CUDA_TRY(cached_alloc((void **)&ctx->h_ctl, sizeof(Control), -1, nullptr));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, kThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
     ctx->grid_traverse = per_sm * ctx->sms;
     ctx->arena_stride = arena_stride_bytes();
@@ -1232,10 +1234,15 @@ int launch_traverse(lcb_ctx *ctx, const uint32_t *E, unsigned w0, int slot, cons
 {
     Params pr{ctx->prm.k, ctx->prm.max_branch, ctx->prm.min_block, ctx->prm.max_flank, ctx->prm.looking_depth};
     CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, sizeof(unsigned), ctx->stream));
-    k_traverse<<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, w0,
-                                                                 (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
-                                                                 ctx->d_ctl, ctx->d_arena, ctx->arena_stride,
-                                                                 ctx->prm.collect_counters);
+    if (ctx->prm.collect_counters)
+        k_traverse<true><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, w0,
+                                                                           (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
+                                                                           ctx->d_ctl, ctx->d_arena, ctx->arena_stride,
+                                                                           ctx->prm.collect_counters);
+    else
+        k_traverse<false><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, w0,
+                                                                            (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
+                                                                            ctx->d_ctl, ctx->d_arena, ctx->arena_stride, 0);
     ctx->st.kernel_launches++;
     ctx->st.traverse_launches++;
     return LCB_OK;

@@ -121,6 +121,7 @@ struct Ctx { // warp-uniform traversal state (registers)
     int nright, nleft;           // successful pushes
     int ninst, ngood, nbest, hcount, nrs;
     int err; // 0 or LCB_ERR_CAPACITY
+    bool collect; // count walk/occurrence/scan/score steps (diagnostics; off on the timed path)
     // shadow state (WarpSmem::s_*)
     bool snap_valid;
     int snap_ninst, snap_ngood, snap_hcount, snap_right_flank, snap_right_vertex, snap_nright;
@@ -128,6 +129,18 @@ struct Ctx { // warp-uniform traversal state (registers)
 };
 
 __device__ __forceinline__ int ffs_lane(unsigned m) { return __ffs((int)m) - 1; }
+
+// position of the k-th (0-based) set bit of a 4-bit mask (cheap replacement of __fns for the walk scheduler)
+__device__ __forceinline__ int kth_bit4(unsigned m, int k)
+{
+    int r = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (((m >> b) & 1u) && __popc(m & ((1u << b) - 1u)) == k) r = b;
+    return r;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ unsigned hash_of(int key) { return (unsigned)key * 2654435761u; }
 
@@ -458,7 +471,7 @@ __device__ __forceinline__ bool scan_used(Ctx &c, int lo, int hi)
         bool u = f <= hi && __ldg(c.E + f) < c.thresh;
         any = __any_sync(kFull, u);
     }
-    c.ct.scan += (unsigned long long)(hi - lo + 1);
+    if (c.collect) c.ct.scan += (unsigned long long)(hi - lo + 1);
     return any;
 }
 
@@ -539,7 +552,7 @@ __device__ __forceinline__ bool push_parallel(Ctx &c, const bool BACK, int v, in
             outcome = (extend && cend_v != v) ? 1 : (!q.used ? 2 : 3);
         }
     }
-    c.ct.scan += (unsigned long long)__reduce_add_sync(kFull, scan_lo <= scan_hi ? (unsigned)(scan_hi - scan_lo + 1) : 0u);
+    if (c.collect) c.ct.scan += (unsigned long long)__reduce_add_sync(kFull, scan_lo <= scan_hi ? (unsigned)(scan_hi - scan_lo + 1) : 0u);
     // ---- apply.  Candidates of different lanes are different instances (different chromosomes).
     bool newly_good = false;
     if (live && cand >= 0 && scan_lo <= scan_hi) inst_extend_reads(c.inst[cand], scan_lo, scan_hi);
@@ -607,14 +620,15 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
         int av = v < 0 ? -v : v;
         o0 = __ldg(c.ix.vtx_off + av), o1 = __ldg(c.ix.vtx_off + av + 1);
     }
-    c.ct.occ += o1 - o0;
-    c.ct.pushes++;
+    if (c.collect) c.ct.occ += o1 - o0, c.ct.pushes++;
     bool handled = false;
     if (o1 - o0 <= 32u) {
         handled = push_parallel(c, BACK, v, dist, o0, o1 - o0, e_ch_g, e_ch_pos, e_other);
         if (c.err) return true;
-        if (handled) c.ct.push_par++;
-        else c.ct.push_ser++;
+        if (c.collect) {
+            if (handled) c.ct.push_par++;
+            else c.ct.push_ser++;
+        }
     }
     for (unsigned base = o0; base < o1 && !handled; base += 32) {
         unsigned o = base + (unsigned)c.lane;
@@ -762,7 +776,7 @@ __device__ __forceinline__ long long path_score(Ctx &c)
             total += term;
         }
     }
-    c.ct.score += (unsigned long long)c.ngood;
+    if (c.collect) c.ct.score += (unsigned long long)c.ngood;
     bad = __any_sync(kFull, bad);
     return bad ? -(long long)0x7FFFFFFF : total;
 }
@@ -825,8 +839,17 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
                     const int K = __popc(pend), L = 32 / K;
                     const int k = c.lane / L, dd = c.lane % L + 1;
                     const bool lane_on = k < K;
-                    const int wi = lane_on ? (int)__fns(pend, 0, k + 1) : 0;
-                    const int src = (int)__fns(em, 0, gb + wi + 1);
+                    const int wi = lane_on ? kth_bit4(pend, k) : 0;
+                    // lane of the list entry that is the (gb + wi)-th eligible one: K ballots instead of __fns per lane
+                    int src = 0;
+                    {
+                        const int my_rank = __popc(em & ((1u << c.lane) - 1u));
+                        for (int kk = 0; kk < K; kk++) {
+                            const int target = gb + kth_bit4(pend, kk);
+                            const unsigned hit = __ballot_sync(kFull, elig && my_rank == target);
+                            if (k == kk) src = ffs_lane(hit);
+                        }
+                    }
                     const int id = __shfl_sync(kFull, my_id, src & 31);
                     const unsigned qord = (unsigned)(lb + (src & 31));
                     const Inst &I = c.inst[id];
@@ -843,6 +866,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
                     bool used = false, inpath = false;
                     if (in_range) {
                         const int4 rc = __ldg(c.ix.rec + g);
+                        prefetch_l1(c.ix.occ + rc.z); // the push of this vertex starts with its occurrence list
                         vid = pos ? rc.x : -rc.x;
                         long long dp = (long long)(unsigned)rc.y - (long long)obp;
                         if (dp < 0) dp = -dp;
@@ -877,7 +901,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
                     distinct += __popc(__ballot_sync(kFull, fresh));
                     { // loop-body executions and the epochs each walk depended on
                         const bool stop_in_body = lane_on && dd - 1 == nok && in_range;
-                        if (attempt == 0) c.ct.walk += (unsigned long long)__popc(__ballot_sync(kFull, active || stop_in_body));
+                        if (c.collect && attempt == 0) c.ct.walk += (unsigned long long)__popc(__ballot_sync(kFull, active || stop_in_body));
                         const bool dep = flag >= 0 && !try_used && (active || (stop_in_body && !inpath));
                         for (int kk = 0; kk < K; kk++) {
                             const int lo = __reduce_min_sync(kFull, dep && k == kk ? flag : 0x7FFFFFFF);
@@ -890,7 +914,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
                     unsigned next_pend = 0;
                     for (int kk = 0; kk < K; kk++) {
                         const unsigned segk = L == 32 ? kFull : (((1u << L) - 1u) << (kk * L));
-                        if (!(failm & segk)) next_pend |= 1u << __fns(pend, 0, kk + 1);
+                        if (!(failm & segk)) next_pend |= 1u << kth_bit4(pend, kk);
                     }
                     pend = next_pend;
                     d0 += L;
@@ -977,7 +1001,7 @@ __device__ __forceinline__ int mpv_fast(Ctx &c, bool forward, bool try_used, Nex
     const int L = 32 / E; // 32 or 16 lanes (= depths) per instance
     const int slot = c.lane / L, d = c.lane % L + 1;
     const bool lane_on = slot < E;
-    const int src = lane_on ? (int)__fns(em, 0, slot + 1) : 0;
+    const int src = !lane_on ? 0 : (slot == 0 ? ffs_lane(em) : ffs_lane(em & (em - 1))); // E <= 2 here
     const int id = __shfl_sync(kFull, my_id, src);
     const Inst &I = c.inst[id];
     const bool pos = (I.flags & kPos) != 0;
@@ -993,6 +1017,7 @@ __device__ __forceinline__ int mpv_fast(Ctx &c, bool forward, bool try_used, Nex
     bool used = false, inpath = false;
     if (in_range) {
         const int4 rc = __ldg(c.ix.rec + g);
+        prefetch_l1(c.ix.occ + rc.z);
         vid = pos ? rc.x : -rc.x;
         bp = (unsigned)rc.y, o0 = rc.z, w = (unsigned)rc.w;
         long long dp = (long long)bp - (long long)obp;
@@ -1013,7 +1038,7 @@ __device__ __forceinline__ int mpv_fast(Ctx &c, bool forward, bool try_used, Nex
     const bool active = lane_on && d - 1 < nok;
     { // loop-body executions (walk steps) and the epochs each walk depended on
         const bool stop_in_body = lane_on && d - 1 == nok && in_range;
-        c.ct.walk += (unsigned long long)__popc(__ballot_sync(kFull, active || stop_in_body));
+        if (c.collect) c.ct.walk += (unsigned long long)__popc(__ballot_sync(kFull, active || stop_in_body));
         const bool dep = flag >= 0 && !try_used && (active || (lane_on && d - 1 == nok && in_range && !inpath));
         for (int s = 0; s < E; s++) {
             const int lo = __reduce_min_sync(kFull, dep && slot == s ? flag : 0x7FFFFFFF);
@@ -1059,9 +1084,9 @@ __device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &bes
     for (int attempt = 0; attempt < 2 && nx.vid == 0 && !c.err; attempt++) { // forward retries with tryUsed (:782-785)
         if (attempt == 1 && !FORWARD) break;
         if (mpv_fast(c, FORWARD, attempt == 1, nx, sg)) {
-            c.ct.mpv_fast++;
+            if (c.collect) c.ct.mpv_fast++;
         } else {
-            c.ct.mpv_slow++;
+            if (c.collect) c.ct.mpv_slow++;
             sg.valid = false;
             nx = most_popular_vertex(c, FORWARD, attempt == 1);
         }
