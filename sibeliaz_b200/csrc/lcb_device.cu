@@ -1312,7 +1312,6 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         }
         uint32_t *Ecur = Ebase, *Enew = Ea, *Efree = Eb;
         bool retry = false;
-        unsigned first_dirty = 0;
         for (unsigned round = 1;; round++) {
             ctx->st.rounds++;
             // A. speculative evaluations, plus the commit-time re-runs the last validation queued (tagged items)
@@ -1367,7 +1366,6 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
                 retry = true;
                 break;
             }
-            if (round == 1) first_dirty = ctx->h_ctl->dirty;
             // rotate epoch buffers: the new epochs become current
             if (Ecur == Ebase) {
                 Ecur = Enew, Enew = Efree;
@@ -1429,7 +1427,6 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         {
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_window).count();
             const double rate = n / std::max(ms, 1e-3);
-            (void)first_dirty;
             if (hold > 0) {
                 hold--;
             } else if (n == W && prev_rate > 0 && rate < 0.7 * prev_rate && W > phase) {
