@@ -77,8 +77,8 @@ typedef struct lcb_params {
     int32_t max_flank;     /* maxFlankingSize; the CLI passes -b again (sibeliaz.cpp:136)       */
     int32_t looking_depth; /* hard-coded 8 in the reference (sibeliaz.cpp:137)                  */
     int32_t phase_size;    /* hard-coded 256 (blocksfinder.h:519); part of the output semantics */
-    int32_t window_init;   /* speculation window (seeds), multiple of phase_size; 0 = default   */
-    int32_t window_max;    /* 0 = default                                                       */
+    int32_t window_init;   /* seeds admitted per round at the start (multiple of phase_size); 0 = default */
+    int32_t window_max;    /* bound on the active (speculated, uncommitted) seeds; 0 = default  */
     int32_t device;        /* CUDA device ordinal                                               */
     int32_t collect_counters; /* 1: also count walk / occurrence / scan / score steps on device */
 } lcb_params;
@@ -93,7 +93,7 @@ typedef struct lcb_block_instance { /* BlockInstance(id, chr, start, end), block
 typedef struct lcb_stats {
     uint64_t n_records, n_vertices, n_seeds;
     uint64_t n_block_instances, n_blocks;  /* blocksInstance_.size(), blocksFound_               */
-    uint64_t windows, rounds;              /* speculation windows / evaluation rounds             */
+    uint64_t windows, rounds;              /* times the active set started from empty / evaluation rounds */
     uint64_t traversals_first, traversals_rerun; /* Process() evaluations: phase-snapshot / commit-time */
     uint64_t kernel_launches;              /* kernels of this library launched by find_blocks+enumerate */
     uint64_t t_walk, t_occ, t_scan, t_score; /* device-side step counts (collect_counters=1)      */
@@ -105,6 +105,7 @@ typedef struct lcb_stats {
     double ms_step_device;                 /* CUDA-event time from the start of seed enumeration to the end of
                                               find_blocks on the library's stream (when find_blocks enumerates)  */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t pool_restarts;                /* active sets abandoned because a result pool ran full */
 } lcb_stats;
 
 void lcb_default_params(lcb_params *p);

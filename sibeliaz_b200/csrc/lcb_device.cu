@@ -17,6 +17,11 @@
 // final_i depends only on epochs < i, so the system has exactly one solution -- the reference's result --
 // and Jacobi iteration reaches it: every round re-evaluates (all in parallel) only the seeds whose recorded
 // read-set saw a changed epoch.  Block ids and the blocksInstance_ order are then a prefix sum in seed order.
+//
+// The window ROLLS: seeds [c0, c1) are active; every round admits new seeds at c1 (evaluated against the current
+// epoch estimate, next to the re-evaluations of the unconverged ones, so the latency-bound tail rounds of earlier
+// seeds are filled with fresh work) and commits the clean prefix [c0, first dirty seed): all seeds before the first
+// dirty one are consistent with epochs that only they determine, hence final (same induction as above).
 #include "sibeliaz_lcb.h"
 
 #include <cuda_runtime.h>
@@ -47,18 +52,20 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 
 struct Control { // device-resident round state, mirrored to pinned host memory once per round
     unsigned head;      // work-queue cursor of the running traversal launch
+    unsigned max_ns;    // longest single evaluation since the last reset (globaltimer ns, saturating)
     unsigned n0, n1;    // lengths of the two work lists (slot 0: speculative, slot 1: commit-time re-run)
     unsigned dirty;     // seeds whose dependencies changed in the last validation
+    unsigned first_dirty; // smallest such seed index (0xFFFFFFFF: none): everything before it is final
     unsigned err;       // first LCB_ERR_* raised by a kernel
     unsigned pool_overflow;
     unsigned long long inst_used, rs_used; // bump allocators
     unsigned long long ct_walk, ct_occ, ct_scan, ct_score;
     unsigned long long runs0, runs1;
-    unsigned n_blocks, n_out; // emit: blocks / instances of the current window
+    unsigned blocks_done, out_done; // emit: blocks / instances committed so far
     unsigned long long dbg[5];
 };
 
-struct Window { // per-window arrays, indexed by j = seed - w0
+struct Window { // per-seed arrays of the active seeds, ring-indexed by j = seed & mask
     unsigned *res_off[2], *res_cnt[2]; // best instances of slot s in inst_pool
     unsigned *rs_off[2], *rs_cnt[2];   // read-set of slot s in rs_pool
     unsigned char *conf, *has1;
@@ -67,7 +74,15 @@ struct Window { // per-window arrays, indexed by j = seed - w0
     int4 *inst_pool;
     int2 *rs_pool;
     unsigned long long inst_cap, rs_cap;
+    unsigned mask; // ring size - 1
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 #define CUDA_TRY(x)                                                                                       \
     do {                                                                                                  \
@@ -134,7 +149,7 @@ NcclApi *nccl_api()
 template <bool COLLECT>
 __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
                                                         const int *__restrict__ seed_vid,
-                                                        const unsigned char *__restrict__ seed_ch, unsigned w0,
+                                                        const unsigned char *__restrict__ seed_ch,
                                                         unsigned phase, int force_slot, const unsigned *__restrict__ list,
                                                         const unsigned *__restrict__ n_ptr, Window win, Control *ctl,
                                                         unsigned char *arena_base, size_t arena_stride, int collect)
@@ -167,26 +182,20 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
     }
     const unsigned n = *n_ptr;
     unsigned done = 0, done1 = 0;
+    unsigned long long longest = 0;
     while (true) {
         unsigned idx = 0;
         if (lane == 0) idx = atomicAdd(&ctl->head, 1u);
         idx = __shfl_sync(kFull, idx, 0);
         if (idx >= n) break;
         const unsigned item = list[idx];
-        const unsigned j = item & 0x7FFFFFFFu;
+        const unsigned i = item & 0x7FFFFFFFu;
+        const unsigned j = i & win.mask;
         const int slot = force_slot >= 0 ? force_slot : (int)(item >> 31); // bit 31: commit-time re-run
-        const unsigned i = w0 + j;
         c.thresh = slot == 0 ? (i / phase) * phase : i;
-        const long long t_begin = collect == 2 ? clock64() : 0;
-        const unsigned p_begin = c.ct.pushes, s_begin = c.ct.mpv_slow + c.ct.push_ser;
+        const unsigned long long t_begin = global_ns();
         process_seed(c, seed_vid[i], seed_ch[i]);
-        if (collect == 2 && lane == 0 && slot == 0) {
-            unsigned cyc = (unsigned)min((long long)0xFFFFFFFFll, clock64() - t_begin);
-            if (cyc > win.blk[j]) {
-                win.blk[j] = cyc;
-                win.out_off[j] = ((c.ct.pushes - p_begin) << 12) | min(4095u, c.ct.mpv_slow + c.ct.push_ser - s_begin);
-            }
-        }
+        longest = max(longest, global_ns() - t_begin);
         if (c.err) {
             if (lane == 0) atomicCAS(&ctl->err, 0u, (unsigned)c.err);
             break;
@@ -221,6 +230,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
         else done1++;
     }
     if (lane == 0) {
+        if (longest) atomicMax(&ctl->max_ns, (unsigned)min(longest, 0xFFFFFFFFull));
         if (done) atomicAdd(&ctl->runs0, (unsigned long long)done);
         if (done1) atomicAdd(&ctl->runs1, (unsigned long long)done1);
         if (collect) {
@@ -263,21 +273,21 @@ __device__ __forceinline__ bool result_conflicts(const Window &win, unsigned j, 
 }
 
 // commit-time conflict test for freshly evaluated seeds (blocksfinder.h:375-398); queues re-runs
-__global__ void k_conflict(const uint32_t *__restrict__ E, unsigned w0, const unsigned *__restrict__ list,
+__global__ void k_conflict(const uint32_t *__restrict__ E, const unsigned *__restrict__ list,
                            const unsigned *__restrict__ n_ptr, Window win, Control *ctl)
 {
     const int lane = threadIdx.x & 31;
     const unsigned n = *n_ptr;
     for (unsigned idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += gridDim.x * (blockDim.x >> 5)) {
         if (list[idx] >> 31) continue; // a commit-time re-run queued by the last validation: nothing to test
-        const unsigned j = list[idx];
+        const unsigned i = list[idx], j = i & win.mask;
         bool conf = false;
-        if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, E, w0 + j, lane);
+        if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, E, i, lane);
         if (lane == 0) {
             win.conf[j] = conf;
             if (conf && !win.has1[j]) {
                 win.has1[j] = 1;
-                win.list1[atomicAdd(&ctl->n1, 1u)] = j;
+                win.list1[atomicAdd(&ctl->n1, 1u)] = i;
             }
             if (!conf) win.has1[j] = 0;
         }
@@ -292,17 +302,26 @@ __device__ __forceinline__ void final_result(const Window &win, unsigned j, unsi
     if (cnt <= 1) cnt = 0; // `if (instance.size() > 1)` blocksfinder.h:375,408
 }
 
-// epoch'[e] = min(seed index) over the window's final results
-__global__ void k_claim(uint32_t *__restrict__ Enew, unsigned w0, unsigned n, Window win)
+// start of a round's new epochs: the committed claims only (claims of seeds < c0 are final and minimal)
+__global__ void k_rebase(uint32_t *dst, const uint32_t *src, size_t n, uint32_t c0) // dst may alias src
+{
+    for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t e = src[f];
+        dst[f] = e < c0 ? e : kFree;
+    }
+}
+
+// epoch'[e] = min(seed index) over the final results of the active seeds [lo, hi)
+__global__ void k_claim(uint32_t *__restrict__ Enew, unsigned lo_seed, unsigned hi_seed, Window win)
 {
     const int lane = threadIdx.x & 31;
-    for (unsigned j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += gridDim.x * (blockDim.x >> 5)) {
+    for (unsigned i = lo_seed + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < hi_seed; i += gridDim.x * (blockDim.x >> 5)) {
         unsigned off, cnt;
-        final_result(win, j, off, cnt);
+        final_result(win, i & win.mask, off, cnt);
         for (unsigned t = 0; t < cnt; t++) {
             int lo, hi;
             inst_edges(win.inst_pool[off + t], lo, hi);
-            for (int f = lo + lane; f <= hi; f += 32) atomicMin(&Enew[f], w0 + j);
+            for (int f = lo + lane; f <= hi; f += 32) atomicMin(&Enew[f], i);
         }
     }
 }
@@ -324,17 +343,17 @@ __device__ __forceinline__ bool readset_changed(const int2 *rs, unsigned cnt, co
 }
 
 // re-validate every seed of the window against the new epochs; build next round's work lists
-__global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned w0,
-                           unsigned n, unsigned phase, Window win, Control *ctl)
+__global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned lo_seed,
+                           unsigned hi_seed, unsigned phase, Window win, Control *ctl)
 {
     const int lane = threadIdx.x & 31;
-    for (unsigned j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += gridDim.x * (blockDim.x >> 5)) {
-        const unsigned i = w0 + j;
+    for (unsigned i = lo_seed + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < hi_seed; i += gridDim.x * (blockDim.x >> 5)) {
+        const unsigned j = i & win.mask;
         const uint32_t T = (i / phase) * phase;
         unsigned dirty = 0;
         if (readset_changed(win.rs_pool + win.rs_off[0][j], win.rs_cnt[0][j], Ecur, Enew, T, lane)) {
             if (lane == 0) {
-                win.list0[atomicAdd(&ctl->n0, 1u)] = j;
+                win.list0[atomicAdd(&ctl->n0, 1u)] = i;
                 win.has1[j] = 0;
             }
             dirty = 1;
@@ -352,14 +371,32 @@ __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__
                 win.conf[j] = conf;
                 if (rerun) {
                     win.has1[j] = 1;
-                    win.list0[atomicAdd(&ctl->n0, 1u)] = j | 0x80000000u; // evaluated together with the speculative work
+                    win.list0[atomicAdd(&ctl->n0, 1u)] = i | 0x80000000u; // evaluated together with the speculative work
                 }
                 if (!conf) win.has1[j] = 0;
             }
             if (rerun) dirty = 1;
         }
-        if (lane == 0 && dirty) atomicAdd(&ctl->dirty, 1u);
+        if (lane == 0 && dirty) {
+            atomicAdd(&ctl->dirty, 1u);
+            atomicMin(&ctl->first_dirty, i);
+        }
     }
+}
+
+// admission of the seeds [lo, lo + n): fresh per-seed state; this rank's share (i % R == me) joins work list 0
+__global__ void k_admit(unsigned lo, unsigned n, unsigned R, unsigned me, unsigned n0_before, Window win, Control *ctl)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned first_own = lo + (me + R - lo % R) % R; // smallest i >= lo with i % R == me
+    if (t == 0) ctl->n0 = n0_before + (lo + n > first_own ? (lo + n - first_own + R - 1) / R : 0u);
+    if (t >= n) return;
+    const unsigned i = lo + t, j = i & win.mask;
+    win.res_cnt[0][j] = win.res_cnt[1][j] = 0;
+    win.rs_cnt[0][j] = win.rs_cnt[1][j] = 0;
+    win.conf[j] = 0;
+    win.has1[j] = 0;
+    if (i % R == me) win.list0[n0_before + (i - first_own) / R] = i;
 }
 
 __global__ void k_iota(unsigned *list, unsigned n, unsigned first = 0, unsigned stride = 1)
@@ -371,21 +408,22 @@ __global__ void k_iota(unsigned *list, unsigned n, unsigned first = 0, unsigned 
 // Finalize (blocksfinder.h:312-332) for a converged window: block ids and output offsets are prefix
 // sums in seed order (one block, W <= 65536)
 // per-seed size of the final result (0 for seeds this rank does not own); summed across ranks before the scan
-__global__ void k_final_counts(unsigned n, Window win, unsigned *cnt_out)
+__global__ void k_final_counts(unsigned lo, unsigned n, Window win, unsigned *cnt_out)
 {
-    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
     unsigned off, cnt;
-    final_result(win, j, off, cnt);
-    cnt_out[j] = cnt;
+    final_result(win, (lo + t) & win.mask, off, cnt);
+    cnt_out[t] = cnt;
 }
 
-__global__ void __launch_bounds__(1024) k_emit_scan(unsigned n, Window win, Control *ctl, unsigned blocks_before,
-                                                     unsigned out_before, const unsigned *__restrict__ counts)
+__global__ void __launch_bounds__(1024) k_emit_scan(unsigned first, unsigned n, Window win, Control *ctl,
+                                                     const unsigned *__restrict__ counts)
 {
     __shared__ unsigned sb[1024], so[1024];
+    const unsigned blocks_before = ctl->blocks_done, out_before = ctl->out_done; // updated after the scan's barriers
     const unsigned per = (n + 1023) / 1024;
-    const unsigned lo = threadIdx.x * per, hi = min(n, lo + per);
+    const unsigned lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
     unsigned nb = 0, no = 0;
     for (unsigned j = lo; j < hi; j++) {
         const unsigned cnt = counts[j];
@@ -401,22 +439,23 @@ __global__ void __launch_bounds__(1024) k_emit_scan(unsigned n, Window win, Cont
         __syncthreads();
     }
     unsigned b = blocks_before + sb[threadIdx.x] - nb, o = out_before + so[threadIdx.x] - no;
-    for (unsigned j = lo; j < hi; j++) {
-        const unsigned cnt = counts[j];
+    for (unsigned t = lo; t < hi; t++) {
+        const unsigned cnt = counts[t], j = (first + t) & win.mask;
         win.out_off[j] = o;
         win.blk[j] = cnt ? ++b : 0;
         o += cnt;
     }
     if (threadIdx.x == 1023) {
-        ctl->n_blocks = sb[1023];
-        ctl->n_out = so[1023];
+        ctl->blocks_done = blocks_before + sb[1023];
+        ctl->out_done = out_before + so[1023];
     }
 }
 
-__global__ void k_emit_write(Index ix, int k, unsigned n, Window win, lcb_block_instance *out)
+__global__ void k_emit_write(Index ix, int k, unsigned first, unsigned n, Window win, lcb_block_instance *out)
 {
-    unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    unsigned t_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= n) return;
+    const unsigned j = (first + t_) & win.mask;
     unsigned off, cnt;
     final_result(win, j, off, cnt);
     for (unsigned t = 0; t < cnt; t++) {
@@ -658,7 +697,7 @@ struct lcb_ctx {
     int4 *d_rec = nullptr;
     int2 *d_occ = nullptr;
     uint32_t *d_vtx_off = nullptr, *d_chr_off = nullptr;
-    uint32_t *d_E[3] = {nullptr, nullptr, nullptr};
+    uint32_t *d_E[2] = {nullptr, nullptr};
     // seeds
     uint64_t n_seeds = 0;
     bool seeds_ready = false;
@@ -966,7 +1005,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
         if ((rc = dev_alloc(ctx, &ctx->d_occ, (size_t)N))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
-        for (int e = 0; e < 3; e++)
+        for (int e = 0; e < 2; e++)
             if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
         CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, rec, b_rec, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, oc, b_occ, cudaMemcpyHostToDevice, ctx->stream));
@@ -987,8 +1026,10 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     ctx->st.n_vertices = (uint64_t)V;
     // ---- window state, pools, arena ----
     int rc;
-    const unsigned W = (unsigned)p.window_max;
+    unsigned W = 256; // ring of per-seed state: a power of two >= the largest active set
+    while (W < (unsigned)p.window_max) W <<= 1;
     ctx->wmax = W;
+    ctx->win.mask = W - 1;
     for (int s = 0; s < 2; s++) {
         if ((rc = dev_alloc(ctx, &ctx->win.res_off[s], W))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->win.res_cnt[s], W))) return rc;
@@ -1002,7 +1043,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if ((rc = dev_alloc(ctx, &ctx->win.list0, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.list1, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_wnext, 4))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_wnext, 8))) return rc;
     ctx->win.inst_cap = kInstPoolCap;
     ctx->win.rs_cap = kRsPoolCap;
     if (const char *e = getenv("LCB_TEST_POOL_ENTRIES")) { // testing aid: tiny result pools force the window-halving retry
@@ -1230,17 +1271,17 @@ extern "C" int lcb_get_seeds(lcb_ctx *ctx, int64_t *vid, uint8_t *ch, uint64_t *
 
 namespace {
 
-int launch_traverse(lcb_ctx *ctx, const uint32_t *E, unsigned w0, int slot, const unsigned *list, const unsigned *n_ptr)
+int launch_traverse(lcb_ctx *ctx, const uint32_t *E, int slot, const unsigned *list, const unsigned *n_ptr, bool reset_longest)
 {
     Params pr{ctx->prm.k, ctx->prm.max_branch, ctx->prm.min_block, ctx->prm.max_flank, ctx->prm.looking_depth};
-    CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, sizeof(unsigned), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, (reset_longest ? 2 : 1) * sizeof(unsigned), ctx->stream)); // head (+ max_ns)
     if (ctx->prm.collect_counters)
-        k_traverse<true><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, w0,
+        k_traverse<true><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
                                                                            (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
                                                                            ctx->d_ctl, ctx->d_arena, ctx->arena_stride,
                                                                            ctx->prm.collect_counters);
     else
-        k_traverse<false><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, w0,
+        k_traverse<false><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
                                                                             (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
                                                                             ctx->d_ctl, ctx->d_arena, ctx->arena_stride, 0);
     ctx->st.kernel_launches++;
@@ -1266,186 +1307,144 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     ctx->step_timed = !ctx->seeds_ready;
     if (!ctx->seeds_ready && (rc = lcb_enumerate_seeds(ctx, nullptr))) return rc;
     auto t_begin = std::chrono::steady_clock::now();
+    if (ctx->n_seeds >= 0x7FFFFFF0ull) {
+        ctx->error = "too many seeds for 31-bit work items";
+        return LCB_ERR_ARG;
+    }
     const unsigned S = (unsigned)ctx->n_seeds;
     const unsigned phase = (unsigned)ctx->prm.phase_size;
     const size_t N = (size_t)ctx->ix.N;
-    uint32_t *Ebase = ctx->d_E[0], *Ea = ctx->d_E[1], *Eb = ctx->d_E[2];
-    CUDA_TRY(cudaMemsetAsync(Ebase, 0xFF, (N + 32) * sizeof(uint32_t), ctx->stream));
+    uint32_t *Ecur = ctx->d_E[0], *Enew = ctx->d_E[1];
+    CUDA_TRY(cudaMemsetAsync(Ecur, 0xFF, (N + 32) * sizeof(uint32_t), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(Enew, 0xFF, (N + 32) * sizeof(uint32_t), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
     memset(ctx->h_ctl, 0, sizeof(Control));
     if (ctx->n_ranks > 1) CUDA_TRY(cudaMemsetAsync(ctx->d_out, 0, (N + 1) * sizeof(lcb_block_instance), ctx->stream));
-    unsigned blocks_done = 0, out_done = 0;
-    unsigned W = (unsigned)ctx->prm.window_init;
     const unsigned vgrid = (unsigned)ctx->sms * 8;
+    const unsigned egrid = (unsigned)std::min<size_t>((N + 1023) / 1024 + 1, (size_t)ctx->sms * 16);
     float trav_ms = 0;
-    ctx->st.windows = ctx->st.rounds = 0;
-    double prev_rate = 0;
-    int hold = 0;
+    ctx->st.windows = ctx->st.rounds = ctx->st.pool_restarts = 0;
     const bool trace_rounds = getenv("LCB_TRACE_ROUNDS") != nullptr;
-    for (unsigned w0 = 0; w0 < S;) {
-        const unsigned n = std::min(W, S - w0);
-        const auto t_window = std::chrono::steady_clock::now();
-        // fresh window: every seed needs its speculative evaluation
-        CUDA_TRY(cudaMemsetAsync(ctx->win.conf, 0, n, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(ctx->win.has1, 0, n, ctx->stream));
-        if (ctx->prm.collect_counters == 2) {
-            CUDA_TRY(cudaMemsetAsync(ctx->win.blk, 0, n * sizeof(unsigned), ctx->stream));
-            CUDA_TRY(cudaMemsetAsync(ctx->win.out_off, 0, n * sizeof(unsigned), ctx->stream));
+    const unsigned R = (unsigned)ctx->n_ranks, me = (unsigned)ctx->rank;
+    // rolling active set [c0, c1): c0 = commit frontier, c1 = admission frontier
+    unsigned c0 = 0, c1 = 0;
+    unsigned n0 = 0;                                     // this rank's work list 0 as left by the last validation
+    unsigned delta = (unsigned)ctx->prm.window_init;     // seeds admitted per round (adapted)
+    unsigned cap = (unsigned)ctx->prm.window_max;        // bound on the active set (halved by pool overflows)
+    bool drain = false;                                  // result pools half full: stop admitting until the set is empty
+    while (c0 < S) {
+        // ---- admission
+        if (c0 == c1) { // nothing active: no pool entry is referenced any more
+            CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->inst_used, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            drain = false;
+            n0 = 0;
+            ctx->st.windows++;
         }
-        // seeds are dealt round-robin over the ranks; a rank sees the others' seeds as "no result, empty read-set"
-        const unsigned R = (unsigned)ctx->n_ranks, me = (unsigned)ctx->rank;
-        const unsigned n_own = n > me ? (n - me + R - 1) / R : 0;
-        for (int s = 0; s < 2; s++) { // every seed starts as "no result, empty read-set" (other ranks' seeds stay that way)
-            CUDA_TRY(cudaMemsetAsync(ctx->win.res_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
-            CUDA_TRY(cudaMemsetAsync(ctx->win.rs_cnt[s], 0, n * sizeof(unsigned), ctx->stream));
+        unsigned admit = 0;
+        if (!drain && c1 < S && c1 - c0 < cap) admit = std::min(std::min(delta, S - c1), cap - (c1 - c0));
+        if (admit) {
+            k_admit<<<(admit + 255) / 256, 256, 0, ctx->stream>>>(c1, admit, R, me, n0, ctx->win, ctx->d_ctl);
+            ctx->st.kernel_launches++;
+            c1 += admit;
         }
-        if (n_own) k_iota<<<(n_own + 255) / 256, 256, 0, ctx->stream>>>(ctx->win.list0, n_own, me, R);
-        ctx->st.kernel_launches++;
+        ctx->st.rounds++;
+        // A. speculative evaluations (new + invalidated seeds), plus the commit-time re-runs the last validation
+        //    queued (tagged items)
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        if ((rc = launch_traverse(ctx, Ecur, -1, ctx->win.list0, &ctx->d_ctl->n0, true))) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        // B. commit-time conflicts of the freshly evaluated seeds
+        k_conflict<<<vgrid, 256, 0, ctx->stream>>>(Ecur, ctx->win.list0, &ctx->d_ctl->n0, ctx->win, ctx->d_ctl);
+        // C. commit-time re-runs of the conflicts found in B
+        CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
+        if ((rc = launch_traverse(ctx, Ecur, 1, ctx->win.list1, &ctx->d_ctl->n1, false))) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
+        // D. new epochs: committed claims + the active seeds' current final results
+        k_rebase<<<egrid, 256, 0, ctx->stream>>>(Enew, Ecur, N, c0);
+        k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, c0, c1, ctx->win);
+#ifdef LCB_WITH_NCCL
+        // the one real exchange of the path: every rank's claims meet in a min-reduction over NVLink
+        if (R > 1) NCCL_TRY(ncclAllReduce(Enew, Enew, N, ncclUint32, ncclMin, ctx->comm, ctx->stream));
+#endif
+        // E. validation + next work lists
+        CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream));        // n0, n1, dirty
+        CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->first_dirty, 0xFF, sizeof(unsigned), ctx->stream));
+        k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, c0, c1, phase, ctx->win, ctx->d_ctl);
+        ctx->st.kernel_launches += 4;
+        if ((rc = fetch_control(ctx))) return rc;
+        float ms = 0, ms1 = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        cudaEventElapsedTime(&ms1, ctx->ev2, ctx->ev3);
+        trav_ms += ms + ms1;
+        Control &h = *ctx->h_ctl;
+        if (h.inst_used * 2 > ctx->win.inst_cap || h.rs_used * 2 > ctx->win.rs_cap) drain = true;
+        // Admission rate: a launch lasts max(longest evaluation, work / resident warps).  While it is latency-bound
+        // more fresh seeds are free; when the fresh work dominates, far-ahead speculation only adds re-evaluations.
+        unsigned next_delta = delta;
         {
-            Control z{};
-            z.n0 = n_own;
-            z.ct_walk = ctx->h_ctl->ct_walk, z.ct_occ = ctx->h_ctl->ct_occ, z.ct_scan = ctx->h_ctl->ct_scan,
-            z.ct_score = ctx->h_ctl->ct_score, z.runs0 = ctx->h_ctl->runs0, z.runs1 = ctx->h_ctl->runs1;
-            for (int q = 0; q < 5; q++) z.dbg[q] = ctx->h_ctl->dbg[q];
-            *ctx->h_ctl = z;
-            CUDA_TRY(cudaMemcpyAsync(ctx->d_ctl, ctx->h_ctl, sizeof(Control), cudaMemcpyHostToDevice, ctx->stream));
+            const double longest_ms = h.max_ns * 1e-6;
+            if (ms < 1.5 * longest_ms || ms < 0.25) next_delta = (unsigned)std::min<unsigned long long>((unsigned long long)ctx->prm.window_max, 2ull * delta);
+            else if (ms > 3.0 * longest_ms) next_delta = std::max(phase, delta / 2 / phase * phase);
         }
-        uint32_t *Ecur = Ebase, *Enew = Ea, *Efree = Eb;
-        bool retry = false;
-        for (unsigned round = 1;; round++) {
-            ctx->st.rounds++;
-            // A. speculative evaluations, plus the commit-time re-runs the last validation queued (tagged items)
-            CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-            if ((rc = launch_traverse(ctx, Ecur, w0, -1, ctx->win.list0, &ctx->d_ctl->n0))) return rc;
-            CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-            // B. commit-time conflicts of the freshly evaluated seeds
-            k_conflict<<<vgrid, 256, 0, ctx->stream>>>(Ecur, w0, ctx->win.list0, &ctx->d_ctl->n0, ctx->win, ctx->d_ctl);
-            // C. commit-time re-runs of the conflicts found in B
-            CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
-            if ((rc = launch_traverse(ctx, Ecur, w0, 1, ctx->win.list1, &ctx->d_ctl->n1))) return rc;
-            CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
-            // D. new epochs
-            CUDA_TRY(cudaMemcpyAsync(Enew, Ebase, N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-            k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, w0, n, ctx->win);
+        unsigned first_dirty = h.first_dirty;
 #ifdef LCB_WITH_NCCL
-            // the one real exchange of the path: every rank's claims meet in a min-reduction over NVLink
-            if (R > 1) NCCL_TRY(ncclAllReduce(Enew, Enew, N, ncclUint32, ncclMin, ctx->comm, ctx->stream));
-#endif
-            // E. validation + next work lists
-            CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream)); // n0, n1, dirty
-            k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, w0, n, phase, ctx->win, ctx->d_ctl);
-            ctx->st.kernel_launches += 3;
-            if ((rc = fetch_control(ctx))) return rc;
-#ifdef LCB_WITH_NCCL
-            if (R > 1) { // agree on termination / failure: {dirty, err, pool_overflow} summed over ranks
-                unsigned local[4] = {ctx->h_ctl->dirty, ctx->h_ctl->err, ctx->h_ctl->pool_overflow, 0};
-                CUDA_TRY(cudaMemcpyAsync(ctx->d_wnext, local, sizeof local, cudaMemcpyHostToDevice, ctx->stream));
-                NCCL_TRY(ncclAllReduce(ctx->d_wnext, ctx->d_wnext, 4, ncclUint32, ncclSum, ctx->comm, ctx->stream));
-                CUDA_TRY(cudaMemcpyAsync(local, ctx->d_wnext, sizeof local, cudaMemcpyDeviceToHost, ctx->stream));
-                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-                ctx->h_ctl->dirty = local[0];
-                if (local[1] && !ctx->h_ctl->err) ctx->h_ctl->err = LCB_ERR_CAPACITY;
-                ctx->h_ctl->pool_overflow = local[2];
-            }
-#endif
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-            trav_ms += ms;
-            float ms1 = 0;
-            cudaEventElapsedTime(&ms1, ctx->ev2, ctx->ev3);
-            trav_ms += ms1;
-            if (trace_rounds)
-                fprintf(stderr, "[round] w0=%u n=%u round=%u speculative=%.3f ms rerun=%.3f ms next: n0=%u n1=%u dirty=%u\n", w0, n, round, ms, ms1,
-                        ctx->h_ctl->n0, ctx->h_ctl->n1, ctx->h_ctl->dirty);
-            if (ctx->h_ctl->err) {
-                ctx->arena_dirty = true;
-                ctx->error = "a per-seed device buffer overflowed its hard cap (path, instance or read-set too large)";
-                return (int)ctx->h_ctl->err;
-            }
-            if (ctx->h_ctl->pool_overflow) {
-                retry = true;
-                break;
-            }
-            // rotate epoch buffers: the new epochs become current
-            if (Ecur == Ebase) {
-                Ecur = Enew, Enew = Efree;
-            } else {
-                std::swap(Ecur, Enew);
-            }
-            if (ctx->h_ctl->dirty == 0) break;
+        if (R > 1) { // every rank must take the same decisions: one max-reduction carries them all
+            unsigned local[6] = {~first_dirty, h.err, h.pool_overflow, drain ? 1u : 0u, me == 0 ? next_delta : 0u, 0u};
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_wnext, local, sizeof local, cudaMemcpyHostToDevice, ctx->stream));
+            NCCL_TRY(ncclAllReduce(ctx->d_wnext, ctx->d_wnext, 6, ncclUint32, ncclMax, ctx->comm, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(local, ctx->d_wnext, sizeof local, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            first_dirty = ~local[0];
+            if (local[1] && !h.err) h.err = LCB_ERR_CAPACITY;
+            h.pool_overflow = local[2];
+            drain = local[3] != 0;
+            next_delta = local[4];
         }
-        if (trace_rounds && ctx->prm.collect_counters == 2) { // developer aid: slowest seeds of the window
-            std::vector<unsigned> c0(n), c1(n), rc0(n), rs0(n);
-            std::vector<int> vids(n);
-            cudaMemcpy(c0.data(), ctx->win.blk, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(c1.data(), ctx->win.out_off, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(rc0.data(), ctx->win.res_cnt[0], n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(rs0.data(), ctx->win.rs_cnt[0], n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(vids.data(), ctx->d_seed_vid + w0, n * 4, cudaMemcpyDeviceToHost);
-            std::vector<unsigned> idx(n);
-            for (unsigned q = 0; q < n; q++) idx[q] = q;
-            std::partial_sort(idx.begin(), idx.begin() + std::min(n, 6u), idx.end(), [&](unsigned a, unsigned b) { return c0[a] > c0[b]; });
-            unsigned long long sum = 0;
-            for (unsigned q = 0; q < n; q++) sum += c0[q];
-            fprintf(stderr, "[slow] window w0=%u: mean speculative %.1f kcycles; top:", w0, sum / 1e3 / n);
-            for (unsigned q = 0; q < std::min(n, 6u); q++)
-                fprintf(stderr, " (seed %u vid %d: %u kcyc, %u pushes, %u slow-path calls, %u inst, %u reads)", w0 + idx[q], vids[idx[q]], c0[idx[q]] / 1000, c1[idx[q]] >> 12, c1[idx[q]] & 4095, rc0[idx[q]], rs0[idx[q]]);
-            fprintf(stderr, "\n[slow] cumulative pushes %llu mpv fast/slow %llu/%llu push parallel/serial %llu/%llu\n", ctx->h_ctl->dbg[0], ctx->h_ctl->dbg[1], ctx->h_ctl->dbg[2], ctx->h_ctl->dbg[3], ctx->h_ctl->dbg[4]);
+#endif
+        if (trace_rounds)
+            fprintf(stderr, "[round] %llu active [%u,%u) admitted %u speculative=%.3f ms rerun=%.3f ms longest=%.3f ms next: n0=%u dirty=%u first=%u delta=%u pools %.1f%% %.1f%%\n",
+                    (unsigned long long)ctx->st.rounds, c0, c1, admit, ms, ms1, h.max_ns * 1e-6, h.n0, h.dirty, first_dirty, next_delta,
+                    100.0 * h.inst_used / ctx->win.inst_cap, 100.0 * h.rs_used / ctx->win.rs_cap);
+        if (h.err) {
+            ctx->arena_dirty = true;
+            ctx->error = "a per-seed device buffer overflowed its hard cap (path, instance or read-set too large)";
+            return (int)h.err;
         }
-        if (retry) {
-            if (W <= phase) {
-                ctx->error = "window result pools overflowed at the minimum window size";
+        if (h.pool_overflow) {
+            // a result pool ran full: forget the active set (committed seeds are final), halve it and start again
+            if (c1 - c0 <= phase) {
+                ctx->error = "result pools overflowed at the minimum active set (one phase)";
                 return LCB_ERR_CAPACITY;
             }
-            W = std::max(phase, W / 2 / phase * phase);
+            cap = std::max(phase, (c1 - c0) / 2 / phase * phase);
+            delta = std::min(delta, cap);
+            c1 = c0;
+            CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->pool_overflow, 0, sizeof(unsigned), ctx->stream));
+            k_rebase<<<egrid, 256, 0, ctx->stream>>>(Ecur, Ecur, N, c0); // drop the abandoned seeds' claims
+            ctx->st.kernel_launches++;
+            ctx->st.pool_restarts++;
             continue;
         }
-        // window converged: Ecur holds base + this window's claims
-        k_final_counts<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->win, ctx->d_counts);
+        // F. commit the clean prefix: Finalize in seed order (block ids, blocksInstance_ records)
+        const unsigned fd = std::min(first_dirty, c1);
+        if (fd > c0) {
+            const unsigned n = fd - c0;
+            k_final_counts<<<(n + 255) / 256, 256, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_counts);
 #ifdef LCB_WITH_NCCL
-        if (R > 1) NCCL_TRY(ncclAllReduce(ctx->d_counts, ctx->d_counts, n, ncclUint32, ncclSum, ctx->comm, ctx->stream));
+            if (R > 1) NCCL_TRY(ncclAllReduce(ctx->d_counts, ctx->d_counts, n, ncclUint32, ncclSum, ctx->comm, ctx->stream));
 #endif
-        k_emit_scan<<<1, 1024, 0, ctx->stream>>>(n, ctx->win, ctx->d_ctl, blocks_done, out_done, ctx->d_counts);
-        k_emit_write<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ix, ctx->prm.k, n, ctx->win, ctx->d_out);
-        ctx->st.kernel_launches += 3;
-        if ((rc = fetch_control(ctx))) return rc;
-        blocks_done += ctx->h_ctl->n_blocks;
-        out_done += ctx->h_ctl->n_out;
-        Ebase = Ecur; // the converged epochs become the committed base; the other two buffers are scratch again
-        {
-            int q = 0;
-            uint32_t *other[2] = {nullptr, nullptr};
-            for (int e = 0; e < 3; e++)
-                if (ctx->d_E[e] != Ebase) other[q++] = ctx->d_E[e];
-            Ea = other[0], Eb = other[1];
+            k_emit_scan<<<1, 1024, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_ctl, ctx->d_counts);
+            k_emit_write<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ix, ctx->prm.k, c0, n, ctx->win, ctx->d_out);
+            ctx->st.kernel_launches += 3;
+            c0 = fd;
         }
-        ctx->st.windows++;
-        w0 += n;
-        // Adapt the window by measured throughput (seeds per ms).  The traversal is latency-bound, so wider
-        // windows are nearly free until speculation on stale epochs multiplies the work (repeat-rich seeds);
-        // grow while the rate holds, step back and hold for a few windows when it drops.
-        {
-            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_window).count();
-            const double rate = n / std::max(ms, 1e-3);
-            if (hold > 0) {
-                hold--;
-            } else if (n == W && prev_rate > 0 && rate < 0.7 * prev_rate && W > phase) {
-                W = std::max(phase, W / 2 / phase * phase);
-                hold = 3;
-            } else if (n == W) {
-                W = std::min((unsigned)ctx->prm.window_max, W * 2);
-            }
-            prev_rate = rate;
-#ifdef LCB_WITH_NCCL
-            if (R > 1) { // every rank must walk the same windows: rank 0's choice wins
-                CUDA_TRY(cudaMemcpyAsync(ctx->d_wnext, &W, sizeof W, cudaMemcpyHostToDevice, ctx->stream));
-                NCCL_TRY(ncclBroadcast(ctx->d_wnext, ctx->d_wnext, 1, ncclUint32, 0, ctx->comm, ctx->stream));
-                CUDA_TRY(cudaMemcpyAsync(&W, ctx->d_wnext, sizeof W, cudaMemcpyDeviceToHost, ctx->stream));
-                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            }
-#endif
-        }
+        std::swap(Ecur, Enew); // the new epochs become current
+        n0 = h.n0;
+        delta = std::min(next_delta, cap);
     }
+    if ((rc = fetch_control(ctx))) return rc; // totals of the last commit
+    const unsigned out_done = ctx->h_ctl->out_done, blocks_done = ctx->h_ctl->blocks_done;
     // ---- results ----
     auto t_d2h = std::chrono::steady_clock::now();
     lcb_block_instance *host = (lcb_block_instance *)malloc(sizeof(lcb_block_instance) * std::max<size_t>(out_done, 1));
