@@ -76,7 +76,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("LCB_LIB_PATH") or LIB_PATH  # LCB_LIB_PATH: developer builds (build.py --selfcheck)
     if not os.path.exists(path):
         raise LcbError(4, "%s is missing: run `python -m sibeliaz_b200.build` (there is no fallback path)" % path)
     lib = C.CDLL(path)
@@ -110,7 +110,7 @@ def load_library(path=None):
     lib.lcb_write_output.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_char_p, C.c_int, C.c_int,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
     lib.lcb_version.restype = C.c_char_p
-    if path == LIB_PATH:
+    if path in (LIB_PATH, os.environ.get("LCB_LIB_PATH")):
         _lib = lib
     return lib
 

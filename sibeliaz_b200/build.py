@@ -61,6 +61,24 @@ def _run(cmd):
     return r.stdout
 
 
+def build_selfcheck(verbose=False):
+    """Developer build: every shortcut path of the traversal also runs the general path and compares (-DLCB_CHECK_MPV);
+    a mismatch makes lcb_find_blocks fail with code 90.  Load it with LCB_LIB_PATH=<returned path>."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    inc = os.path.join(ROOT, "include")
+    srcs = [os.path.join(CSRC, f) for f in ("lcb_device.cu", "lcb_host.cpp")]
+    out = os.path.join(LIBDIR, "libsibeliaz_lcb_check.so")
+    cmd = [_nvcc()] + ARCH + NVCC_FLAGS + ["-DLCB_CHECK_MPV", "-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", out] + srcs
+    nccl = _nccl()
+    if nccl:
+        cmd += ["-DLCB_WITH_NCCL", "-I", nccl[0], '-DLCB_NCCL_PATH="%s"' % nccl[1], "-ldl"]
+    cmd += ["-cudart", "shared"]
+    o = _run(cmd)
+    if verbose:
+        print(o)
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(BINDIR, exist_ok=True)
@@ -86,4 +104,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--selfcheck" in sys.argv:
+        print(build_selfcheck(verbose=True))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -62,7 +62,7 @@ struct Control { // device-resident round state, mirrored to pinned host memory 
     unsigned long long ct_walk, ct_occ, ct_scan, ct_score;
     unsigned long long runs0, runs1;
     unsigned blocks_done, out_done; // emit: blocks / instances committed so far
-    unsigned long long dbg[5];
+    unsigned long long dbg[6];
 };
 
 struct Window { // per-seed arrays of the active seeds, ring-indexed by j = seed & mask
@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
     c.err = 0;
     c.collect = COLLECT;
     c.ct.walk = c.ct.occ = c.ct.scan = c.ct.score = 0;
-    c.ct.pushes = c.ct.mpv_fast = c.ct.mpv_slow = c.ct.push_par = c.ct.push_ser = 0;
+    c.ct.pushes = c.ct.mpv_fast = c.ct.mpv_mid = c.ct.mpv_slow = c.ct.push_par = c.ct.push_ser = 0;
+    c.vote_clean = false;
     {
         unsigned char *p = arena_base + warp_global * arena_stride;
         c.ar.inst = (Inst *)p, p += sizeof(Inst) * kInstMax;
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
             atomicAdd(&ctl->dbg[2], (unsigned long long)c.ct.mpv_slow);
             atomicAdd(&ctl->dbg[3], (unsigned long long)c.ct.push_par);
             atomicAdd(&ctl->dbg[4], (unsigned long long)c.ct.push_ser);
+            atomicAdd(&ctl->dbg[5], (unsigned long long)c.ct.mpv_mid);
         }
     }
 }

@@ -96,7 +96,7 @@ struct WarpArena { // per-warp HBM scratch (spill + variable-length logs)
 
 struct Counters {
     unsigned long long walk, occ, scan, score;
-    unsigned pushes, mpv_fast, mpv_slow, push_par, push_ser; // developer diagnostics
+    unsigned pushes, mpv_fast, mpv_mid, mpv_slow, push_par, push_ser; // developer diagnostics
 };
 
 struct Ctx { // warp-uniform traversal state (registers)
@@ -122,6 +122,7 @@ struct Ctx { // warp-uniform traversal state (registers)
     int ninst, ngood, nbest, hcount, nrs;
     int err; // 0 or LCB_ERR_CAPACITY
     bool collect; // count walk/occurrence/scan/score steps (diagnostics; off on the timed path)
+    bool vote_clean; // the shared-memory vote table is all-empty (mpv_mid leaves it so, the general path does not)
     // shadow state (WarpSmem::s_*)
     bool snap_valid;
     int snap_ninst, snap_ngood, snap_hcount, snap_right_flank, snap_right_vertex, snap_nright;
@@ -813,6 +814,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
     int2 *tab = c.sm->vote;
     unsigned *last = c.sm->vlast;
     int cap = kVoteSmem;
+    c.vote_clean = false;
     for (int attempt = 0; attempt < 2; attempt++) {
         for (int i = c.lane; i < cap; i += 32) tab[i] = make_int2(0, 0), last[i] = 0u;
         __syncwarp();
@@ -967,6 +969,188 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
     return best;
 }
 
+
+// MostPopularVertex for up to four walks of up to 8 * kMidTiers junctions each -- the common case on a handful of
+// genomes, where the general path would spend two or three serial passes.  Every lane owns one depth of one walk in each
+// tier, so all junction records and epochs of all walks are requested at once (one memory round trip), the vote is
+// accumulated once in the shared-memory table, and the closed-form resolution (see most_popular_vertex) is evaluated by
+// the lanes that own the items instead of by scanning the table; the lanes then empty the slots they used.
+// Returns 0 when the general path must be taken (more walks, or a walk longer than its lanes).
+constexpr int kMidTiers = 3;
+__device__ __forceinline__ int mpv_mid(Ctx &c, bool forward, bool try_used, Next &best)
+{
+    const int start_vid = forward ? c.right_vertex : c.left_vertex;
+    const bool use_good = c.ngood >= 2;
+    const int n = use_good ? c.ngood : c.ninst;
+    best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
+    if (n > 32) return 0;
+    int my_id = 0;
+    bool elig = false;
+    if (c.lane < n) {
+        my_id = use_good ? (int)c.good[c.lane] : c.lane;
+        elig = (forward ? c.inst[my_id].bv : c.inst[my_id].fv) == start_vid;
+    }
+    const unsigned em = __ballot_sync(kFull, elig);
+    const int E = __popc(em);
+    if (E == 0) return 1;
+    if (E > 4) return 0;
+    const int k = c.lane >> 3, dd = c.lane & 7;
+    const bool lane_on = k < E;
+    int src = 0;
+    {
+        unsigned m = em;
+        for (int kk = 0; kk < E; kk++) {
+            const int l = ffs_lane(m);
+            m &= m - 1;
+            if (k == kk) src = l;
+        }
+    }
+    const int id = __shfl_sync(kFull, my_id, src);
+    const Inst &I = c.inst[id];
+    const bool pos = (I.flags & kPos) != 0;
+    const int og = forward ? I.bg : I.fg;
+    const unsigned obp = forward ? I.bbp : I.fbp;
+    const unsigned weight = (I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp) + 1u;
+    const int clo = I.clo, chi = I.chi;
+    const int step = (forward == pos) ? 1 : -1;
+    const unsigned seg = 0xFFu << (k * 8);
+    int vid[kMidTiers], flag[kMidTiers];
+    bool inr[kMidTiers], ok[kMidTiers], inpath[kMidTiers];
+    {
+        int4 rc[kMidTiers];
+        uint32_t ep[kMidTiers];
+#pragma unroll
+        for (int t = 0; t < kMidTiers; t++) { // every load of every walk is in flight before the first one is used
+            const int g = og + step * (t * 8 + dd + 1);
+            inr[t] = lane_on && g >= clo && g < chi; // it.Valid()
+            const bool has = pos || g > clo;
+            flag[t] = (inr[t] && has) ? (pos ? g : g - 1) : -1;
+            rc[t] = make_int4(0, 0, 0, 0);
+            ep[t] = kFree;
+            if (inr[t]) rc[t] = __ldg(c.ix.rec + g);
+            if (flag[t] >= 0 && !try_used) ep[t] = __ldg(c.E + flag[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < kMidTiers; t++) {
+            const int d = t * 8 + dd + 1;
+            vid[t] = 0;
+            inpath[t] = false;
+            bool used = false;
+            if (inr[t]) {
+                if (t == 0) prefetch_l1(c.ix.occ + rc[t].z); // the push of this vertex starts with its occurrence list
+                vid[t] = pos ? rc[t].x : -rc[t].x;
+                long long dp = (long long)(unsigned)rc[t].y - (long long)obp;
+                if (dp < 0) dp = -dp;
+                inr[t] = d < c.pr.depth || dp <= c.pr.b;
+            }
+            if (inr[t]) {
+                used = flag[t] >= 0 && ep[t] < c.thresh; // ep stays kFree under try_used
+                inpath[t] = hash_find(c.hash, c.hmask, vid[t]) != kNotSet;
+            } else {
+                flag[t] = -1;
+            }
+            ok[t] = inr[t] && !inpath[t] && !used;
+        }
+    }
+    // first junction of every walk that ends it
+    int nok = 8 * kMidTiers;
+#pragma unroll
+    for (int t = kMidTiers - 1; t >= 0; t--) {
+        const unsigned fail = __ballot_sync(kFull, lane_on && !ok[t]) & seg;
+        if (fail) nok = t * 8 + ffs_lane(fail) - k * 8;
+    }
+    if (__any_sync(kFull, lane_on && nok == 8 * kMidTiers)) return 0; // a walk needs more depth than its lanes offer
+    bool active[kMidTiers];
+    int mylo = 0x7FFFFFFF, myhi = -1;
+    unsigned steps = 0;
+#pragma unroll
+    for (int t = 0; t < kMidTiers; t++) {
+        const int di = t * 8 + dd; // 0-based depth
+        active[t] = lane_on && di < nok;
+        const bool stop_in_body = lane_on && di == nok && inr[t];
+        if (c.collect) steps += (unsigned)__popc(__ballot_sync(kFull, active[t] || stop_in_body));
+        const bool dep = flag[t] >= 0 && !try_used && (active[t] || (stop_in_body && !inpath[t]));
+        if (dep) mylo = min(mylo, flag[t]), myhi = max(myhi, flag[t]);
+    }
+    if (c.collect) c.ct.walk += steps;
+    for (int s = 0; s < E; s++) { // the epochs each walk depended on
+        const int lo = __reduce_min_sync(kFull, k == s ? mylo : 0x7FFFFFFF);
+        const int hi = __reduce_max_sync(kFull, k == s ? myhi : -1);
+        const int sid = __shfl_sync(kFull, id, s * 8);
+        if (lo <= hi && c.lane == 0) inst_extend_reads(c.inst[sid], lo, hi);
+    }
+    __syncwarp();
+    // ---- vote
+    int2 *tab = c.sm->vote;
+    unsigned *last = c.sm->vlast;
+    if (!c.vote_clean) {
+        for (int i = c.lane; i < kVoteSmem; i += 32) tab[i] = make_int2(0, 0), last[i] = 0u;
+        c.vote_clean = true;
+        __syncwarp();
+    }
+    unsigned sl[kMidTiers], ev[kMidTiers];
+#pragma unroll
+    for (int t = 0; t < kMidTiers; t++) {
+        sl[t] = 0;
+        ev[t] = ((unsigned)src << 20) | (unsigned)(t * 8 + dd + 1);
+        if (active[t]) { // count[vid] += weight; remember the last (list position, depth) that touched it
+            unsigned x = (hash_of(vid[t]) >> 12) & (unsigned)(kVoteSmem - 1);
+            while (true) {
+                const int old = atomicCAS(&tab[x].x, 0, vid[t]);
+                if (old == 0 || old == vid[t]) break;
+                x = (x + 1) & (unsigned)(kVoteSmem - 1);
+            }
+            sl[t] = x;
+            atomicAdd((unsigned *)&tab[x].y, weight);
+            atomicMax(&last[x], ev[t]);
+        }
+    }
+    __syncwarp();
+    // ---- resolve: among the vertices with the maximal final count, the one whose LAST increment came from the smallest
+    // origin (- strand first, then (chr, idx)); that increment's item is the winner and also names the walk to follow
+    unsigned total[kMidTiers];
+    bool is_last[kMidTiers];
+    unsigned mymax = 0;
+#pragma unroll
+    for (int t = 0; t < kMidTiers; t++) {
+        total[t] = 0;
+        is_last[t] = false;
+        if (active[t]) {
+            total[t] = (unsigned)tab[sl[t]].y;
+            is_last[t] = last[sl[t]] == ev[t];
+            mymax = max(mymax, total[t]);
+        }
+    }
+    const unsigned M = __reduce_max_sync(kFull, mymax);
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < kMidTiers; t++)
+        if (active[t]) tab[sl[t]] = make_int2(0, 0), last[sl[t]] = 0u; // leave the table empty
+    __syncwarp();
+    if (M == 0) return 1;
+    const unsigned okey = (pos ? 0x80000000u : 0u) | (unsigned)og;
+    unsigned myev = 0xFFFFFFFFu;
+    int myt = -1;
+#pragma unroll
+    for (int t = 0; t < kMidTiers; t++)
+        if (is_last[t] && total[t] == M && ev[t] < myev) myev = ev[t], myt = t;
+    const unsigned kmin = __reduce_min_sync(kFull, myt >= 0 ? okey : 0xFFFFFFFFu);
+    // candidates of one walk share okey; different walks with equal okey cannot exist (an origin is one junction+strand)
+    const unsigned emin = __reduce_min_sync(kFull, (myt >= 0 && okey == kmin) ? myev : 0xFFFFFFFFu);
+    const unsigned win = __ballot_sync(kFull, myt >= 0 && okey == kmin && myev == emin);
+    if (!win) return 1;
+    const int wl = ffs_lane(win);
+    int wv = 0;
+#pragma unroll
+    for (int t = 0; t < kMidTiers; t++)
+        if (myt == t) wv = vid[t];
+    best.vid = __shfl_sync(kFull, wv, wl);
+    best.og = __shfl_sync(kFull, og, wl);
+    best.opos = __shfl_sync(kFull, (int)pos, wl) != 0;
+    best.d = (int)(emin & 0xFFFFFu);
+    return 1;
+}
+
 struct Staged { // per-lane copy of the look-ahead walks of the last MostPopularVertex (fast path)
     int vid, o0;
     unsigned bp, w;
@@ -1085,9 +1269,14 @@ __device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &bes
         if (attempt == 1 && !FORWARD) break;
         if (mpv_fast(c, FORWARD, attempt == 1, nx, sg)) {
             if (c.collect) c.ct.mpv_fast++;
+        } else if (sg.valid = false, mpv_mid(c, FORWARD, attempt == 1, nx)) {
+            if (c.collect) c.ct.mpv_mid++;
+#ifdef LCB_CHECK_MPV
+            const Next chk = most_popular_vertex(c, FORWARD, attempt == 1);
+            if (chk.vid != nx.vid || (nx.vid != 0 && (chk.og != nx.og || chk.d != nx.d || chk.opos != nx.opos))) c.err = 90;
+#endif
         } else {
             if (c.collect) c.ct.mpv_slow++;
-            sg.valid = false;
             nx = most_popular_vertex(c, FORWARD, attempt == 1);
         }
     }
