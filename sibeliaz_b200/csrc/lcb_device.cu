@@ -53,7 +53,7 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 struct Control { // device-resident round state, mirrored to pinned host memory once per round
     unsigned head;      // work-queue cursor of the running traversal launch
     unsigned max_ns;    // longest single evaluation since the last reset (globaltimer ns, saturating)
-    unsigned n0, n1;    // lengths of the two work lists (slot 0: speculative, slot 1: commit-time re-run)
+    unsigned n0, n1;    // length of the work list (bit 31 of an item: commit-time re-run only); n1 unused
     unsigned dirty;     // seeds whose dependencies changed in the last validation
     unsigned first_dirty; // smallest such seed index (0xFFFFFFFF: none): everything before it is final
     unsigned err;       // first LCB_ERR_* raised by a kernel
@@ -70,7 +70,7 @@ struct Window { // per-seed arrays of the active seeds, ring-indexed by j = seed
     unsigned *rs_off[2], *rs_cnt[2];   // read-set of slot s in rs_pool
     unsigned char *conf, *has1;
     unsigned *blk, *out_off;
-    unsigned *list0, *list1;
+    unsigned *list0;
     int4 *inst_pool;
     int2 *rs_pool;
     unsigned long long inst_cap, rs_cap;
@@ -143,6 +143,14 @@ NcclApi *nccl_api()
     } while (0)
 #endif
 
+// edges of one instance as an epoch index range: Finalize's MarkUsed loop (blocksfinder.h:327-330)
+__device__ __forceinline__ void inst_edges(const int4 &b, int &lo, int &hi)
+{
+    int fg = b.x & 0x7FFFFFFF, bg = b.y;
+    lo = min(fg, bg);
+    hi = max(fg, bg) - 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // traversal kernel: persistent warps pull (seed, slot) items from a list
 // ------------------------------------------------------------------------------------------------
@@ -192,43 +200,67 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
         const unsigned item = list[idx];
         const unsigned i = item & 0x7FFFFFFFu;
         const unsigned j = i & win.mask;
-        const int slot = force_slot >= 0 ? force_slot : (int)(item >> 31); // bit 31: commit-time re-run
-        c.thresh = slot == 0 ? (i / phase) * phase : i;
-        const unsigned long long t_begin = global_ns();
-        process_seed(c, seed_vid[i], seed_ch[i]);
-        longest = max(longest, global_ns() - t_begin);
+        int slot = force_slot >= 0 ? force_slot : (int)(item >> 31); // bit 31: commit-time re-run queued by the validation
+        // at most two evaluations: the speculative one and, when its result runs into edges that earlier seeds of its
+        // phase claimed, the commit-time re-run right behind it (blocksfinder.h:375-412) -- one call site, same warp
+        while (true) {
+            c.thresh = slot == 0 ? (i / phase) * phase : i;
+            const unsigned long long t_begin = global_ns();
+            process_seed(c, seed_vid[i], seed_ch[i]);
+            longest = max(longest, global_ns() - t_begin);
+            if (c.err) break;
+            // publish bestInstance and the read-set
+            unsigned long long io = 0, ro = 0;
+            if (lane == 0) {
+                io = atomicAdd(&ctl->inst_used, (unsigned long long)c.nbest);
+                ro = atomicAdd(&ctl->rs_used, (unsigned long long)c.nrs);
+            }
+            io = __shfl_sync(kFull, io, 0);
+            ro = __shfl_sync(kFull, ro, 0);
+            if (io + c.nbest > win.inst_cap || ro + c.nrs > win.rs_cap) {
+                // the host abandons the active set and starts it again; until it notices, the kernels queued behind this
+                // one must see a harmless (empty) entry for this seed
+                if (lane == 0) {
+                    atomicExch(&ctl->pool_overflow, 1u);
+                    win.res_cnt[slot][j] = 0;
+                    win.rs_cnt[slot][j] = 0;
+                }
+                break;
+            }
+            for (int t = lane; t < c.nbest; t += 32) win.inst_pool[io + t] = c.best[t];
+            for (int t = lane; t < c.nrs; t += 32) win.rs_pool[ro + t] = c.ar.rs[t];
+            if (lane == 0) {
+                win.res_off[slot][j] = (unsigned)io;
+                win.res_cnt[slot][j] = (unsigned)c.nbest;
+                win.rs_off[slot][j] = (unsigned)ro;
+                win.rs_cnt[slot][j] = (unsigned)c.nrs;
+            }
+            if (slot != 0) {
+                done1++;
+                break;
+            }
+            done++;
+            bool conf = false; // commit-time conflict test of the fresh result: any of its edges claimed by a seed < i?
+            if (c.nbest > 1)
+                for (int t = 0; t < c.nbest && !conf; t++) {
+                    int lo, hi;
+                    inst_edges(c.best[t], lo, hi);
+                    for (int base = lo; base <= hi && !conf; base += 32) {
+                        const int f = base + lane;
+                        conf = __any_sync(kFull, f <= hi && __ldg(E + f) < i);
+                    }
+                }
+            if (lane == 0) {
+                win.conf[j] = conf;
+                win.has1[j] = conf;
+            }
+            if (!conf) break;
+            slot = 1;
+        }
         if (c.err) {
             if (lane == 0) atomicCAS(&ctl->err, 0u, (unsigned)c.err);
             break;
         }
-        // publish bestInstance and the read-set
-        unsigned long long io = 0, ro = 0;
-        if (lane == 0) {
-            io = atomicAdd(&ctl->inst_used, (unsigned long long)c.nbest);
-            ro = atomicAdd(&ctl->rs_used, (unsigned long long)c.nrs);
-        }
-        io = __shfl_sync(kFull, io, 0);
-        ro = __shfl_sync(kFull, ro, 0);
-        if (io + c.nbest > win.inst_cap || ro + c.nrs > win.rs_cap) {
-            // the host halves the window and starts it again; until it notices, the kernels queued behind this one
-            // must see a harmless (empty) entry for this seed
-            if (lane == 0) {
-                atomicExch(&ctl->pool_overflow, 1u);
-                win.res_cnt[slot][j] = 0;
-                win.rs_cnt[slot][j] = 0;
-            }
-            continue;
-        }
-        for (int t = lane; t < c.nbest; t += 32) win.inst_pool[io + t] = c.best[t];
-        for (int t = lane; t < c.nrs; t += 32) win.rs_pool[ro + t] = c.ar.rs[t];
-        if (lane == 0) {
-            win.res_off[slot][j] = (unsigned)io;
-            win.res_cnt[slot][j] = (unsigned)c.nbest;
-            win.rs_off[slot][j] = (unsigned)ro;
-            win.rs_cnt[slot][j] = (unsigned)c.nrs;
-        }
-        if (slot == 0) done++;
-        else done1++;
     }
     if (lane == 0) {
         if (longest) atomicMax(&ctl->max_ns, (unsigned)min(longest, 0xFFFFFFFFull));
@@ -249,14 +281,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_traverse(Index ix, Params pr, c
     }
 }
 
-// edges of one instance as an epoch index range: Finalize's MarkUsed loop (blocksfinder.h:327-330)
-__device__ __forceinline__ void inst_edges(const int4 &b, int &lo, int &hi)
-{
-    int fg = b.x & 0x7FFFFFFF, bg = b.y;
-    lo = min(fg, bg);
-    hi = max(fg, bg) - 1;
-}
-
 // does any edge of result `slot 0` of seed j carry an epoch < limit?   (warp-wide)
 __device__ __forceinline__ bool result_conflicts(const Window &win, unsigned j, const uint32_t *E, uint32_t limit,
                                                  int lane)
@@ -272,28 +296,6 @@ __device__ __forceinline__ bool result_conflicts(const Window &win, unsigned j, 
         }
     }
     return hit;
-}
-
-// commit-time conflict test for freshly evaluated seeds (blocksfinder.h:375-398); queues re-runs
-__global__ void k_conflict(const uint32_t *__restrict__ E, const unsigned *__restrict__ list,
-                           const unsigned *__restrict__ n_ptr, Window win, Control *ctl)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned n = *n_ptr;
-    for (unsigned idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < n; idx += gridDim.x * (blockDim.x >> 5)) {
-        if (list[idx] >> 31) continue; // a commit-time re-run queued by the last validation: nothing to test
-        const unsigned i = list[idx], j = i & win.mask;
-        bool conf = false;
-        if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, E, i, lane);
-        if (lane == 0) {
-            win.conf[j] = conf;
-            if (conf && !win.has1[j]) {
-                win.has1[j] = 1;
-                win.list1[atomicAdd(&ctl->n1, 1u)] = i;
-            }
-            if (!conf) win.has1[j] = 0;
-        }
-    }
 }
 
 __device__ __forceinline__ void final_result(const Window &win, unsigned j, unsigned &off, unsigned &cnt)
@@ -726,7 +728,7 @@ struct lcb_ctx {
     bool arena_dirty = false;
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
     bool step_timed = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace {
@@ -847,7 +849,7 @@ extern "C" void lcb_default_params(lcb_params *p)
     p->looking_depth = 8;
     p->phase_size = 256;
     p->window_init = 16384;
-    p->window_max = 262144;
+    p->window_max = 1 << 20;
     p->device = 0;
     p->collect_counters = 0;
 }
@@ -905,8 +907,6 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     if (ctx->h_ctl) cached_free(ctx->h_ctl, sizeof(Control), -1);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
-    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -921,7 +921,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if (p.phase_size <= 0) p.phase_size = 256;
     if (p.looking_depth <= 0) p.looking_depth = 8;
     if (p.window_init <= 0) p.window_init = 16384;
-    if (p.window_max <= 0) p.window_max = 262144;
+    if (p.window_max <= 0) p.window_max = 1 << 20;
     p.window_max = std::min(p.window_max, 1 << 20);
     p.window_max = std::max(p.phase_size, p.window_max / p.phase_size * p.phase_size);
     p.window_init = std::max(p.phase_size, std::min(p.window_init, p.window_max) / p.phase_size * p.phase_size);
@@ -952,8 +952,6 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(cudaEventCreate(&ctx->ev_step0));
     CUDA_TRY(cudaEventCreate(&ctx->ev_step1));
-    CUDA_TRY(cudaEventCreate(&ctx->ev2));
-    CUDA_TRY(cudaEventCreate(&ctx->ev3));
     const int64_t N = v->n_records, V = v->n_vertices;
     const int C = v->n_chr;
     auto t0 = std::chrono::steady_clock::now();
@@ -1043,7 +1041,6 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     if ((rc = dev_alloc(ctx, &ctx->win.blk, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.out_off, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.list0, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->win.list1, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_wnext, 8))) return rc;
     ctx->win.inst_cap = kInstPoolCap;
@@ -1327,6 +1324,9 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     float trav_ms = 0;
     ctx->st.windows = ctx->st.rounds = ctx->st.pool_restarts = 0;
     const bool trace_rounds = getenv("LCB_TRACE_ROUNDS") != nullptr;
+    // admission thresholds (developer knobs): round time relative to its longest single evaluation
+    const double grow_below = getenv("LCB_GROW_BELOW") ? atof(getenv("LCB_GROW_BELOW")) : 1.2;
+    const double shrink_above = getenv("LCB_SHRINK_ABOVE") ? atof(getenv("LCB_SHRINK_ABOVE")) : 2.0;
     const unsigned R = (unsigned)ctx->n_ranks, me = (unsigned)ctx->rank;
     // rolling active set [c0, c1): c0 = commit frontier, c1 = admission frontier
     unsigned c0 = 0, c1 = 0;
@@ -1350,17 +1350,11 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             c1 += admit;
         }
         ctx->st.rounds++;
-        // A. speculative evaluations (new + invalidated seeds), plus the commit-time re-runs the last validation
-        //    queued (tagged items)
+        // A. speculative evaluations (new + invalidated seeds), each followed at once by its commit-time re-run when the
+        //    fresh result conflicts; plus the commit-time re-runs the last validation queued (tagged items)
         CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
         if ((rc = launch_traverse(ctx, Ecur, -1, ctx->win.list0, &ctx->d_ctl->n0, true))) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-        // B. commit-time conflicts of the freshly evaluated seeds
-        k_conflict<<<vgrid, 256, 0, ctx->stream>>>(Ecur, ctx->win.list0, &ctx->d_ctl->n0, ctx->win, ctx->d_ctl);
-        // C. commit-time re-runs of the conflicts found in B
-        CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
-        if ((rc = launch_traverse(ctx, Ecur, 1, ctx->win.list1, &ctx->d_ctl->n1, false))) return rc;
-        CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
         // D. new epochs: committed claims + the active seeds' current final results
         k_rebase<<<egrid, 256, 0, ctx->stream>>>(Enew, Ecur, N, c0);
         k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, c0, c1, ctx->win);
@@ -1372,12 +1366,11 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream));        // n0, n1, dirty
         CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->first_dirty, 0xFF, sizeof(unsigned), ctx->stream));
         k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, c0, c1, phase, ctx->win, ctx->d_ctl);
-        ctx->st.kernel_launches += 4;
+        ctx->st.kernel_launches += 3;
         if ((rc = fetch_control(ctx))) return rc;
-        float ms = 0, ms1 = 0;
+        float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        cudaEventElapsedTime(&ms1, ctx->ev2, ctx->ev3);
-        trav_ms += ms + ms1;
+        trav_ms += ms;
         Control &h = *ctx->h_ctl;
         if (h.inst_used * 2 > ctx->win.inst_cap || h.rs_used * 2 > ctx->win.rs_cap) drain = true;
         // Admission rate: a launch lasts max(longest evaluation, work / resident warps).  While it is latency-bound
@@ -1385,8 +1378,8 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         unsigned next_delta = delta;
         {
             const double longest_ms = h.max_ns * 1e-6;
-            if (ms < 1.5 * longest_ms || ms < 0.25) next_delta = (unsigned)std::min<unsigned long long>((unsigned long long)ctx->prm.window_max, 2ull * delta);
-            else if (ms > 3.0 * longest_ms) next_delta = std::max(phase, delta / 2 / phase * phase);
+            if (ms < grow_below * longest_ms || ms < 0.25) next_delta = (unsigned)std::min<unsigned long long>((unsigned long long)ctx->prm.window_max, 2ull * delta);
+            else if (ms > shrink_above * longest_ms) next_delta = std::max(phase, delta / 2 / phase * phase);
         }
         unsigned first_dirty = h.first_dirty;
 #ifdef LCB_WITH_NCCL
@@ -1404,8 +1397,8 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         }
 #endif
         if (trace_rounds)
-            fprintf(stderr, "[round] %llu active [%u,%u) admitted %u speculative=%.3f ms rerun=%.3f ms longest=%.3f ms next: n0=%u dirty=%u first=%u delta=%u pools %.1f%% %.1f%%\n",
-                    (unsigned long long)ctx->st.rounds, c0, c1, admit, ms, ms1, h.max_ns * 1e-6, h.n0, h.dirty, first_dirty, next_delta,
+            fprintf(stderr, "[round] %llu active [%u,%u) admitted %u traverse=%.3f ms longest=%.3f ms next: n0=%u dirty=%u first=%u delta=%u pools %.1f%% %.1f%%\n",
+                    (unsigned long long)ctx->st.rounds, c0, c1, admit, ms, h.max_ns * 1e-6, h.n0, h.dirty, first_dirty, next_delta,
                     100.0 * h.inst_used / ctx->win.inst_cap, 100.0 * h.rs_used / ctx->win.rs_cap);
         if (h.err) {
             ctx->arena_dirty = true;

@@ -88,7 +88,7 @@ struct WarpArena { // per-warp HBM scratch (spill + variable-length logs)
     unsigned short *good; // kInstMax
     int2 *hash;           // kHashMax
     int *hslot;           // kPathMax: slots occupied in the HBM hash (for O(path) clearing)
-    int4 *redge;          // kPathMax: successful right edges {end vertex, length, source g, source strand}
+    int4 *redge;          // kPathMax: successful right edges {end vertex, length, source g | strand << 31, path distance}
     int2 *vote;           // kVoteMax
     unsigned *vlast;      // kVoteMax
     int2 *rs;             // kReadSetMax: read-set intervals [lo, hi] over epoch indices
@@ -124,7 +124,7 @@ struct Ctx { // warp-uniform traversal state (registers)
     bool collect; // count walk/occurrence/scan/score steps (diagnostics; off on the timed path)
     bool vote_clean; // the shared-memory vote table is all-empty (mpv_mid leaves it so, the general path does not)
     // shadow state (WarpSmem::s_*)
-    bool snap_valid;
+    bool snap_valid, snap_hash;
     int snap_ninst, snap_ngood, snap_hcount, snap_right_flank, snap_right_vertex, snap_nright;
     Counters ct;
 };
@@ -368,7 +368,7 @@ __device__ __forceinline__ void path_clear(Ctx &c)
 // which recomputes exactly this state.
 __device__ __forceinline__ void snapshot_state(Ctx &c)
 {
-    if (c.icap != kInstSmem || c.hbig) {
+    if (c.icap != kInstSmem) {
         c.snap_valid = false;
         return;
     }
@@ -377,7 +377,10 @@ __device__ __forceinline__ void snapshot_state(Ctx &c)
     int *dst = (int *)sm->s_inst;
     const int words = c.ninst * (int)(sizeof(Inst) / sizeof(int));
     for (int i = c.lane; i < words; i += 32) dst[i] = src[i];
-    for (int i = c.lane; i < kHashSmem; i += 32) sm->s_hash[i] = sm->hash[i];
+    // a path hash that outgrew shared memory is not copied: restore_state rebuilds it from the right-edge log
+    c.snap_hash = !c.hbig;
+    if (c.snap_hash)
+        for (int i = c.lane; i < kHashSmem; i += 32) sm->s_hash[i] = sm->hash[i];
     if (c.lane < c.ninst) sm->s_ord[c.lane] = sm->ord[c.lane];
     if (c.lane < c.ngood) sm->s_good[c.lane] = sm->good[c.lane];
     c.snap_ninst = c.ninst, c.snap_ngood = c.ngood, c.snap_hcount = c.hcount;
@@ -394,12 +397,21 @@ __device__ __forceinline__ void restore_state(Ctx &c)
     int *dst = (int *)sm->inst;
     const int words = c.snap_ninst * (int)(sizeof(Inst) / sizeof(int));
     for (int i = c.lane; i < words; i += 32) dst[i] = src[i];
-    for (int i = c.lane; i < kHashSmem; i += 32) sm->hash[i] = sm->s_hash[i];
     if (c.lane < c.snap_ninst) sm->ord[c.lane] = sm->s_ord[c.lane];
     if (c.lane < c.snap_ngood) sm->good[c.lane] = sm->s_good[c.lane];
-    c.ninst = c.snap_ninst, c.ngood = c.snap_ngood, c.hcount = c.snap_hcount;
+    c.ninst = c.snap_ninst, c.ngood = c.snap_ngood;
     c.right_flank = c.snap_right_flank, c.right_vertex = c.snap_right_vertex, c.nright = c.snap_nright;
     c.left_flank = 0, c.left_vertex = c.origin, c.nleft = 0;
+    if (c.snap_hash) {
+        for (int i = c.lane; i < kHashSmem; i += 32) sm->hash[i] = sm->s_hash[i];
+        c.hcount = c.snap_hcount;
+    } else { // same insertion order as Init + the pushes it replaces: origin, then every successful right edge
+        hash_insert(c, c.origin, 0);
+        for (int i = 0; i < c.snap_nright && !c.err; i++) {
+            const int4 e = c.ar.redge[i];
+            hash_insert(c, e.x, e.w);
+        }
+    }
     __syncwarp();
 }
 
@@ -490,28 +502,41 @@ __device__ __forceinline__ bool push_parallel(Ctx &c, const bool BACK, int v, in
     Occ q;
     q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = -1 - c.lane, q.chi = 0, q.v_id = 0;
     if (live) q = load_occurrence(c, o0 + (unsigned)c.lane, v);
-    {
-        const unsigned peers = __match_any_sync(kFull, q.clo);
-        if (__any_sync(kFull, live && (peers & (peers - 1)) != 0)) return false;
+    { // an occurrence list is sorted by (chr, idx): two occurrences on one chromosome are neighbours in it
+        const int prev_clo = __shfl_up_sync(kFull, q.clo, 1);
+        if (__any_sync(kFull, live && c.lane > 0 && prev_clo == q.clo)) return false;
     }
-    int outcome = 0, cand = -1, scan_lo = 0, scan_hi = -1; // 0 skip, 1 extend, 2 new instance, 3 found used
-    if (live) {
-        const int n = c.ninst;
-        int ub = n;
+    // multiset neighbours of every occurrence: lane p holds the p-th instance (id, key) of the multiset order, every lane
+    // finds its upper_bound by shuffles instead of chasing ord[] -> inst[].key through shared memory
+    const int n = c.ninst;
+    int ub = n, hi_cand = -1, lo_cand = -1, hi_key = 0, lo_key = 0;
+    if (n <= 32) {
+        int ordreg = 0, keyreg = 0x7FFFFFFF;
+        if (c.lane < n) {
+            ordreg = c.ord[c.lane];
+            keyreg = c.inst[ordreg].key;
+        }
+        for (int p = n - 1; p >= 0; p--) {
+            const int kp = __shfl_sync(kFull, keyreg, p);
+            if (kp > q.g) ub = p;
+        }
+        const int hs = min(ub, 31), ls = max(ub - 1, 0);
+        hi_cand = __shfl_sync(kFull, ordreg, hs), hi_key = __shfl_sync(kFull, keyreg, hs);
+        lo_cand = __shfl_sync(kFull, ordreg, ls), lo_key = __shfl_sync(kFull, keyreg, ls);
+    } else if (live) {
         for (int p = 0; p < n; p++)
             if (c.inst[c.ord[p]].key > q.g) {
                 ub = p;
                 break;
             }
+        if (ub < n) hi_cand = c.ord[ub], hi_key = c.inst[hi_cand].key;
+        if (ub > 0) lo_cand = c.ord[ub - 1], lo_key = c.inst[lo_cand].key;
+    }
+    int outcome = 0, cand = -1, scan_lo = 0, scan_hi = -1; // 0 skip, 1 extend, 2 new instance, 3 found used
+    if (live) {
         int hi_id = -1, lo_id = -1;
-        if (ub < n) {
-            int id = c.ord[ub];
-            if (c.inst[id].key < q.chi) hi_id = id;
-        }
-        if (ub > 0) {
-            int id = c.ord[ub - 1];
-            if (c.inst[id].key >= q.clo) lo_id = id;
-        }
+        if (ub < n && hi_key < q.chi) hi_id = hi_cand;
+        if (ub > 0 && lo_key >= q.clo) lo_id = lo_cand;
         bool within = false;
         if (hi_id >= 0) {
             int a = c.inst[hi_id].fg, b = c.inst[hi_id].bg;
@@ -732,7 +757,7 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
             c.err = LCB_ERR_CAPACITY;
             return true;
         }
-        if (c.lane == 0) c.ar.redge[c.nright] = make_int4(v, len, e_ch_g, (int)e_ch_pos);
+        if (c.lane == 0) c.ar.redge[c.nright] = make_int4(v, len, e_ch_g | (e_ch_pos ? (int)0x80000000 : 0), dist);
         c.nright++;
         c.right_flank = dist;
         c.right_vertex = v;
@@ -1373,7 +1398,7 @@ __device__ __forceinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
                 path_init(c, vid, ch);
                 for (int i = 0; i < replay && !c.err; i++) {
                     int4 e = c.ar.redge[i];
-                    path_push(c, true, e.x, e.y, e.z, e.w != 0, 0, -1, -1);
+                    path_push(c, true, e.x, e.y, e.z & 0x7FFFFFFF, e.z < 0, 0, -1, -1);
                 }
                 if (c.err) return;
             }
