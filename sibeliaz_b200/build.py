@@ -61,14 +61,15 @@ def _run(cmd):
     return r.stdout
 
 
-def build_selfcheck(verbose=False):
+def build_selfcheck(verbose=False, defines=("-DLCB_CHECK_MPV",), name="libsibeliaz_lcb_check.so"):
     """Developer build: every shortcut path of the traversal also runs the general path and compares (-DLCB_CHECK_MPV);
-    a mismatch makes lcb_find_blocks fail with code 90.  Load it with LCB_LIB_PATH=<returned path>."""
+    a mismatch makes lcb_find_blocks fail with code 90.  Load it with LCB_LIB_PATH=<returned path>.
+    Also used for other experimental -D variants (`--variant name -DX=Y ...`)."""
     os.makedirs(LIBDIR, exist_ok=True)
     inc = os.path.join(ROOT, "include")
     srcs = [os.path.join(CSRC, f) for f in ("lcb_device.cu", "lcb_host.cpp")]
-    out = os.path.join(LIBDIR, "libsibeliaz_lcb_check.so")
-    cmd = [_nvcc()] + ARCH + NVCC_FLAGS + ["-DLCB_CHECK_MPV", "-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", out] + srcs
+    out = os.path.join(LIBDIR, name)
+    cmd = [_nvcc()] + ARCH + NVCC_FLAGS + list(defines) + ["-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", out] + srcs
     nccl = _nccl()
     if nccl:
         cmd += ["-DLCB_WITH_NCCL", "-I", nccl[0], '-DLCB_NCCL_PATH="%s"' % nccl[1], "-ldl"]
@@ -104,7 +105,10 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    if "--selfcheck" in sys.argv:
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_selfcheck(verbose=True, defines=sys.argv[i + 2:], name="libsibeliaz_lcb_%s.so" % sys.argv[i + 1]))
+    elif "--selfcheck" in sys.argv:
         print(build_selfcheck(verbose=True))
     else:
         print(build(force="--force" in sys.argv, verbose=True))

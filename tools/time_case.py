@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--dir", default="/tmp/lcb_time")
+    ap.add_argument("--dbg", default=None, help="junction file made earlier by the reference twopaco for exactly this synthetic")
     a = ap.parse_args()
     import numpy as np
     import sibeliaz_b200 as sb
@@ -36,6 +37,8 @@ def main():
     dbg = os.path.join(d, "g.dbg")
     t = time.time()
     fas = generate(d, a.kind, a.genomes, a.length, a.rate, a.seed)
+    if a.dbg:
+        dbg = a.dbg
     if not os.path.exists(dbg):
         run_twopaco(fas, a.k, dbg, threads=min(16, os.cpu_count() or 1))
     print("input ready in %.1fs" % (time.time() - t), flush=True)
