@@ -54,10 +54,18 @@ typedef struct lcb_index_view {
     const uint8_t *prev_rc;   /* [N] complement(seq[pos-1]), 'N' at pos 0 (:642)                 */
     const int64_t *vtx_off;   /* [V+1] CSR over the occurrence lists vertex_[|id|] (:695)        */
     const int64_t *occ_g;     /* [N] occurrences of each vertex as g, sorted by (chr, idx) (:646)*/
+    /* Optional (may be NULL): the same index already in the device record layout, e.g. built by
+     * lcb_index_pack while the CUDA context is still being created; lcb_create then uploads these as they are.
+     *   packed_rec[g] = int32x4 {id, bp, first occurrence slot of |id|, (#occurrences << 16) | (next_ch << 8) | prev_rc}
+     *   packed_occ[o] = int32x2 {g | (stored id < 0 ? 1 << 31 : 0), bp}   in occ_g order */
+    const void *packed_rec;   /* [N] 16-byte records                                             */
+    const void *packed_occ;   /* [N] 8-byte records                                              */
 } lcb_index_view;
 
 int lcb_index_load(const char *graph_file, const char *const *fasta_files, int n_fasta, int k, int abundance,
                    lcb_index **out, char *err, size_t errlen);
+/* Builds the device record layout on the host threads (optional; lcb_create packs by itself otherwise). */
+int lcb_index_pack(lcb_index *);
 int lcb_index_get_view(const lcb_index *, lcb_index_view *view);
 int32_t lcb_index_num_chr(const lcb_index *);
 const char *lcb_index_chr_name(const lcb_index *, int32_t chr);

@@ -40,7 +40,7 @@ class IndexView(C.Structure):
     _fields_ = [("n_chr", C.c_int32), ("n_records", C.c_int64), ("n_vertices", C.c_int64),
                 ("chr_off", C.POINTER(C.c_int64)), ("pos_id", C.POINTER(C.c_int32)), ("pos_bp", C.POINTER(C.c_uint32)),
                 ("next_ch", C.POINTER(C.c_uint8)), ("prev_rc", C.POINTER(C.c_uint8)), ("vtx_off", C.POINTER(C.c_int64)),
-                ("occ_g", C.POINTER(C.c_int64))]
+                ("occ_g", C.POINTER(C.c_int64)), ("packed_rec", C.c_void_p), ("packed_occ", C.c_void_p)]
 
 
 class Params(C.Structure):

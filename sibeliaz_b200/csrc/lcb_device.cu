@@ -884,6 +884,34 @@ extern "C" int lcb_warmup(int device)
     cudaDeviceSynchronize();
     lap("pools + memset");
     {
+        // CUDA loads kernels lazily, on first use: touch all of them here, off the critical path
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_traverse<false>);
+        cudaFuncGetAttributes(&fa, k_rebase);
+        cudaFuncGetAttributes(&fa, k_claim);
+        cudaFuncGetAttributes(&fa, k_validate);
+        cudaFuncGetAttributes(&fa, k_admit);
+        cudaFuncGetAttributes(&fa, k_final_counts);
+        cudaFuncGetAttributes(&fa, k_emit_scan);
+        cudaFuncGetAttributes(&fa, k_emit_write);
+        cudaFuncGetAttributes(&fa, k_seed_enum<false>);
+        cudaFuncGetAttributes(&fa, k_seed_enum<true>);
+        cudaFuncGetAttributes(&fa, k_scan_tiles);
+        cudaFuncGetAttributes(&fa, k_scan_sums);
+        cudaFuncGetAttributes(&fa, k_scan_add);
+        cudaFuncGetAttributes(&fa, k_radix_hist<unsigned>);
+        cudaFuncGetAttributes(&fa, k_radix_hist<unsigned long long>);
+        cudaFuncGetAttributes(&fa, k_radix_scatter<unsigned>);
+        cudaFuncGetAttributes(&fa, k_radix_scatter<unsigned long long>);
+        cudaFuncGetAttributes(&fa, k_is_uniform_digit);
+        cudaFuncGetAttributes(&fa, k_iota);
+        cudaFuncGetAttributes(&fa, k_gather<int>);
+        cudaFuncGetAttributes(&fa, k_gather<unsigned>);
+        cudaFuncGetAttributes(&fa, k_gather<unsigned char>);
+        cudaFuncGetAttributes(&fa, k_gather<unsigned long long>);
+        lap("kernel preload");
+    }
+    {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         size_t ab = (arena_bytes + 511) & ~(size_t)511;
         g_cache.push_back(CachedBlock{arena, ab, device, true});
@@ -970,7 +998,28 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     lap("stream + events");
     auto t0 = std::chrono::steady_clock::now();
     // ---- pack + upload the index (8 B + 2 B per record, u32 CSR) ----
-    {
+    if (v->packed_rec && v->packed_occ) {
+        // the host already holds the device layout (lcb_index_pack): straight copies, no pinned staging to allocate
+        const size_t b_rec = sizeof(int4) * (size_t)N, b_occ = sizeof(int2) * (size_t)N;
+        std::vector<uint32_t> vo((size_t)V + 2), co((size_t)C + 1);
+        for (int64_t i = 0; i <= V; i++) vo[(size_t)i] = (uint32_t)v->vtx_off[i];
+        vo[(size_t)V + 1] = vo[(size_t)V];
+        for (int i = 0; i <= C; i++) co[(size_t)i] = (uint32_t)v->chr_off[i];
+        int rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_rec, (size_t)N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_occ, (size_t)N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
+        for (int e = 0; e < 2; e++)
+            if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
+        lap("index alloc");
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, v->packed_rec, b_rec, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, v->packed_occ, b_occ, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_vtx_off, vo.data(), vo.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_chr_off, co.data(), co.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->st.h2d_bytes = (uint64_t)(b_rec + b_occ + (vo.size() + co.size()) * sizeof(uint32_t));
+    } else {
         // packed into ONE pinned staging buffer so the copies are true async DMA from page-locked memory
         const size_t b_rec = sizeof(int4) * (size_t)N, b_occ = sizeof(int2) * (size_t)N, b_vo = sizeof(uint32_t) * ((size_t)V + 2),
                      b_co = sizeof(uint32_t) * ((size_t)C + 1);
@@ -1065,15 +1114,18 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
         unsigned long long v = strtoull(e, nullptr, 10);
         if (v >= 1024) ctx->win.inst_cap = std::min(ctx->win.inst_cap, v), ctx->win.rs_cap = std::min(ctx->win.rs_cap, v);
     }
+    lap("ring arrays");
     if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.rs_pool, (size_t)ctx->win.rs_cap))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_ctl, 1))) return rc;
     CUDA_TRY(cached_alloc((void **)&ctx->h_ctl, sizeof(Control), -1, nullptr));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
+    lap("pools + control");
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
     ctx->grid_traverse = per_sm * ctx->sms;
+    lap("occupancy query");
     ctx->arena_stride = arena_stride_bytes();
     size_t arena_bytes = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock;
     bool arena_cached = false;

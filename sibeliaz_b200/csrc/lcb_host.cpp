@@ -109,6 +109,7 @@ struct lcb_index {
     std::vector<int32_t> pos_id;
     std::vector<uint32_t> pos_bp;
     std::vector<uint8_t> next_ch, prev_rc;
+    std::vector<int32_t> packed_rec, packed_occ; // 4 / 2 words per record (lcb_index_pack)
     FastaRecords fasta;
     std::string error;
 };
@@ -404,9 +405,44 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
     return LCB_OK;
 }
 
+extern "C" int lcb_index_pack(lcb_index *ix)
+{
+    if (!ix) return LCB_ERR_ARG;
+    const size_t N = (size_t)ix->N;
+    if (ix->packed_rec.size() == 4 * N && ix->packed_occ.size() == 2 * N) return LCB_OK;
+    ix->packed_rec.resize(4 * N);
+    ix->packed_occ.resize(2 * N);
+    const unsigned T = WorkerCount();
+    std::vector<int> too_many(T, 0);
+    Parallel(T, [&](unsigned t, unsigned TT) {
+        for (size_t g = N * t / TT; g < N * (t + 1) / TT; g++) {
+            const int32_t id = ix->pos_id[g];
+            const size_t a = (size_t)(id < 0 ? -(int64_t)id : (int64_t)id);
+            const int64_t o0 = ix->vtx_off[a], cnt = ix->vtx_off[a + 1] - o0;
+            if (cnt > 65535) too_many[t] = 1;
+            int32_t *r = &ix->packed_rec[4 * g];
+            r[0] = id, r[1] = (int32_t)ix->pos_bp[g], r[2] = (int32_t)o0;
+            r[3] = (int32_t)(((uint32_t)cnt << 16) | ((uint32_t)ix->next_ch[g] << 8) | (uint32_t)ix->prev_rc[g]);
+            const size_t og = (size_t)ix->occ_g[g]; // occurrence slot g of the CSR (not record g)
+            int32_t *o = &ix->packed_occ[2 * g];
+            o[0] = (int32_t)((uint32_t)og | (ix->pos_id[og] < 0 ? 0x80000000u : 0u)), o[1] = (int32_t)ix->pos_bp[og];
+        }
+    });
+    for (unsigned t = 0; t < T; t++)
+        if (too_many[t]) {
+            ix->packed_rec.clear();
+            ix->packed_occ.clear();
+            return LCB_ERR_ARG; // lcb_create reports the reason (abundance above 65535)
+        }
+    return LCB_OK;
+}
+
 extern "C" int lcb_index_get_view(const lcb_index *ix, lcb_index_view *v)
 {
     if (!ix || !v) return LCB_ERR_ARG;
+    const bool packed = ix->N > 0 && ix->packed_rec.size() == 4 * (size_t)ix->N && ix->packed_occ.size() == 2 * (size_t)ix->N;
+    v->packed_rec = packed ? ix->packed_rec.data() : nullptr;
+    v->packed_occ = packed ? ix->packed_occ.data() : nullptr;
     v->n_chr = ix->C;
     v->n_records = ix->N;
     v->n_vertices = ix->V;
