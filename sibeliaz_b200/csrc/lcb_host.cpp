@@ -560,7 +560,24 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
             return a.abs_id() < b.abs_id();
         };
         lap("copy + count");
-        std::sort(inst.begin(), inst.end(), by_multiplicity);
+        {
+            // std::sort's permutation is a function of the comparison outcomes only, so sorting 16-byte (key, index)
+            // pairs whose integer order IS by_multiplicity yields the reference's order without chasing copies[] in
+            // every comparison and without moving 24-byte records
+            struct Keyed {
+                uint64_t key;
+                uint32_t idx;
+            };
+            std::vector<Keyed> keyed(n);
+            for (uint64_t i = 0; i < n; i++) {
+                const uint32_t a = (uint32_t)inst[i].abs_id();
+                keyed[i] = Keyed{((uint64_t)(0xFFFFFFFFu - (uint32_t)copies[a]) << 32) | a, (uint32_t)i};
+            }
+            std::sort(keyed.begin(), keyed.end(), [](const Keyed &a, const Keyed &b) { return a.key < b.key; });
+            std::vector<OutBlock> sorted(n);
+            for (uint64_t i = 0; i < n; i++) sorted[i] = inst[keyed[i].idx];
+            inst.swap(sorted);
+        }
         lap("sort by multiplicity");
         // trimming against per-base coverage bitmaps, blocksfinder.h:607-656
         std::vector<Bitmap> covered((size_t)C);
@@ -572,6 +589,12 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
             while (hi < inst.size() && !by_multiplicity(inst[lo], inst[hi])) ++hi;
             group.clear();
             for (size_t i = lo; i < hi; i++) {
+                if (i + 12 < inst.size()) { // the bitmaps are far larger than the caches: fetch the words of a later record now
+                    const OutBlock &f = inst[i + 12];
+                    const Bitmap &fc = covered[f.chr];
+                    __builtin_prefetch(&fc.w[f.start >> 6], 1);
+                    __builtin_prefetch(&fc.w[f.end >> 6], 1);
+                }
                 Bitmap &cov = covered[inst[i].chr];
                 uint64_t s = inst[i].start, e = inst[i].end;
                 while (cov.test(s) && s < e) ++s;
@@ -638,12 +661,29 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
                     p.put('\n');
                 }
             });
-            size_t total_len = t.s.size();
-            for (auto &p : part) total_len += p.s.size();
-            t.s.reserve(total_len);
-            for (auto &p : part) t.s.append(p.s);
             lap("sort rows + format");
-            WriteFile(std::string(out_dir) + "/blocks_coords.gff", t.s);
+            // the parts go to their offsets of the file from their own threads (no concatenated copy)
+            std::vector<size_t> off(T + 1, t.s.size());
+            for (unsigned i = 0; i < T; i++) off[i + 1] = off[i] + part[i].s.size();
+            const std::string path = std::string(out_dir) + "/blocks_coords.gff";
+            const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (fd < 0) throw Failure(LCB_ERR_IO, "Cannot open file " + path);
+            auto put_at = [fd](const std::string &data, size_t at) {
+                size_t done = 0;
+                while (done < data.size()) {
+                    ssize_t w = ::pwrite(fd, data.data() + done, data.size() - done, (off_t)(at + done));
+                    if (w < 0 && errno == EINTR) continue;
+                    if (w <= 0) return false;
+                    done += (size_t)w;
+                }
+                return true;
+            };
+            std::vector<int> ok(T, 1);
+            bool head_ok = put_at(t.s, 0);
+            Parallel(T, [&](unsigned tt, unsigned) { ok[tt] = put_at(part[tt].s, off[tt]) ? 1 : 0; });
+            bool all_ok = head_ok && ::close(fd) == 0;
+            for (unsigned i = 0; i < T; i++) all_ok = all_ok && ok[i];
+            if (!all_ok) throw Failure(LCB_ERR_IO, "Cannot write file " + path);
             lap("write gff");
         }
         if (gen_seq) {
