@@ -1,7 +1,7 @@
 """World-size-2 (gloo, CPU) test of the multi-rank protocol of DESIGN.md section 7, the one lcb_device.cu runs over
-NCCL: seeds of a window dealt round-robin over ranks, every rank evaluates / validates only its own seeds against a
-replicated epoch array, claims meet in an all-reduce(MIN), dirty counters in an all-reduce(SUM), block ids are a prefix
-sum over all-reduced per-seed counts.  Seed evaluation itself is the oracle's epoch-threshold Process
+NCCL: the seeds of the rolling active set dealt round-robin over ranks, every rank evaluates / validates only its own
+seeds against a replicated epoch array, claims meet in an all-reduce(MIN), the first dirty seed in an all-reduce(MAX) of
+its complement, the clean prefix is committed with block ids from a prefix sum over all-reduced per-seed counts.  Seed evaluation itself is the oracle's epoch-threshold Process
 (oracle/liblcb_oracle_epoch.so), so the test checks the PROTOCOL -- sharding, reductions, termination, ordered emit --
 independently of CUDA.  The result must equal the sequential oracle's blocksInstance_ list."""
 import ctypes as C
@@ -63,75 +63,86 @@ def _worker(rank, world, port, graph, fastas, k, W, out_queue):
                 return True
         return False
 
-    Ebase = np.full(N, INF, np.uint32)
+    # rolling active set [c0, c1) as in lcb_find_blocks: admit `W` seeds per round (at most 4 W active), evaluate own
+    # dirty + new seeds (commit-time re-run right behind a conflicting speculative result), rebase + claim + all-reduce,
+    # validate own seeds, agree on the first dirty seed, commit the clean prefix
+    Ecur = np.full(N, INF, np.uint32)
     out, blocks_before, rounds_total = [], 0, 0
-    for w0 in range(0, S, W):
-        n = min(W, S - w0)
-        own = list(range(rank, n, world))
-        r0, R0, r1, R1, conf = {}, {}, {}, {}, {j: False for j in own}
-        need0, need1 = set(own), set()
-        Ecur = Ebase.copy()
-        while True:
-            rounds_total += 1
-            for j in sorted(need0):
-                i = w0 + j
-                r0[j], R0[j] = process(i, i // PHASE * PHASE, Ecur)
-                conf[j] = conflicts(r0[j], Ecur, i)
-                if conf[j] and j not in r1:
-                    need1.add(j)
-                if not conf[j]:
-                    r1.pop(j, None)
-            for j in sorted(need1):
-                r1[j], R1[j] = process(w0 + j, w0 + j, Ecur)
-            need0, need1 = set(), set()
-            fin = {j: (r1[j] if conf[j] else r0[j]) for j in own}
-            Enew = Ebase.astype(np.int64)
-            for j in own:
-                if len(fin[j]) > 1:
-                    for e in edges(fin[j]):
-                        Enew[e] = np.minimum(Enew[e], w0 + j)
-            t = torch.from_numpy(Enew)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # <- the exchange step (ncclAllReduce(min) on the device)
-            Enew = t.numpy().astype(np.uint32)
-            dirty = 0
-            for j in own:
-                i = w0 + j
-                if changed(R0[j], Ecur, Enew, i // PHASE * PHASE):
-                    need0.add(j)
-                    r1.pop(j, None)
-                    dirty += 1
-                    continue
-                c = conflicts(r0[j], Enew, i)
-                dirty += c != conf[j]
-                conf[j] = c
-                if c and (j not in r1 or changed(R1[j], Ecur, Enew, i)):
-                    need1.add(j)
-                    dirty += 1
-                if not c:
-                    r1.pop(j, None)
-            d = torch.tensor([dirty])
-            dist.all_reduce(d, op=dist.ReduceOp.SUM)
-            Ecur = Enew
-            if d.item() == 0:
-                break
-        Ebase = Ecur
-        counts = np.zeros(n, np.int64)
-        for j in own:
-            f = r1[j] if conf[j] else r0[j]
-            counts[j] = len(f) if len(f) > 1 else 0
-        t = torch.from_numpy(counts)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ids = blocks_before + np.cumsum(counts > 0)
-        for j in own:
-            f = r1[j] if conf[j] else r0[j]
+    c0 = c1 = 0
+    r0, R0, r1, R1, conf = {}, {}, {}, {}, {}
+    need0, need1 = set(), set()
+    while c0 < S:
+        admit = min(W, S - c1, max(0, 4 * W - (c1 - c0)))
+        for i in range(c1, c1 + admit):
+            if i % world == rank:
+                need0.add(i)
+                conf[i] = False
+        c1 += admit
+        rounds_total += 1
+        for i in sorted(need0):
+            r0[i], R0[i] = process(i, i // PHASE * PHASE, Ecur)
+            r1.pop(i, None)
+            conf[i] = conflicts(r0[i], Ecur, i)
+            if conf[i]:
+                r1[i], R1[i] = process(i, i, Ecur)
+        for i in sorted(need1):
+            r1[i], R1[i] = process(i, i, Ecur)
+        need0, need1 = set(), set()
+        own = [i for i in range(c0, c1) if i % world == rank]
+        Enew = np.where(Ecur < c0, Ecur, INF).astype(np.int64)  # k_rebase: committed claims only
+        for i in own:
+            f = r1[i] if conf[i] else r0[i]
             if len(f) > 1:
-                for fgs, bg in f:
-                    pos, fg = bool(fgs >> 62), int(fgs & ((1 << 62) - 1))
-                    if pos:
-                        out.append((w0 + j, int(ids[j]), int(pos_bp[fg]), int(pos_bp[bg]) + k))
-                    else:
-                        out.append((w0 + j, -int(ids[j]), int(pos_bp[bg]), int(pos_bp[fg]) + k))
-        blocks_before = int(ids[-1]) if n else blocks_before
+                for e in edges(f):
+                    Enew[e] = np.minimum(Enew[e], i)
+        t = torch.from_numpy(Enew)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)  # <- the exchange step (ncclAllReduce(min) on the device)
+        Enew = t.numpy().astype(np.uint32)
+        first_dirty = INF
+        for i in own:
+            dirty = False
+            if changed(R0[i], Ecur, Enew, i // PHASE * PHASE):
+                need0.add(i)
+                dirty = True
+            else:
+                c = conflicts(r0[i], Enew, i)
+                dirty = c != conf[i]
+                conf[i] = c
+                if c and (i not in r1 or changed(R1[i], Ecur, Enew, i)):
+                    need1.add(i)
+                    dirty = True
+                if not c:
+                    r1.pop(i, None)
+            if dirty:
+                first_dirty = min(first_dirty, i)
+        d = torch.tensor([INF - first_dirty])
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)  # one max-reduction carries the round's decisions on the device
+        fd = min(INF - int(d.item()), c1)
+        if fd > c0:
+            counts = np.zeros(fd - c0, np.int64)
+            for i in own:
+                if i < fd:
+                    f = r1[i] if conf[i] else r0[i]
+                    counts[i - c0] = len(f) if len(f) > 1 else 0
+            t = torch.from_numpy(counts)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ids = blocks_before + np.cumsum(counts > 0)
+            for i in own:
+                if i >= fd:
+                    continue
+                f = r1[i] if conf[i] else r0[i]
+                if len(f) > 1:
+                    for fgs, bg in f:
+                        pos, fg = bool(fgs >> 62), int(fgs & ((1 << 62) - 1))
+                        if pos:
+                            out.append((i, int(ids[i - c0]), int(pos_bp[fg]), int(pos_bp[bg]) + k))
+                        else:
+                            out.append((i, -int(ids[i - c0]), int(pos_bp[bg]), int(pos_bp[fg]) + k))
+                for tab in (r0, R0, r1, R1, conf):
+                    tab.pop(i, None)
+            blocks_before = int(ids[-1])
+            c0 = fd
+        Ecur = Enew
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:
