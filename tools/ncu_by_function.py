@@ -65,7 +65,11 @@ def main():
     h = rows[hdr]
     body = rows[hdr + 1:]
     ci = {n: h.index(n) for n in ("# Samples", "Instructions Executed", "stall_long_sb", "stall_wait", "stall_short_sb", "stall_branch_resolving", "stall_selected", "stall_no_inst", "stall_not_selected", "stall_lg", "stall_mio", "stall_math", "stall_dispatch", "stall_barrier")}
-    if len(body) != len(instr):
+    body = [r for r in body if r and r[0].startswith("0x")]
+    if instr and len(body) % len(instr) == 0 and len(body) > len(instr):
+        print("%d launches in the report: aggregated" % (len(body) // len(instr)))
+        instr = instr * (len(body) // len(instr))
+    elif len(body) != len(instr):
         print("warning: %d SASS rows in the report vs %d instructions in this build (stale build?)" % (len(body), len(instr)))
     agg = collections.defaultdict(lambda: collections.Counter())
     lines = collections.Counter()
