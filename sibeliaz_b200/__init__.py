@@ -68,6 +68,16 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class GraphStats(C.Structure):
+    # keep in sync with lcg_stats in include/sibeliaz_graph.h
+    _fields_ = [(n, C.c_uint64) for n in ("n_records", "n_bases", "n_kmers", "n_distinct", "n_candidates", "n_bifurcations",
+                                          "n_junctions", "table_slots", "kernel_launches")] + \
+               [(n, C.c_double) for n in ("ms_parse", "ms_h2d", "ms_device", "ms_edges", "ms_d2h", "ms_total")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -110,6 +120,17 @@ def load_library(path=None):
     lib.lcb_write_output.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_char_p, C.c_int, C.c_int,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
     lib.lcb_version.restype = C.c_char_p
+    lib.lcg_build_from_fasta.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_void_p),
+                                         C.c_char_p, C.c_size_t]
+    lib.lcg_build.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint64, C.c_int,
+                              C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    lib.lcg_num_junctions.argtypes = [C.c_void_p]
+    lib.lcg_num_junctions.restype = C.c_uint64
+    lib.lcg_get_junctions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lcg_write_junction_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.lcg_get_stats.argtypes = [C.c_void_p, C.POINTER(GraphStats)]
+    lib.lcg_free.argtypes = [C.c_void_p]
+    lib.lcg_free.restype = None
     if path in (LIB_PATH, os.environ.get("LCB_LIB_PATH")):
         _lib = lib
     return lib
@@ -309,3 +330,55 @@ class BlocksFinder:
             self.close()
         except Exception:
             pass
+
+
+class JunctionGraph:
+    """Junctions of the compacted de Bruijn graph of a set of FASTA files, found on the GPU (reference: the `twopaco`
+    step of the pipeline, TwoPaCo VertexEnumeratorImpl, vertexenumerator.h:122-466).  `sequences=` takes in-memory
+    records (bytes) instead of files."""
+
+    def __init__(self, fastas=None, k=25, device=0, abundance=2 ** 64 - 1, sequences=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        if sequences is not None:
+            bufs = [np.frombuffer(bytes(s), dtype=np.uint8) for s in sequences]
+            ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data if len(b) else None for b in bufs])
+            lens = (C.c_uint64 * len(bufs))(*[len(b) for b in bufs])
+            rc = self._lib.lcg_build(ptrs, lens, len(bufs), int(k), int(abundance), int(device), C.byref(self._h), err, len(err))
+        else:
+            files = (C.c_char_p * len(fastas))(*[os.fsencode(f) for f in fastas])
+            rc = self._lib.lcg_build_from_fasta(files, len(fastas), int(k), int(abundance), int(device), C.byref(self._h), err, len(err))
+        if rc:
+            raise LcbError(rc, err.value.decode(errors="replace"))
+        st = GraphStats()
+        self._lib.lcg_get_stats(self._h, C.byref(st))
+        self.stats = st.as_dict()
+        self.k = int(k)
+
+    def junctions(self):
+        n = self._lib.lcg_num_junctions(self._h)
+        out = dict(chr=np.zeros(n, np.uint32), pos=np.zeros(n, np.uint32), id=np.zeros(n, np.int64))
+        self._lib.lcg_get_junctions(self._h, out["chr"].ctypes.data, out["pos"].ctypes.data, out["id"].ctypes.data)
+        return out
+
+    def write(self, path):
+        err = C.create_string_buffer(1024)
+        rc = self._lib.lcg_write_junction_file(self._h, os.fsencode(path), err, len(err))
+        if rc:
+            raise LcbError(rc, err.value.decode(errors="replace"))
+        return path
+
+    def close(self):
+        if self._h:
+            self._lib.lcg_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+GRAPH_CLI_PATH = os.path.join(_HERE, "bin", "twopaco")

@@ -14,6 +14,9 @@ LIBDIR = os.path.join(HERE, "lib")
 BINDIR = os.path.join(HERE, "bin")
 LIB = os.path.join(LIBDIR, "libsibeliaz_lcb.so")
 CLI = os.path.join(BINDIR, "sibeliaz-lcb")
+CLI_GRAPH = os.path.join(BINDIR, "twopaco")
+SOURCES = ("lcb_device.cu", "lcb_host.cpp", "graph_device.cu", "graph_host.cpp")
+HEADERS = ("lcb_traverse.cuh", "device_prims.cuh", "host_common.h", "graph_internal.h")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-pthread"]
@@ -67,7 +70,7 @@ def build_selfcheck(verbose=False, defines=("-DLCB_CHECK_MPV",), name="libsibeli
     Also used for other experimental -D variants (`--variant name -DX=Y ...`)."""
     os.makedirs(LIBDIR, exist_ok=True)
     inc = os.path.join(ROOT, "include")
-    srcs = [os.path.join(CSRC, f) for f in ("lcb_device.cu", "lcb_host.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
     out = os.path.join(LIBDIR, name)
     cmd = [_nvcc()] + ARCH + NVCC_FLAGS + list(defines) + ["-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", out] + srcs
     nccl = _nccl()
@@ -84,8 +87,8 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(BINDIR, exist_ok=True)
     inc = os.path.join(ROOT, "include")
-    srcs = [os.path.join(CSRC, f) for f in ("lcb_device.cu", "lcb_host.cpp")]
-    deps = srcs + [os.path.join(CSRC, "lcb_traverse.cuh"), os.path.join(inc, "sibeliaz_lcb.h"), __file__]
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(inc, "sibeliaz_lcb.h"), os.path.join(inc, "sibeliaz_graph.h"), __file__]
     nvcc = _nvcc()
     if force or _newer(LIB, deps):
         cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", LIB] + srcs
@@ -100,6 +103,10 @@ def build(force=False, verbose=False):
     main_src = os.path.join(CSRC, "sibeliaz_lcb_main.cpp")
     if os.path.exists(main_src) and (force or _newer(CLI, [main_src, LIB])):
         _run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, main_src, "-o", CLI, "-L", LIBDIR, "-lsibeliaz_lcb",
+              "-Wl,-rpath,$ORIGIN/../lib"])
+    graph_src = os.path.join(CSRC, "twopaco_main.cpp")
+    if os.path.exists(graph_src) and (force or _newer(CLI_GRAPH, [graph_src, LIB])):
+        _run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, graph_src, "-o", CLI_GRAPH, "-L", LIBDIR, "-lsibeliaz_lcb",
               "-Wl,-rpath,$ORIGIN/../lib"])
     return LIB
 

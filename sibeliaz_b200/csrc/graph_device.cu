@@ -1,0 +1,525 @@
+// graph_device.cu -- device pipeline of the B200-native junction finder (include/sibeliaz_graph.h): what TwoPaCo's
+// VertexEnumeratorImpl computes with a Bloom filter, two passes over 1024 mutex-guarded hash sets and temporary files
+// (TwoPaCo/src/graphconstructor/vertexenumerator.h:122-466), done exactly with ONE open-addressing k-mer table in HBM.
+//
+// Text layout: G = 'N' rec0 'N' rec1 'N' ... 'N', packed to 2 bits per base + 1 "not definite" bit per base, so that the
+// k-mer starting at any position is two 64-bit loads and a funnel shift (k <= 31).  One thread per position:
+//
+//   k_pack        bytes -> 2-bit codes + N mask                                         streaming, 1.4 B per base
+//   k_edges       every definite k-mer: canonical key, find-or-insert, OR the neighbour characters it shows (with the
+//                 A/T dummies next to 'N', vertexenumerator.h:1046-1058) into the vertex' mask   <- the HBM-bound kernel:
+//                 one random 8-byte key probe + one 8-byte mask word per position
+//   k_candidates  positions with more than one in- or out-edge (vertexenumerator.h:630-660): flag them and OR their
+//                 canonical (prev, next) pair into the vertex (what CandidateFinalFilteringWorker's hash sets collect)
+//   k_decide      per table slot: bifurcation <=> >= 2 candidate occurrences whose pairs differ, or agree on an 'N'
+//                 (vertexenumerator.h:760-790); collect the bifurcation k-mers
+//   radix sort    ids = 1 + rank of the canonical k-mer (deterministic; bifurcationstorage.h:65 sorts too)
+//   k_assign_ids, compaction of the flagged positions (genome order), k_emit_ids   -> (position, signed id) list
+//
+// The rules with all their citations are spelled out in the header of include/sibeliaz_graph.h's companion document
+// (DESIGN.md section 9); the tests compare this pipeline byte for byte with a CPU restatement of them.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "graph_internal.h"
+
+namespace {
+
+#include "device_prims.cuh"
+
+constexpr uint64_t kEmpty = ~0ULL;
+constexpr int kIdShift = 34;               // info: 0-3 in chars, 4-7 out chars, 8-32 pairs, 33 "a pair seen twice", 34.. id
+constexpr uint64_t kMultiBit = 1ULL << 33;
+
+struct Text {
+    const uint64_t *bits; // 32 bases per word, base i of a word at bits 2i
+    const uint32_t *nm;   // 32 bases per word, bit i set: not definite
+    uint64_t n;           // positions in G
+    int k;
+};
+
+struct Table {
+    uint64_t *keys;
+    unsigned long long *info;
+    uint64_t mask;
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ unsigned comp4(unsigned m) // neighbour-character set under complement: bit c -> bit 3 - c
+{
+    return ((m & 1u) << 3) | ((m & 2u) << 1) | ((m & 4u) >> 1) | ((m & 8u) >> 3);
+}
+
+struct Kmer {
+    uint64_t key; // canonical: the smaller of the k-mer and its reverse complement, first base most significant
+    bool fwd;     // the k-mer itself is the canonical one
+    int prev, next; // 0-3, 4 = not definite
+};
+
+// k-mer at position p (1 <= p, p + k < n).  Returns false when it holds a non-definite character.
+__device__ __forceinline__ bool load_kmer(const Text &t, uint64_t p, Kmer &out)
+{
+    const int k = t.k;
+    const uint64_t q = p - 1; // window [p - 1, p + k]: prev, k-mer, next  (k + 2 <= 33 bits of the N mask)
+    const uint64_t w = q >> 5;
+    const unsigned off = (unsigned)(q & 31);
+    const uint64_t nmw = ((uint64_t)t.nm[w] | ((uint64_t)t.nm[w + 1] << 32)) >> off;
+    if ((nmw >> 1) & ((1ULL << k) - 1)) return false;
+    const bool prev_n = nmw & 1, next_n = (nmw >> (k + 1)) & 1;
+    // 2-bit codes of [p - 1, p + k]: up to 66 bits -> the k-mer from two words, prev and next on their own
+    const uint64_t pw = p >> 5;
+    const unsigned po = 2u * (unsigned)(p & 31);
+    uint64_t x = t.bits[pw] >> po;
+    if (po) x |= t.bits[pw + 1] << (64 - po);
+    const uint64_t kmask = (1ULL << (2 * k)) - 1;
+    x &= kmask; // base i of the k-mer at bits 2i
+    const uint64_t r = __brevll(x);
+    const uint64_t fw = (((r & 0x5555555555555555ULL) << 1) | ((r >> 1) & 0x5555555555555555ULL)) >> (64 - 2 * k);
+    const uint64_t rc = ~x & kmask; // reverse complement with ITS first base most significant
+    out.fwd = fw < rc;
+    out.key = out.fwd ? fw : rc;
+    out.prev = prev_n ? 4 : (int)((t.bits[q >> 5] >> (2 * (q & 31))) & 3);
+    const uint64_t e = p + (uint64_t)k;
+    out.next = next_n ? 4 : (int)((t.bits[e >> 5] >> (2 * (e & 31))) & 3);
+    return true;
+}
+
+__device__ __forceinline__ uint64_t find_or_insert(const Table &tb, uint64_t key)
+{
+    uint64_t s = mix64(key) & tb.mask;
+    while (true) {
+        const uint64_t cur = tb.keys[s];
+        if (cur == key) return s;
+        if (cur == kEmpty) {
+            const unsigned long long old = atomicCAS((unsigned long long *)&tb.keys[s], (unsigned long long)kEmpty, (unsigned long long)key);
+            if (old == kEmpty || old == key) return s;
+        }
+        s = (s + 1) & tb.mask;
+    }
+}
+
+__device__ __forceinline__ uint64_t find(const Table &tb, uint64_t key) // the key is present
+{
+    uint64_t s = mix64(key) & tb.mask;
+    while (tb.keys[s] != key) s = (s + 1) & tb.mask;
+    return s;
+}
+
+// ---- bytes -> 2-bit codes + N mask: one thread per 32 bases ------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ text, uint64_t words, uint64_t *__restrict__ bits,
+                                              uint32_t *__restrict__ nm)
+{
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const uint4 *src = (const uint4 *)(text + w * 32);
+    uint64_t b = 0;
+    uint32_t m = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint4 v = src[h];
+        const uint32_t part[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const unsigned c = (part[j >> 2] >> (8 * (j & 3))) & 0xDFu; // letters to upper case
+            unsigned code = 4;
+            if (c == 'A') code = 0;
+            else if (c == 'C') code = 1;
+            else if (c == 'G') code = 2;
+            else if (c == 'T') code = 3;
+            const int i = h * 16 + j;
+            if (code < 4) b |= (uint64_t)code << (2 * i);
+            else m |= 1u << i;
+        }
+    }
+    bits[w] = b;
+    nm[w] = m;
+}
+
+// ---- the table-building pass ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_edges(Text t, Table tb, unsigned long long *n_kmers)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    bool live = false;
+    if (p + (uint64_t)t.k < t.n) {
+        Kmer km;
+        if (load_kmer(t, p, km)) {
+            live = true;
+            // the neighbour characters this occurrence shows; next to a non-definite character the two dummies A and T
+            const unsigned in = km.prev < 4 ? 1u << km.prev : 9u, out = km.next < 4 ? 1u << km.next : 9u;
+            const unsigned long long add = km.fwd ? (in | (out << 4)) : (comp4(out) | (comp4(in) << 4));
+            const uint64_t s = find_or_insert(tb, km.key);
+            if ((tb.info[s] & add) != add) atomicOr(&tb.info[s], add);
+        }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_kmers, (unsigned long long)__popc(m));
+}
+
+__global__ void __launch_bounds__(256) k_candidates(Text t, Table tb, uint8_t *__restrict__ flag, unsigned *__restrict__ count)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (p + (uint64_t)t.k >= t.n) return;
+    Kmer km;
+    if (!load_kmer(t, p, km)) return;
+    const uint64_t s = find(tb, km.key);
+    const unsigned long long info = tb.info[s];
+    const unsigned vin = (unsigned)info & 15u, vout = ((unsigned)info >> 4) & 15u;
+    const int in = km.prev < 4 ? __popc(km.fwd ? vin : vout) : 2;
+    const int out = km.next < 4 ? __popc(km.fwd ? vout : vin) : 2;
+    if (in <= 1 && out <= 1) return;
+    flag[p] = 1;
+    const int cp = km.fwd ? km.prev : (km.next < 4 ? 3 - km.next : 4), cn = km.fwd ? km.next : (km.prev < 4 ? 3 - km.prev : 4);
+    const unsigned long long bit = 1ULL << (8 + cp * 5 + cn);
+    const unsigned long long old = atomicOr(&tb.info[s], bit);
+    if ((old & bit) && !(old & kMultiBit)) atomicOr(&tb.info[s], kMultiBit);
+    if (count) atomicAdd(&count[s], 1u); // only with a finite abundance threshold (twopaco -a)
+}
+
+__device__ __forceinline__ bool is_bifurcation(unsigned long long info)
+{
+    const unsigned pairs = (unsigned)(info >> 8) & 0x1FFFFFFu;
+    if (!pairs) return false;
+    if (pairs & (pairs - 1)) return true; // two different (prev, next) pairs
+    if (!(info & kMultiBit)) return false; // a single candidate occurrence
+    const int p = __ffs((int)pairs) - 1;
+    return p / 5 == 4 || p % 5 == 4; // the shared prev (or next) is 'N': unknown twice
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_decide(Table tb, const unsigned *__restrict__ count, unsigned long long abundance,
+                                                unsigned long long *counters /* [0] distinct, [1] bifurcations */,
+                                                uint64_t *__restrict__ bif_keys)
+{
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool used = false, bif = false;
+    uint64_t key = kEmpty;
+    if (s <= tb.mask) {
+        key = tb.keys[s];
+        used = key != kEmpty;
+        if (used) bif = is_bifurcation(tb.info[s]) && (!count || (unsigned long long)count[s] <= abundance);
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mb = __ballot_sync(0xFFFFFFFFu, bif);
+    if (!FILL) {
+        const unsigned mu = __ballot_sync(0xFFFFFFFFu, used);
+        if (lane == 0) {
+            if (mu) atomicAdd(&counters[0], (unsigned long long)__popc(mu));
+            if (mb) atomicAdd(&counters[1], (unsigned long long)__popc(mb));
+        }
+    } else if (mb) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(mb));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (bif) bif_keys[base + __popc(mb & ((1u << lane) - 1))] = key;
+    }
+}
+
+__global__ void k_assign_ids(Table tb, const uint64_t *__restrict__ sorted, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t s = find(tb, sorted[i]);
+    atomicOr(&tb.info[s], (unsigned long long)(i + 1) << kIdShift);
+}
+
+// ---- ordered compaction of the flagged positions: 256 threads x 16 flags per block ---------------------------------
+constexpr int kFlagTile = 4096;
+__device__ __forceinline__ unsigned flags16(const uint8_t *flag, uint64_t base, uint64_t n)
+{
+    unsigned m = 0; // bit j: flag[base + j]
+    if (base + 16 <= n) {
+        const uint4 v = *(const uint4 *)(flag + base);
+        const uint32_t part[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if ((part[j >> 2] >> (8 * (j & 3))) & 0xFFu) m |= 1u << j;
+    } else {
+        for (int j = 0; j < 16 && base + j < n; j++)
+            if (flag[base + j]) m |= 1u << j;
+    }
+    return m;
+}
+__global__ void __launch_bounds__(256) k_flag_count(const uint8_t *__restrict__ flag, uint64_t n, unsigned *__restrict__ block_count)
+{
+    __shared__ unsigned s[8];
+    const uint64_t base = (uint64_t)blockIdx.x * kFlagTile + (uint64_t)threadIdx.x * 16;
+    unsigned c = base < n ? __popc(flags16(flag, base, n)) : 0;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; w++) tot += s[w];
+        block_count[blockIdx.x] = tot;
+    }
+}
+__global__ void __launch_bounds__(256) k_flag_write(const uint8_t *__restrict__ flag, uint64_t n, const unsigned *__restrict__ block_off,
+                                                    uint64_t *__restrict__ out)
+{
+    __shared__ unsigned s[256];
+    const uint64_t base = (uint64_t)blockIdx.x * kFlagTile + (uint64_t)threadIdx.x * 16;
+    const unsigned m = base < n ? flags16(flag, base, n) : 0;
+    const unsigned c = __popc(m);
+    s[threadIdx.x] = c;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        const unsigned x = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+        __syncthreads();
+        s[threadIdx.x] += x;
+        __syncthreads();
+    }
+    uint64_t w = (uint64_t)block_off[blockIdx.x] + s[threadIdx.x] - c;
+    for (unsigned mm = m; mm; mm &= mm - 1) out[w++] = base + (uint64_t)(__ffs((int)mm) - 1);
+}
+
+__global__ void k_emit_ids(Text t, Table tb, const uint64_t *__restrict__ pos, unsigned n, int32_t *__restrict__ id)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Kmer km;
+    load_kmer(t, pos[i], km); // flagged positions hold definite k-mers
+    const long long v = (long long)(tb.info[find(tb, km.key)] >> kIdShift);
+    id[i] = (int32_t)(km.fwd ? v : -v);
+}
+
+// ---- host helpers ----------------------------------------------------------------------------------------------------
+struct Scope { // frees everything on every exit path
+    std::vector<void *> dev;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Scope()
+    {
+        for (void *p : dev) cudaFree(p);
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+#define CU(x)                                                                    \
+    do {                                                                         \
+        cudaError_t e_ = (x);                                                    \
+        if (e_ != cudaSuccess) {                                                 \
+            err = std::string(#x) + ": " + cudaGetErrorString(e_);               \
+            return LCG_ERR_CUDA;                                                 \
+        }                                                                        \
+    } while (0)
+
+template <typename T>
+int dalloc(Scope &sc, T **p, size_t n, std::string &err)
+{
+    void *q = nullptr;
+    CU(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    sc.dev.push_back(q);
+    *p = (T *)q;
+    return LCG_OK;
+}
+
+int exclusive_scan_u32(Scope &sc, const unsigned *in, unsigned *out, size_t n, unsigned *d_total, unsigned *d_tile, uint64_t &launches,
+                       std::string &err)
+{
+    const unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
+    k_scan_tiles<<<tiles, 256, 0, sc.stream>>>(in, out, d_tile, n);
+    k_scan_sums<<<1, 32, 0, sc.stream>>>(d_tile, tiles, d_total);
+    k_scan_add<<<(unsigned)((n + 255) / 256), 256, 0, sc.stream>>>(out, d_tile, n);
+    launches += 3;
+    CU(cudaGetLastError());
+    return LCG_OK;
+}
+
+} // namespace
+
+namespace lcg {
+
+int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
+    const int k = in.k;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        err = "no CUDA device: this library has no CPU fallback";
+        return LCG_ERR_CUDA;
+    }
+    CU(cudaSetDevice(in.device));
+    {
+        int major = 0;
+        CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, in.device));
+        if (major < 10) {
+            err = "device " + std::to_string(in.device) + " is not sm_100-class";
+            return LCG_ERR_CUDA;
+        }
+    }
+    Scope sc;
+    CU(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+    for (auto &e : sc.ev) CU(cudaEventCreate(&e));
+    lcg_stats &st = out.st;
+    st.n_records = (uint64_t)in.n_records;
+    // ---- layout of G
+    std::vector<uint64_t> goff((size_t)in.n_records + 1);
+    uint64_t g = 1;
+    for (int r = 0; r < in.n_records; r++) {
+        goff[(size_t)r] = g;
+        g += in.len[r] + 1;
+        st.n_bases += in.len[r];
+    }
+    goff[(size_t)in.n_records] = g;
+    const uint64_t G = g;                                // positions; G[0] and G[G-1] are 'N'
+    const uint64_t words = (G + 31) / 32 + 2;            // + padding words read by windows near the end
+    const uint64_t padded = words * 32;
+    // ---- k-mer table: a power of two >= 2 x positions
+    uint64_t cap = 1 << 16;
+    while (cap < 2 * G) cap <<= 1;
+    st.table_slots = cap;
+    const bool finite_abundance = in.abundance != UINT64_MAX;
+    {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const double need = (double)cap * (16.0 + (finite_abundance ? 4.0 : 0.0)) + (double)padded * (1.0 + 1.0 + 0.25 + 0.125) + (64 << 20);
+        if (need > (double)free_b) {
+            err = "the k-mer table (" + std::to_string((unsigned long long)(need / (1 << 20))) + " MiB) does not fit the device (" +
+                  std::to_string((unsigned long long)(free_b >> 20)) + " MiB free)";
+            return LCG_ERR_MEMORY;
+        }
+    }
+    uint8_t *d_text = nullptr, *d_flag = nullptr;
+    uint64_t *d_bits = nullptr, *d_keys = nullptr;
+    uint32_t *d_nm = nullptr;
+    unsigned long long *d_info = nullptr, *d_ctr = nullptr;
+    unsigned *d_cnt = nullptr;
+    int rc;
+    if ((rc = dalloc(sc, &d_text, padded, err))) return rc;
+    if ((rc = dalloc(sc, &d_bits, words, err))) return rc;
+    if ((rc = dalloc(sc, &d_nm, words, err))) return rc;
+    if ((rc = dalloc(sc, &d_flag, padded, err))) return rc;
+    if ((rc = dalloc(sc, &d_keys, cap, err))) return rc;
+    if ((rc = dalloc(sc, &d_info, cap, err))) return rc;
+    if ((rc = dalloc(sc, &d_ctr, 4, err))) return rc;
+    if (finite_abundance && (rc = dalloc(sc, &d_cnt, cap, err))) return rc;
+    // ---- sequences -> device (separators and padding stay 'N')
+    const auto t_h2d = std::chrono::steady_clock::now();
+    CU(cudaMemsetAsync(d_text, 'N', padded, sc.stream));
+    CU(cudaStreamSynchronize(sc.stream));
+    for (int r = 0; r < in.n_records; r++)
+        if (in.len[r]) CU(cudaMemcpyAsync(d_text + goff[(size_t)r], in.seq[r], in.len[r], cudaMemcpyHostToDevice, sc.stream));
+    CU(cudaStreamSynchronize(sc.stream));
+    st.ms_h2d = ms_since(t_h2d);
+    // ---- device pipeline
+    CU(cudaEventRecord(sc.ev[0], sc.stream));
+    CU(cudaMemsetAsync(d_keys, 0xFF, cap * sizeof(uint64_t), sc.stream));
+    CU(cudaMemsetAsync(d_info, 0, cap * sizeof(unsigned long long), sc.stream));
+    CU(cudaMemsetAsync(d_flag, 0, padded, sc.stream));
+    CU(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), sc.stream));
+    if (d_cnt) CU(cudaMemsetAsync(d_cnt, 0, cap * sizeof(unsigned), sc.stream));
+    k_pack<<<(unsigned)((words + 255) / 256), 256, 0, sc.stream>>>(d_text, words, d_bits, d_nm);
+    const Text text{d_bits, d_nm, G, k};
+    const Table tb{d_keys, d_info, cap - 1};
+    const unsigned pos_blocks = (unsigned)((G + 255) / 256);
+    CU(cudaEventRecord(sc.ev[1], sc.stream));
+    k_edges<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_ctr + 2);
+    CU(cudaEventRecord(sc.ev[2], sc.stream));
+    k_candidates<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_flag, d_cnt);
+    const unsigned slot_blocks = (unsigned)((cap + 255) / 256);
+    k_decide<false><<<slot_blocks, 256, 0, sc.stream>>>(tb, d_cnt, (unsigned long long)in.abundance, d_ctr, nullptr);
+    st.kernel_launches += 4;
+    unsigned long long h_ctr[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, sc.stream));
+    CU(cudaStreamSynchronize(sc.stream));
+    CU(cudaGetLastError());
+    st.n_distinct = h_ctr[0];
+    st.n_bifurcations = h_ctr[1];
+    st.n_kmers = h_ctr[2];
+    if (h_ctr[1] >= (1ULL << 29)) {
+        err = "more than 2^29 junction vertices";
+        return LCG_ERR_ARG;
+    }
+    const unsigned nb = (unsigned)h_ctr[1];
+    // ---- ids: sort the bifurcation k-mers
+    uint64_t *d_bif = nullptr, *d_sorted = nullptr;
+    if ((rc = dalloc(sc, &d_bif, nb, err))) return rc;
+    if ((rc = dalloc(sc, &d_sorted, nb, err))) return rc;
+    if (nb) {
+        CU(cudaMemsetAsync(d_ctr + 1, 0, sizeof(unsigned long long), sc.stream));
+        k_decide<true><<<slot_blocks, 256, 0, sc.stream>>>(tb, d_cnt, (unsigned long long)in.abundance, d_ctr, d_bif);
+        unsigned *perm = nullptr, *tmp = nullptr, *d_hist = nullptr, *d_small = nullptr;
+        const unsigned sblocks = (nb + kSortTile - 1) / kSortTile;
+        const size_t hn = (size_t)256 * sblocks;
+        if ((rc = dalloc(sc, &perm, nb, err))) return rc;
+        if ((rc = dalloc(sc, &tmp, nb, err))) return rc;
+        if ((rc = dalloc(sc, &d_hist, hn + hn / kScanTile + 8, err))) return rc;
+        if ((rc = dalloc(sc, &d_small, 8, err))) return rc;
+        k_iota<<<(nb + 255) / 256, 256, 0, sc.stream>>>(perm, nb);
+        st.kernel_launches += 2;
+        for (int shift = 0; shift < 2 * k; shift += 8) { // stable LSD passes over the 2k key bits
+            k_radix_hist<uint64_t><<<sblocks, 256, 0, sc.stream>>>(perm, d_bif, shift, nb, d_hist, 0);
+            if ((rc = exclusive_scan_u32(sc, d_hist, d_hist, hn, d_small, d_hist + hn, st.kernel_launches, err))) return rc;
+            k_radix_scatter<uint64_t><<<sblocks, 256, 0, sc.stream>>>(perm, tmp, d_bif, shift, nb, d_hist, 0);
+            std::swap(perm, tmp);
+            st.kernel_launches += 2;
+        }
+        k_gather<<<(nb + 255) / 256, 256, 0, sc.stream>>>(perm, d_bif, d_sorted, nb);
+        k_assign_ids<<<(nb + 255) / 256, 256, 0, sc.stream>>>(tb, d_sorted, nb);
+        st.kernel_launches += 2;
+    }
+    // ---- flagged positions in genome order
+    const unsigned fblocks = (unsigned)((G + kFlagTile - 1) / kFlagTile);
+    unsigned *d_bc = nullptr, *d_bo = nullptr, *d_tile = nullptr, *d_total = nullptr;
+    if ((rc = dalloc(sc, &d_bc, fblocks, err))) return rc;
+    if ((rc = dalloc(sc, &d_bo, fblocks, err))) return rc;
+    if ((rc = dalloc(sc, &d_tile, fblocks / kScanTile + 8, err))) return rc;
+    if ((rc = dalloc(sc, &d_total, 4, err))) return rc;
+    k_flag_count<<<fblocks, 256, 0, sc.stream>>>(d_flag, G, d_bc);
+    st.kernel_launches += 1;
+    if ((rc = exclusive_scan_u32(sc, d_bc, d_bo, fblocks, d_total, d_tile, st.kernel_launches, err))) return rc;
+    unsigned nc = 0;
+    CU(cudaMemcpyAsync(&nc, d_total, sizeof nc, cudaMemcpyDeviceToHost, sc.stream));
+    CU(cudaStreamSynchronize(sc.stream));
+    CU(cudaGetLastError());
+    st.n_candidates = nc;
+    uint64_t *d_pos = nullptr;
+    int32_t *d_id = nullptr;
+    if ((rc = dalloc(sc, &d_pos, nc, err))) return rc;
+    if ((rc = dalloc(sc, &d_id, nc, err))) return rc;
+    if (nc) {
+        k_flag_write<<<fblocks, 256, 0, sc.stream>>>(d_flag, G, d_bo, d_pos);
+        k_emit_ids<<<(nc + 255) / 256, 256, 0, sc.stream>>>(text, tb, d_pos, nc, d_id);
+        st.kernel_launches += 2;
+    }
+    CU(cudaEventRecord(sc.ev[3], sc.stream));
+    CU(cudaStreamSynchronize(sc.stream));
+    CU(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, sc.ev[0], sc.ev[3]);
+    st.ms_device = ms;
+    cudaEventElapsedTime(&ms, sc.ev[1], sc.ev[2]);
+    st.ms_edges = ms;
+    // ---- results
+    const auto t_d2h = std::chrono::steady_clock::now();
+    out.pos.resize(nc);
+    out.id.resize(nc);
+    if (nc) {
+        CU(cudaMemcpy(out.pos.data(), d_pos, (size_t)nc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out.id.data(), d_id, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    st.ms_d2h = ms_since(t_d2h);
+    st.ms_total = ms_since(t_begin);
+    return LCG_OK;
+}
+
+} // namespace lcg

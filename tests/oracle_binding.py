@@ -124,3 +124,42 @@ def run_reference_lcb(graph, fastas, k, outdir, b=200, m=50, a=150, threads=1, n
     if r.returncode:
         raise RuntimeError(r.stdout)
     return r.stdout
+
+
+# ---- graph construction (oracle/graph_oracle.cpp): the step before the LCB path -----------------------------------
+GRAPH_ORACLE_LIB = os.path.join(ORACLE_DIR, "libgraph_oracle.so")
+_glib = None
+
+
+def graph_lib():
+    global _glib
+    if _glib is None:
+        if not os.path.exists(GRAPH_ORACLE_LIB):
+            build_oracle()
+        L = C.CDLL(GRAPH_ORACLE_LIB)
+        L.gro_build.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int]
+        L.gro_build.restype = C.c_int64
+        L.gro_canonicalize.argtypes = [C.c_char_p, C.c_char_p]
+        L.gro_canonicalize.restype = C.c_int64
+        _glib = L
+    return _glib
+
+
+def graph_oracle_build(fastas, k, out, abundance=2 ** 64 - 1):
+    """Junction file of the FASTA files by the CPU restatement; returns the number of records."""
+    err = C.create_string_buffer(512)
+    files = (C.c_char_p * len(fastas))(*[os.fsencode(f) for f in fastas])
+    n = graph_lib().gro_build(files, len(fastas), k, abundance, os.fsencode(out), err, len(err))
+    if n < 0:
+        raise RuntimeError(err.value.decode())
+    return n
+
+
+def canonical_junctions(path, out=None):
+    """Label-free normal form of a junction file (vertices renumbered by first appearance, first appearance positive):
+    returns its bytes.  Two junction files describe the same graph iff these are equal."""
+    out = out or path + ".canon"
+    if graph_lib().gro_canonicalize(os.fsencode(path), os.fsencode(out)) < 0:
+        raise RuntimeError("cannot canonicalise " + path)
+    with open(out, "rb") as f:
+        return f.read()

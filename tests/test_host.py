@@ -24,6 +24,10 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert set(sb.EXPORTS) <= declared
+    ghdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "sibeliaz_graph.h")).read(), flags=re.S)
+    gdecl = set(re.findall(r"\b(lcg_[a-z_0-9]+)\s*\(", ghdr))
+    assert len(gdecl) >= 7
+    assert not [s for s in sorted(gdecl) if not hasattr(lib, s)]
     assert b"1.2.7" in ctypes.cast(sb.load_library().lcb_version(), ctypes.c_char_p).value
 
 
