@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "graph_internal.h"
@@ -42,9 +43,11 @@ struct Text {
     int k;
 };
 
+struct Slot { // key and vertex word side by side: one 32-byte sector per probe
+    unsigned long long key, info;
+};
 struct Table {
-    uint64_t *keys;
-    unsigned long long *info;
+    Slot *slot;
     uint64_t mask;
 };
 
@@ -101,10 +104,10 @@ __device__ __forceinline__ uint64_t find_or_insert(const Table &tb, uint64_t key
 {
     uint64_t s = mix64(key) & tb.mask;
     while (true) {
-        const uint64_t cur = tb.keys[s];
+        const uint64_t cur = tb.slot[s].key;
         if (cur == key) return s;
         if (cur == kEmpty) {
-            const unsigned long long old = atomicCAS((unsigned long long *)&tb.keys[s], (unsigned long long)kEmpty, (unsigned long long)key);
+            const unsigned long long old = atomicCAS(&tb.slot[s].key, (unsigned long long)kEmpty, (unsigned long long)key);
             if (old == kEmpty || old == key) return s;
         }
         s = (s + 1) & tb.mask;
@@ -114,8 +117,14 @@ __device__ __forceinline__ uint64_t find_or_insert(const Table &tb, uint64_t key
 __device__ __forceinline__ uint64_t find(const Table &tb, uint64_t key) // the key is present
 {
     uint64_t s = mix64(key) & tb.mask;
-    while (tb.keys[s] != key) s = (s + 1) & tb.mask;
+    while (tb.slot[s].key != key) s = (s + 1) & tb.mask;
     return s;
+}
+
+__global__ void k_table_init(Slot *slot, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) *(ulonglong2 *)&slot[i] = make_ulonglong2(kEmpty, 0ULL);
 }
 
 // ---- bytes -> 2-bit codes + N mask: one thread per 32 bases ------------------------------------------------------
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(256) k_edges(Text t, Table tb, unsigned long l
             const unsigned in = km.prev < 4 ? 1u << km.prev : 9u, out = km.next < 4 ? 1u << km.next : 9u;
             const unsigned long long add = km.fwd ? (in | (out << 4)) : (comp4(out) | (comp4(in) << 4));
             const uint64_t s = find_or_insert(tb, km.key);
-            if ((tb.info[s] & add) != add) atomicOr(&tb.info[s], add);
+            if ((tb.slot[s].info & add) != add) atomicOr(&tb.slot[s].info, add);
         }
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(256) k_candidates(Text t, Table tb, uint8_t *_
     Kmer km;
     if (!load_kmer(t, p, km)) return;
     const uint64_t s = find(tb, km.key);
-    const unsigned long long info = tb.info[s];
+    const unsigned long long info = tb.slot[s].info;
     const unsigned vin = (unsigned)info & 15u, vout = ((unsigned)info >> 4) & 15u;
     const int in = km.prev < 4 ? __popc(km.fwd ? vin : vout) : 2;
     const int out = km.next < 4 ? __popc(km.fwd ? vout : vin) : 2;
@@ -183,8 +192,8 @@ __global__ void __launch_bounds__(256) k_candidates(Text t, Table tb, uint8_t *_
     flag[p] = 1;
     const int cp = km.fwd ? km.prev : (km.next < 4 ? 3 - km.next : 4), cn = km.fwd ? km.next : (km.prev < 4 ? 3 - km.prev : 4);
     const unsigned long long bit = 1ULL << (8 + cp * 5 + cn);
-    const unsigned long long old = atomicOr(&tb.info[s], bit);
-    if ((old & bit) && !(old & kMultiBit)) atomicOr(&tb.info[s], kMultiBit);
+    const unsigned long long old = atomicOr(&tb.slot[s].info, bit);
+    if ((old & bit) && !(old & kMultiBit)) atomicOr(&tb.slot[s].info, kMultiBit);
     if (count) atomicAdd(&count[s], 1u); // only with a finite abundance threshold (twopaco -a)
 }
 
@@ -207,9 +216,10 @@ __global__ void __launch_bounds__(256) k_decide(Table tb, const unsigned *__rest
     bool used = false, bif = false;
     uint64_t key = kEmpty;
     if (s <= tb.mask) {
-        key = tb.keys[s];
+        const ulonglong2 v = *(const ulonglong2 *)&tb.slot[s];
+        key = v.x;
         used = key != kEmpty;
-        if (used) bif = is_bifurcation(tb.info[s]) && (!count || (unsigned long long)count[s] <= abundance);
+        if (used) bif = is_bifurcation(v.y) && (!count || (unsigned long long)count[s] <= abundance);
     }
     const unsigned lane = threadIdx.x & 31;
     const unsigned mb = __ballot_sync(0xFFFFFFFFu, bif);
@@ -232,7 +242,7 @@ __global__ void k_assign_ids(Table tb, const uint64_t *__restrict__ sorted, unsi
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t s = find(tb, sorted[i]);
-    atomicOr(&tb.info[s], (unsigned long long)(i + 1) << kIdShift);
+    atomicOr(&tb.slot[s].info, (unsigned long long)(i + 1) << kIdShift);
 }
 
 // ---- ordered compaction of the flagged positions: 256 threads x 16 flags per block ---------------------------------
@@ -292,7 +302,7 @@ __global__ void k_emit_ids(Text t, Table tb, const uint64_t *__restrict__ pos, u
     if (i >= n) return;
     Kmer km;
     load_kmer(t, pos[i], km); // flagged positions hold definite k-mers
-    const long long v = (long long)(tb.info[find(tb, km.key)] >> kIdShift);
+    const long long v = (long long)(tb.slot[find(tb, km.key)].info >> kIdShift);
     id[i] = (int32_t)(km.fwd ? v : -v);
 }
 
@@ -399,17 +409,17 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         }
     }
     uint8_t *d_text = nullptr, *d_flag = nullptr;
-    uint64_t *d_bits = nullptr, *d_keys = nullptr;
+    uint64_t *d_bits = nullptr;
+    Slot *d_slot = nullptr;
     uint32_t *d_nm = nullptr;
-    unsigned long long *d_info = nullptr, *d_ctr = nullptr;
+    unsigned long long *d_ctr = nullptr;
     unsigned *d_cnt = nullptr;
     int rc;
     if ((rc = dalloc(sc, &d_text, padded, err))) return rc;
     if ((rc = dalloc(sc, &d_bits, words, err))) return rc;
     if ((rc = dalloc(sc, &d_nm, words, err))) return rc;
     if ((rc = dalloc(sc, &d_flag, padded, err))) return rc;
-    if ((rc = dalloc(sc, &d_keys, cap, err))) return rc;
-    if ((rc = dalloc(sc, &d_info, cap, err))) return rc;
+    if ((rc = dalloc(sc, &d_slot, cap, err))) return rc;
     if ((rc = dalloc(sc, &d_ctr, 4, err))) return rc;
     if (finite_abundance && (rc = dalloc(sc, &d_cnt, cap, err))) return rc;
     // ---- sequences -> device (separators and padding stay 'N')
@@ -422,14 +432,13 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     st.ms_h2d = ms_since(t_h2d);
     // ---- device pipeline
     CU(cudaEventRecord(sc.ev[0], sc.stream));
-    CU(cudaMemsetAsync(d_keys, 0xFF, cap * sizeof(uint64_t), sc.stream));
-    CU(cudaMemsetAsync(d_info, 0, cap * sizeof(unsigned long long), sc.stream));
+    k_table_init<<<(unsigned)((cap + 255) / 256), 256, 0, sc.stream>>>(d_slot, cap);
     CU(cudaMemsetAsync(d_flag, 0, padded, sc.stream));
     CU(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(unsigned long long), sc.stream));
     if (d_cnt) CU(cudaMemsetAsync(d_cnt, 0, cap * sizeof(unsigned), sc.stream));
     k_pack<<<(unsigned)((words + 255) / 256), 256, 0, sc.stream>>>(d_text, words, d_bits, d_nm);
     const Text text{d_bits, d_nm, G, k};
-    const Table tb{d_keys, d_info, cap - 1};
+    const Table tb{d_slot, cap - 1};
     const unsigned pos_blocks = (unsigned)((G + 255) / 256);
     CU(cudaEventRecord(sc.ev[1], sc.stream));
     k_edges<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_ctr + 2);
@@ -437,7 +446,7 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     k_candidates<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_flag, d_cnt);
     const unsigned slot_blocks = (unsigned)((cap + 255) / 256);
     k_decide<false><<<slot_blocks, 256, 0, sc.stream>>>(tb, d_cnt, (unsigned long long)in.abundance, d_ctr, nullptr);
-    st.kernel_launches += 4;
+    st.kernel_launches += 5;
     unsigned long long h_ctr[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, sc.stream));
     CU(cudaStreamSynchronize(sc.stream));
