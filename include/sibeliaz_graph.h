@@ -57,6 +57,11 @@ int lcg_build_from_fasta(const char *const *fasta_files, int n_files, int k, uin
 int lcg_build(const uint8_t *const *seq, const uint64_t *len, int n_records, int k, uint64_t abundance, int device,
               lcg_graph **out, char *err, size_t errlen);
 
+/* As lcg_build, and the record bytes and the junction records also STAY on the device, for lcb_create_from_graph
+ * (include/sibeliaz_lcb.h): the fused pipeline, no junction file in between.  lcg_free releases them. */
+int lcg_build_resident(const uint8_t *const *seq, const uint64_t *len, int n_records, int k, uint64_t abundance, int device,
+                       lcg_graph **out, char *err, size_t errlen);
+
 uint64_t lcg_num_junctions(const lcg_graph *);
 /* Junction records in genome order (JunctionPosition: chr, pos, id; junctionapi.h:10-39); any pointer may be NULL. */
 int lcg_get_junctions(const lcg_graph *, uint32_t *chr, uint32_t *pos, int64_t *id);

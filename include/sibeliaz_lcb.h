@@ -64,6 +64,12 @@ typedef struct lcb_index_view {
 
 int lcb_index_load(const char *graph_file, const char *const *fasta_files, int n_fasta, int k, int abundance,
                    lcb_index **out, char *err, size_t errlen);
+/* Fused pipeline (no junction file): FASTA records only; the junction part of the index is then built ON THE DEVICE by
+ * lcb_create_from_graph from a graph made by lcg_build_resident (include/sibeliaz_graph.h) out of these very records. */
+int lcb_index_load_fasta(const char *const *fasta_files, int n_fasta, int k, lcb_index **out, char *err, size_t errlen);
+/* Record r is seq[r][0 .. len[r]); the arrays live as long as the index.  Returns the number of records. */
+int32_t lcb_index_get_sequences(const lcb_index *, const uint8_t *const **seq, const uint64_t **len);
+
 /* Builds the device record layout on the host threads (optional; lcb_create packs by itself otherwise). */
 int lcb_index_pack(lcb_index *);
 int lcb_index_get_view(const lcb_index *, lcb_index_view *view);
@@ -124,6 +130,12 @@ int lcb_warmup(int device);
 
 /* Uploads the index (arrays are caller-owned and may be freed once this returns). */
 int lcb_create(const lcb_index_view *index, const lcb_params *params, lcb_ctx **out);
+
+/* Fused pipeline: the junction index (abundance filter, occurrence lists, edge characters: JunctionStorage::Init,
+ * junctionstorage.h:572-650) is built on the device from a resident graph; `index` (from lcb_index_load_fasta on the same
+ * records) learns the number of chromosomes the junctions span and serves lcb_write_output afterwards. */
+struct lcg_graph;
+int lcb_create_from_graph(const struct lcg_graph *graph, lcb_index *index, int abundance, const lcb_params *params, lcb_ctx **out);
 
 /* Multi-GPU (optional): one process per GPU.  Rank 0 obtains an id with lcb_comm_unique_id, the
  * caller distributes the bytes (e.g. torch.distributed broadcast), every rank calls lcb_comm_init. */

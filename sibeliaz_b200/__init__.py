@@ -124,6 +124,11 @@ def load_library(path=None):
                                          C.c_char_p, C.c_size_t]
     lib.lcg_build.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint64, C.c_int,
                               C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    lib.lcg_build_resident.argtypes = lib.lcg_build.argtypes
+    lib.lcb_index_load_fasta.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    lib.lcb_index_get_sequences.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.POINTER(C.c_uint64))]
+    lib.lcb_index_get_sequences.restype = C.c_int32
+    lib.lcb_create_from_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
     lib.lcg_num_junctions.argtypes = [C.c_void_p]
     lib.lcg_num_junctions.restype = C.c_uint64
     lib.lcg_get_junctions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -249,7 +254,10 @@ class BlocksFinder:
         p.device = self.device
         p.window_init, p.window_max = self._window
         p.collect_counters = int(self._collect) if not isinstance(self._collect, bool) else (1 if self._collect else 0)
-        rc = self._lib.lcb_create(C.byref(self.storage.view), C.byref(p), C.byref(self._ctx))
+        if isinstance(self.storage, FusedStorage):
+            rc = self._lib.lcb_create_from_graph(self.storage._graph, self.storage._h, self.storage.abundance, C.byref(p), C.byref(self._ctx))
+        else:
+            rc = self._lib.lcb_create(C.byref(self.storage.view), C.byref(p), C.byref(self._ctx))
         if rc:
             msg = self._lib.lcb_last_error(self._ctx).decode() if self._ctx else "lcb_create failed"
             if self._ctx:
@@ -382,3 +390,42 @@ class JunctionGraph:
 
 
 GRAPH_CLI_PATH = os.path.join(_HERE, "bin", "twopaco")
+
+
+class FusedStorage:
+    """The fused pipeline's stand-in for JunctionStorage: FASTA files only.  The junctions are found on the GPU
+    (lcg_build_resident) and stay there; BlocksFinder builds the junction index on the device from them
+    (lcb_create_from_graph) -- no junction file, no host-side index."""
+
+    def __init__(self, fastas, k, abundance=150, device=0):
+        self._lib = load_library()
+        self.k, self.abundance, self.device = int(k), int(abundance), int(device)
+        self._h, self._graph = C.c_void_p(), C.c_void_p()
+        err = C.create_string_buffer(1024)
+        files = (C.c_char_p * len(fastas))(*[os.fsencode(f) for f in fastas])
+        rc = self._lib.lcb_index_load_fasta(files, len(fastas), self.k, C.byref(self._h), err, len(err))
+        if rc:
+            raise LcbError(rc, err.value.decode(errors="replace"))
+        seq, ln = C.POINTER(C.c_void_p)(), C.POINTER(C.c_uint64)()
+        n = self._lib.lcb_index_get_sequences(self._h, C.byref(seq), C.byref(ln))
+        rc = self._lib.lcg_build_resident(seq, ln, n, self.k, 2 ** 64 - 1, self.device, C.byref(self._graph), err, len(err))
+        if rc:
+            self.close()
+            raise LcbError(rc, err.value.decode(errors="replace"))
+        st = GraphStats()
+        self._lib.lcg_get_stats(self._graph, C.byref(st))
+        self.graph_stats = st.as_dict()
+
+    def close(self):
+        if self._graph:
+            self._lib.lcg_free(self._graph)
+            self._graph = C.c_void_p()
+        if self._h:
+            self._lib.lcb_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

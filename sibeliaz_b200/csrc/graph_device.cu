@@ -14,7 +14,8 @@
 //   k_decide      per table slot: bifurcation <=> >= 2 candidate occurrences whose pairs differ, or agree on an 'N'
 //                 (vertexenumerator.h:760-790); collect the bifurcation k-mers
 //   radix sort    ids = 1 + rank of the canonical k-mer (deterministic; bifurcationstorage.h:65 sorts too)
-//   k_assign_ids, compaction of the flagged positions (genome order), k_emit_ids   -> (position, signed id) list
+//   k_assign_ids, k_mark_stubs, compaction of the flagged positions (genome order), k_emit_ids, k_final_*
+//                 -> the junction records (record, position, signed id; stubs numbered) in genome order, on the device
 //
 // The rules with all their citations are spelled out in the header of include/sibeliaz_graph.h's companion document
 // (DESIGN.md section 9); the tests compare this pipeline byte for byte with a CPU restatement of them.
@@ -212,28 +213,49 @@ __global__ void __launch_bounds__(256) k_decide(Table tb, const unsigned *__rest
                                                 unsigned long long *counters /* [0] distinct, [1] bifurcations */,
                                                 uint64_t *__restrict__ bif_keys)
 {
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool used = false, bif = false;
-    uint64_t key = kEmpty;
-    if (s <= tb.mask) {
-        const ulonglong2 v = *(const ulonglong2 *)&tb.slot[s];
-        key = v.x;
-        used = key != kEmpty;
-        if (used) bif = is_bifurcation(v.y) && (!count || (unsigned long long)count[s] <= abundance);
-    }
+    // grid-stride over the slots; the counting pass keeps its sums in registers (one atomic pair per block), the filling
+    // pass reserves output space once per warp and iteration
+    __shared__ unsigned long long su[8], sb[8];
     const unsigned lane = threadIdx.x & 31;
-    const unsigned mb = __ballot_sync(0xFFFFFFFFu, bif);
-    if (!FILL) {
-        const unsigned mu = __ballot_sync(0xFFFFFFFFu, used);
-        if (lane == 0) {
-            if (mu) atomicAdd(&counters[0], (unsigned long long)__popc(mu));
-            if (mb) atomicAdd(&counters[1], (unsigned long long)__popc(mb));
+    unsigned long long n_used = 0, n_bif = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t slots = tb.mask + 1, rounds = (slots + stride - 1) / stride;
+    for (uint64_t it = 0; it < rounds; it++) {
+        const uint64_t s = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool used = false, bif = false;
+        uint64_t key = kEmpty;
+        if (s < slots) {
+            const ulonglong2 v = *(const ulonglong2 *)&tb.slot[s];
+            key = v.x;
+            used = key != kEmpty;
+            if (used) bif = is_bifurcation(v.y) && (!count || (unsigned long long)count[s] <= abundance);
         }
-    } else if (mb) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(mb));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (bif) bif_keys[base + __popc(mb & ((1u << lane) - 1))] = key;
+        if (!FILL) {
+            n_used += used, n_bif += bif;
+        } else {
+            const unsigned mb = __ballot_sync(0xFFFFFFFFu, bif);
+            if (mb) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(mb));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (bif) bif_keys[base + __popc(mb & ((1u << lane) - 1))] = key;
+            }
+        }
+    }
+    if (!FILL) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            n_used += __shfl_xor_sync(0xFFFFFFFFu, n_used, d);
+            n_bif += __shfl_xor_sync(0xFFFFFFFFu, n_bif, d);
+        }
+        if (lane == 0) su[threadIdx.x >> 5] = n_used, sb[threadIdx.x >> 5] = n_bif;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long a = 0, c = 0;
+            for (int w = 0; w < 8; w++) a += su[w], c += sb[w];
+            if (a) atomicAdd(&counters[0], a);
+            if (c) atomicAdd(&counters[1], c);
+        }
     }
 }
 
@@ -296,14 +318,100 @@ __global__ void __launch_bounds__(256) k_flag_write(const uint8_t *__restrict__ 
     for (unsigned mm = m; mm; mm &= mm - 1) out[w++] = base + (uint64_t)(__ffs((int)mm) - 1);
 }
 
-__global__ void k_emit_ids(Text t, Table tb, const uint64_t *__restrict__ pos, unsigned n, int32_t *__restrict__ id)
+constexpr int32_t kStub = INT32_MIN; // a first / last k-mer of a record that is not a junction: gets a unique id
+
+// first and last k-mer of every record that yields a task (vertexenumerator.h:913-920); bit 1 of the position's flag
+__global__ void k_mark_stubs(const uint64_t *__restrict__ goff, int n_records, int k, uint8_t *__restrict__ flag)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records) return;
+    const uint64_t len = goff[r + 1] - goff[r] - 1;
+    if (len < (uint64_t)k) return; // shorter records yield no task (vertexenumerator.h:1176)
+    flag[goff[r]] |= 2;
+    flag[goff[r] + len - (uint64_t)k] |= 2; // the same byte when len == k; no other thread touches these two
+}
+
+__global__ void k_emit_ids(Text t, Table tb, const uint8_t *__restrict__ flag, const uint64_t *__restrict__ pos, unsigned n,
+                           int32_t *__restrict__ id)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint64_t p = pos[i];
+    const unsigned f = flag[p];
+    int32_t out = 0;
     Kmer km;
-    load_kmer(t, pos[i], km); // flagged positions hold definite k-mers
-    const long long v = (long long)(tb.slot[find(tb, km.key)].info >> kIdShift);
-    id[i] = (int32_t)(km.fwd ? v : -v);
+    if ((f & 1u) && load_kmer(t, p, km)) {
+        const long long v = (long long)(tb.slot[find(tb, km.key)].info >> kIdShift);
+        out = (int32_t)(km.fwd ? v : -v);
+    }
+    if (out == 0 && (f & 2u)) out = kStub;
+    id[i] = out;
+}
+
+// ---- final list: entries with id != 0 in order, stubs numbered in order, position -> (record, offset) ----------------
+constexpr int kFinalTile = 2048; // 256 threads x 8 entries
+__global__ void __launch_bounds__(256) k_final_count(const int32_t *__restrict__ id, unsigned n, unsigned *__restrict__ kept, unsigned *__restrict__ stubs)
+{
+    __shared__ unsigned sk[8], ss[8];
+    const unsigned base = blockIdx.x * kFinalTile + threadIdx.x * 8;
+    unsigned ck = 0, cs = 0;
+    for (int j = 0; j < 8; j++)
+        if (base + j < n) {
+            const int32_t v = id[base + j];
+            ck += v != 0;
+            cs += v == kStub;
+        }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        ck += __shfl_xor_sync(0xFFFFFFFFu, ck, d);
+        cs += __shfl_xor_sync(0xFFFFFFFFu, cs, d);
+    }
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = ck, ss[threadIdx.x >> 5] = cs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned a = 0, b = 0;
+        for (int w = 0; w < 8; w++) a += sk[w], b += ss[w];
+        kept[blockIdx.x] = a;
+        stubs[blockIdx.x] = b;
+    }
+}
+__global__ void __launch_bounds__(256) k_final_write(const int32_t *__restrict__ id, const uint64_t *__restrict__ pos, unsigned n,
+                                                     const unsigned *__restrict__ kept_off, const unsigned *__restrict__ stub_off,
+                                                     const uint64_t *__restrict__ goff, int n_records, int32_t stub_base,
+                                                     uint32_t *__restrict__ out_chr, uint32_t *__restrict__ out_pos, int32_t *__restrict__ out_id)
+{
+    __shared__ unsigned sk[256], ss[256];
+    const unsigned base = blockIdx.x * kFinalTile + threadIdx.x * 8;
+    int32_t v[8];
+    unsigned ck = 0, cs = 0;
+    for (int j = 0; j < 8; j++) {
+        v[j] = base + j < n ? id[base + j] : 0;
+        ck += v[j] != 0;
+        cs += v[j] == kStub;
+    }
+    sk[threadIdx.x] = ck, ss[threadIdx.x] = cs;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        const unsigned a = threadIdx.x >= d ? sk[threadIdx.x - d] : 0, b = threadIdx.x >= d ? ss[threadIdx.x - d] : 0;
+        __syncthreads();
+        sk[threadIdx.x] += a, ss[threadIdx.x] += b;
+        __syncthreads();
+    }
+    unsigned w = kept_off[blockIdx.x] + sk[threadIdx.x] - ck, sn = stub_off[blockIdx.x] + ss[threadIdx.x] - cs;
+    for (int j = 0; j < 8; j++) {
+        if (v[j] == 0) continue;
+        const uint64_t p = pos[base + j];
+        int lo = 0, hi = n_records; // goff[lo] <= p < goff[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (goff[mid] <= p) lo = mid;
+            else hi = mid;
+        }
+        out_chr[w] = (uint32_t)lo;
+        out_pos[w] = (uint32_t)(p - goff[lo]);
+        out_id[w] = v[j] == kStub ? stub_base + (int32_t)sn++ : v[j];
+        w++;
+    }
 }
 
 // ---- host helpers ----------------------------------------------------------------------------------------------------
@@ -362,6 +470,13 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
     };
     const int k = in.k;
+    const bool trace = getenv("LCG_TRACE") != nullptr;
+    cudaStream_t trace_stream = nullptr;
+    auto lap = [&](const char *what) { // developer aid: synchronising stage timer
+        if (!trace) return;
+        if (trace_stream) cudaStreamSynchronize(trace_stream);
+        fprintf(stderr, "[graph] %-26s %9.2f ms\n", what, ms_since(t_begin));
+    };
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         err = "no CUDA device: this library has no CPU fallback";
@@ -379,6 +494,8 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     Scope sc;
     CU(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
     for (auto &e : sc.ev) CU(cudaEventCreate(&e));
+    trace_stream = sc.stream;
+    lap("context + stream");
     lcg_stats &st = out.st;
     st.n_records = (uint64_t)in.n_records;
     // ---- layout of G
@@ -422,6 +539,10 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     if ((rc = dalloc(sc, &d_slot, cap, err))) return rc;
     if ((rc = dalloc(sc, &d_ctr, 4, err))) return rc;
     if (finite_abundance && (rc = dalloc(sc, &d_cnt, cap, err))) return rc;
+    uint64_t *d_goff = nullptr;
+    if ((rc = dalloc(sc, &d_goff, goff.size(), err))) return rc;
+    CU(cudaMemcpyAsync(d_goff, goff.data(), goff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, sc.stream));
+    lap("allocations");
     // ---- sequences -> device (separators and padding stay 'N')
     const auto t_h2d = std::chrono::steady_clock::now();
     CU(cudaMemsetAsync(d_text, 'N', padded, sc.stream));
@@ -430,6 +551,7 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         if (in.len[r]) CU(cudaMemcpyAsync(d_text + goff[(size_t)r], in.seq[r], in.len[r], cudaMemcpyHostToDevice, sc.stream));
     CU(cudaStreamSynchronize(sc.stream));
     st.ms_h2d = ms_since(t_h2d);
+    lap("h2d");
     // ---- device pipeline
     CU(cudaEventRecord(sc.ev[0], sc.stream));
     k_table_init<<<(unsigned)((cap + 255) / 256), 256, 0, sc.stream>>>(d_slot, cap);
@@ -440,13 +562,19 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     const Text text{d_bits, d_nm, G, k};
     const Table tb{d_slot, cap - 1};
     const unsigned pos_blocks = (unsigned)((G + 255) / 256);
+    lap("init + pack");
     CU(cudaEventRecord(sc.ev[1], sc.stream));
     k_edges<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_ctr + 2);
     CU(cudaEventRecord(sc.ev[2], sc.stream));
+    lap("k_edges");
     k_candidates<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_flag, d_cnt);
-    const unsigned slot_blocks = (unsigned)((cap + 255) / 256);
+    if (in.n_records) k_mark_stubs<<<(in.n_records + 255) / 256, 256, 0, sc.stream>>>(d_goff, in.n_records, k, d_flag);
+    lap("k_candidates + stubs");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, in.device);
+    const unsigned slot_blocks = (unsigned)std::min<uint64_t>((cap + 255) / 256, (uint64_t)sms * 16);
     k_decide<false><<<slot_blocks, 256, 0, sc.stream>>>(tb, d_cnt, (unsigned long long)in.abundance, d_ctr, nullptr);
-    st.kernel_launches += 5;
+    st.kernel_launches += 6;
     unsigned long long h_ctr[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost, sc.stream));
     CU(cudaStreamSynchronize(sc.stream));
@@ -459,6 +587,7 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         return LCG_ERR_ARG;
     }
     const unsigned nb = (unsigned)h_ctr[1];
+    lap("k_decide (count)");
     // ---- ids: sort the bifurcation k-mers
     uint64_t *d_bif = nullptr, *d_sorted = nullptr;
     if ((rc = dalloc(sc, &d_bif, nb, err))) return rc;
@@ -486,6 +615,7 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         k_assign_ids<<<(nb + 255) / 256, 256, 0, sc.stream>>>(tb, d_sorted, nb);
         st.kernel_launches += 2;
     }
+    lap("collect + sort + ids");
     // ---- flagged positions in genome order
     const unsigned fblocks = (unsigned)((G + kFlagTile - 1) / kFlagTile);
     unsigned *d_bc = nullptr, *d_bo = nullptr, *d_tile = nullptr, *d_total = nullptr;
@@ -501,34 +631,91 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     CU(cudaStreamSynchronize(sc.stream));
     CU(cudaGetLastError());
     st.n_candidates = nc;
+    lap("flag count + scan");
     uint64_t *d_pos = nullptr;
     int32_t *d_id = nullptr;
     if ((rc = dalloc(sc, &d_pos, nc, err))) return rc;
     if ((rc = dalloc(sc, &d_id, nc, err))) return rc;
+    unsigned nj = 0, ns = 0;
+    uint32_t *d_jchr = nullptr, *d_jpos = nullptr;
+    int32_t *d_jid = nullptr;
     if (nc) {
         k_flag_write<<<fblocks, 256, 0, sc.stream>>>(d_flag, G, d_bo, d_pos);
-        k_emit_ids<<<(nc + 255) / 256, 256, 0, sc.stream>>>(text, tb, d_pos, nc, d_id);
-        st.kernel_launches += 2;
+        k_emit_ids<<<(nc + 255) / 256, 256, 0, sc.stream>>>(text, tb, d_flag, d_pos, nc, d_id);
+        const unsigned qblocks = (nc + kFinalTile - 1) / kFinalTile;
+        unsigned *d_kc = nullptr, *d_sc = nullptr, *d_ko = nullptr, *d_so = nullptr, *d_tile2 = nullptr, *d_tot2 = nullptr;
+        if ((rc = dalloc(sc, &d_kc, qblocks, err))) return rc;
+        if ((rc = dalloc(sc, &d_sc, qblocks, err))) return rc;
+        if ((rc = dalloc(sc, &d_ko, qblocks, err))) return rc;
+        if ((rc = dalloc(sc, &d_so, qblocks, err))) return rc;
+        if ((rc = dalloc(sc, &d_tile2, qblocks / kScanTile + 8, err))) return rc;
+        if ((rc = dalloc(sc, &d_tot2, 4, err))) return rc;
+        k_final_count<<<qblocks, 256, 0, sc.stream>>>(d_id, nc, d_kc, d_sc);
+        st.kernel_launches += 3;
+        if ((rc = exclusive_scan_u32(sc, d_kc, d_ko, qblocks, d_tot2, d_tile2, st.kernel_launches, err))) return rc;
+        if ((rc = exclusive_scan_u32(sc, d_sc, d_so, qblocks, d_tot2 + 1, d_tile2, st.kernel_launches, err))) return rc;
+        unsigned tot[2] = {0, 0};
+        CU(cudaMemcpyAsync(tot, d_tot2, sizeof tot, cudaMemcpyDeviceToHost, sc.stream));
+        CU(cudaStreamSynchronize(sc.stream));
+        CU(cudaGetLastError());
+        nj = tot[0], ns = tot[1];
+        if ((uint64_t)nb + 42 + ns >= 0x7FFFFFFFull) {
+            err = "vertex ids exceed 31 bits";
+            return LCG_ERR_ARG;
+        }
+        if ((rc = dalloc(sc, &d_jchr, nj, err))) return rc;
+        if ((rc = dalloc(sc, &d_jpos, nj, err))) return rc;
+        if ((rc = dalloc(sc, &d_jid, nj, err))) return rc;
+        if (nj) {
+            k_final_write<<<qblocks, 256, 0, sc.stream>>>(d_id, d_pos, nc, d_ko, d_so, d_goff, in.n_records, (int32_t)(nb + 42), d_jchr, d_jpos, d_jid);
+            st.kernel_launches += 1;
+        }
     }
     CU(cudaEventRecord(sc.ev[3], sc.stream));
     CU(cudaStreamSynchronize(sc.stream));
     CU(cudaGetLastError());
+    lap("emit + final list");
     float ms = 0;
     cudaEventElapsedTime(&ms, sc.ev[0], sc.ev[3]);
     st.ms_device = ms;
     cudaEventElapsedTime(&ms, sc.ev[1], sc.ev[2]);
     st.ms_edges = ms;
+    st.n_junctions = nj;
     // ---- results
     const auto t_d2h = std::chrono::steady_clock::now();
-    out.pos.resize(nc);
-    out.id.resize(nc);
-    if (nc) {
-        CU(cudaMemcpy(out.pos.data(), d_pos, (size_t)nc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(out.id.data(), d_id, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    out.n = nj; // plain arrays: a std::vector would zero-fill 180 MB on 4x100 Mbp before the copy overwrites it
+    out.chr.reset(new uint32_t[std::max<size_t>(nj, 1)]);
+    out.pos.reset(new uint32_t[std::max<size_t>(nj, 1)]);
+    out.id.reset(new int32_t[std::max<size_t>(nj, 1)]);
+    if (nj) {
+        CU(cudaMemcpyAsync(out.chr.get(), d_jchr, (size_t)nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc.stream));
+        CU(cudaMemcpyAsync(out.pos.get(), d_jpos, (size_t)nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc.stream));
+        CU(cudaMemcpyAsync(out.id.get(), d_jid, (size_t)nj * sizeof(int32_t), cudaMemcpyDeviceToHost, sc.stream));
+        CU(cudaStreamSynchronize(sc.stream));
     }
     st.ms_d2h = ms_since(t_d2h);
+    lap("d2h");
+    if (in.keep_on_device) { // ownership of these blocks moves to the caller
+        Resident &r = out.resident;
+        r.device = in.device, r.k = k, r.n_records = in.n_records;
+        r.d_text = d_text, r.d_goff = d_goff, r.d_chr = d_jchr, r.d_pos = d_jpos, r.d_id = d_jid;
+        r.n_junctions = nj;
+        r.n_vertices = (ns ? (uint64_t)nb + 42 + ns - 1 : (uint64_t)nb) + 1;
+        r.last_chr = nj ? out.chr[nj - 1] : 0;
+        for (void *keep : {(void *)d_text, (void *)d_goff, (void *)d_jchr, (void *)d_jpos, (void *)d_jid})
+            sc.dev.erase(std::remove(sc.dev.begin(), sc.dev.end(), keep), sc.dev.end());
+    }
     st.ms_total = ms_since(t_begin);
     return LCG_OK;
+}
+
+void free_resident(Resident &r)
+{
+    if (!r.d_text && !r.d_goff && !r.d_chr) return;
+    cudaSetDevice(r.device);
+    for (void *p : {(void *)r.d_text, (void *)r.d_goff, (void *)r.d_chr, (void *)r.d_pos, (void *)r.d_id})
+        if (p) cudaFree(p);
+    r = Resident();
 }
 
 } // namespace lcg

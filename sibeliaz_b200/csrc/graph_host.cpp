@@ -1,8 +1,7 @@
 // graph_host.cpp -- host front end of the junction finder (include/sibeliaz_graph.h): FASTA parsing on the host threads,
-// the device pipeline (graph_device.cu), and the assembly of the junction records the reference's EdgeConstructionWorker
-// writes (TwoPaCo/src/graphconstructor/vertexenumerator.h:856-993): junctions of every record in genome order, a unique
-// "stub" id for the first and the last k-mer of a record when they are not junctions (:913-920), chromosome separators
-// in the file (TwoPaCo/src/common/junctionapi.h:117-131).  Host-only C++ (no CUDA here).
+// the device pipeline (graph_device.cu, which returns the finished junction records: what the reference's
+// EdgeConstructionWorker writes, TwoPaCo/src/graphconstructor/vertexenumerator.h:856-993), and the junction file with its
+// chromosome separators (TwoPaCo/src/common/junctionapi.h:117-131).  Host-only C++ (no CUDA here).
 #include "sibeliaz_graph.h"
 
 #include <chrono>
@@ -11,10 +10,15 @@
 #include "host_common.h"
 
 struct lcg_graph {
-    std::vector<uint32_t> chr, pos;
-    std::vector<int64_t> id;
+    uint64_t n = 0;
+    std::unique_ptr<uint32_t[]> chr, pos;
+    std::unique_ptr<int32_t[]> id; // 31 bits suffice (checked on the device side); widened at the ABI / in the file
     lcg_stats st{};
+    lcg::Resident resident;
+    ~lcg_graph() { lcg::free_resident(resident); }
 };
+
+const lcg::Resident *lcg::resident_of(const lcg_graph *g) { return g && g->resident.d_text ? &g->resident : nullptr; }
 
 namespace {
 
@@ -23,7 +27,7 @@ void SetErr(char *err, size_t errlen, const std::string &m)
     if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
 }
 
-int Build(const uint8_t *const *seq, const uint64_t *len, int n, int k, uint64_t abundance, int device, double ms_parse,
+int Build(const uint8_t *const *seq, const uint64_t *len, int n, int k, uint64_t abundance, int device, double ms_parse, bool keep,
           lcg_graph **out, char *err, size_t errlen)
 {
     if (k < 1 || k > 31 || k % 2 == 0) {
@@ -36,7 +40,7 @@ int Build(const uint8_t *const *seq, const uint64_t *len, int n, int k, uint64_t
             return LCG_ERR_ARG;
         }
     const auto t0 = std::chrono::steady_clock::now();
-    lcg::DeviceInput in{seq, len, n, k, abundance, device};
+    lcg::DeviceInput in{seq, len, n, k, abundance, device, keep};
     lcg::DeviceOutput dev;
     std::string e;
     const int rc = lcg::run_device(in, dev, e);
@@ -44,42 +48,16 @@ int Build(const uint8_t *const *seq, const uint64_t *len, int n, int k, uint64_t
         SetErr(err, errlen, e);
         return rc;
     }
-    // ---- junction records: candidates whose k-mer is a bifurcation, plus the stubs
     lcg_graph *g = new lcg_graph;
     g->st = dev.st;
     g->st.ms_parse = ms_parse;
-    const size_t nc = dev.pos.size();
-    g->chr.reserve(nc + 2 * (size_t)n);
-    g->pos.reserve(nc + 2 * (size_t)n);
-    g->id.reserve(nc + 2 * (size_t)n);
-    int64_t stub = (int64_t)dev.st.n_bifurcations + 42; // vertexenumerator.h:393
-    size_t i = 0;
-    uint64_t goff = 1; // record r starts at G[goff]
-    auto put = [g](uint32_t c, uint32_t p, int64_t id) {
-        g->chr.push_back(c);
-        g->pos.push_back(p);
-        g->id.push_back(id);
-    };
-    for (int r = 0; r < n; r++) {
-        const uint64_t L = len[r], end = goff + L;
-        if (L >= (uint64_t)k) { // shorter records yield no task (vertexenumerator.h:1176)
-            while (i < nc && dev.pos[i] < goff) ++i; // (nothing lives on separators)
-            const uint64_t first = goff, last = goff + L - (uint64_t)k;
-            size_t a = i;
-            bool has_first = false, has_last = false;
-            for (size_t j = a; j < nc && dev.pos[j] < end; j++)
-                if (dev.id[j]) {
-                    has_first = has_first || dev.pos[j] == first;
-                    has_last = has_last || dev.pos[j] == last;
-                }
-            if (!has_first) put((uint32_t)r, 0, stub++);
-            for (; i < nc && dev.pos[i] < end; i++)
-                if (dev.id[i]) put((uint32_t)r, (uint32_t)(dev.pos[i] - goff), (int64_t)dev.id[i]);
-            if (!has_last && last != first) put((uint32_t)r, (uint32_t)(L - (uint64_t)k), stub++);
-        }
-        goff = end + 1;
-    }
-    g->st.n_junctions = g->id.size();
+    g->n = dev.n;
+    g->chr = std::move(dev.chr);
+    g->pos = std::move(dev.pos);
+    g->id = std::move(dev.id);
+    g->st.n_junctions = g->n;
+    g->resident = dev.resident;
+    dev.resident = lcg::Resident();
     g->st.ms_total = ms_parse + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = g;
     return LCG_OK;
@@ -91,7 +69,14 @@ extern "C" int lcg_build(const uint8_t *const *seq, const uint64_t *len, int n_r
                          lcg_graph **out, char *err, size_t errlen)
 {
     if (!out || n_records < 0 || (n_records && (!seq || !len))) return LCG_ERR_ARG;
-    return Build(seq, len, n_records, k, abundance, device, 0.0, out, err, errlen);
+    return Build(seq, len, n_records, k, abundance, device, 0.0, false, out, err, errlen);
+}
+
+extern "C" int lcg_build_resident(const uint8_t *const *seq, const uint64_t *len, int n_records, int k, uint64_t abundance, int device,
+                                  lcg_graph **out, char *err, size_t errlen)
+{
+    if (!out || n_records < 0 || (n_records && (!seq || !len))) return LCG_ERR_ARG;
+    return Build(seq, len, n_records, k, abundance, device, 0.0, true, out, err, errlen);
 }
 
 extern "C" int lcg_build_from_fasta(const char *const *fasta_files, int n_files, int k, uint64_t abundance, int device,
@@ -132,18 +117,19 @@ extern "C" int lcg_build_from_fasta(const char *const *fasta_files, int n_files,
             len.push_back(s.size());
         }
     const double ms_parse = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    return Build(seq.data(), len.data(), (int)seq.size(), k, abundance, device, ms_parse, out, err, errlen);
+    return Build(seq.data(), len.data(), (int)seq.size(), k, abundance, device, ms_parse, false, out, err, errlen);
 }
 
-extern "C" uint64_t lcg_num_junctions(const lcg_graph *g) { return g ? g->id.size() : 0; }
+extern "C" uint64_t lcg_num_junctions(const lcg_graph *g) { return g ? g->n : 0; }
 
 extern "C" int lcg_get_junctions(const lcg_graph *g, uint32_t *chr, uint32_t *pos, int64_t *id)
 {
     if (!g) return LCG_ERR_ARG;
-    const size_t n = g->id.size();
-    if (chr) memcpy(chr, g->chr.data(), n * sizeof(uint32_t));
-    if (pos) memcpy(pos, g->pos.data(), n * sizeof(uint32_t));
-    if (id) memcpy(id, g->id.data(), n * sizeof(int64_t));
+    const size_t n = (size_t)g->n;
+    if (chr) memcpy(chr, g->chr.get(), n * sizeof(uint32_t));
+    if (pos) memcpy(pos, g->pos.get(), n * sizeof(uint32_t));
+    if (id)
+        for (size_t i = 0; i < n; i++) id[i] = g->id[i];
     return LCG_OK;
 }
 
@@ -152,15 +138,15 @@ extern "C" int lcg_write_junction_file(const lcg_graph *g, const char *path, cha
     if (!g || !path) return LCG_ERR_ARG;
     // 12-byte records {u32 pos; i64 id}; {0xFFFFFFFF, INT64_MAX} once per chromosome change (junctionapi.h:117-131)
     std::string buf;
-    buf.reserve(g->id.size() * 12 + 1024);
+    buf.reserve((size_t)g->n * 12 + 1024);
     uint32_t now = 0;
     auto rec = [&buf](uint32_t pos, int64_t id) {
         buf.append((const char *)&pos, 4);
         buf.append((const char *)&id, 8);
     };
-    for (size_t i = 0; i < g->id.size(); i++) {
+    for (size_t i = 0; i < (size_t)g->n; i++) {
         for (; g->chr[i] > now; ++now) rec(0xFFFFFFFFu, INT64_MAX);
-        rec(g->pos[i], g->id[i]);
+        rec(g->pos[i], (int64_t)g->id[i]);
     }
     FILE *f = fopen(path, "wb");
     if (!f) {

@@ -37,6 +37,8 @@
 #include <vector>
 
 #include "lcb_traverse.cuh"
+#include "graph_internal.h"
+#include "lcb_internal.h"
 
 #ifdef LCB_WITH_NCCL
 #include <dlfcn.h>
@@ -570,6 +572,80 @@ __global__ void k_seed_enum(Index ix, unsigned *__restrict__ per_vertex, const u
 
 #include "device_prims.cuh" // scan, stable LSD radix sort, gather, iota (shared with graph_device.cu)
 
+// ------------------------------------------------------------------------------------------------
+// fused pipeline: JunctionStorage::Init (junctionstorage.h:572-650) on the device, from the junction records a
+// resident graph (graph_device.cu) left there.  Same arrays as the host loader builds (lcb_host.cpp), same order.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_u32(unsigned *p, size_t n, unsigned v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_ix_count(const int32_t *__restrict__ id, unsigned n, unsigned *__restrict__ cnt)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) atomicAdd(&cnt[id[j] < 0 ? -id[j] : id[j]], 1u);
+}
+// abundance filter, strict < (junctionstorage.h:610)
+__global__ void k_ix_keep(const int32_t *__restrict__ id, unsigned n, const unsigned *__restrict__ cnt, unsigned a, unsigned *__restrict__ keep)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) keep[j] = cnt[id[j] < 0 ? -id[j] : id[j]] < a ? 1u : 0u;
+}
+__global__ void k_ix_vsize(const unsigned *__restrict__ cnt, unsigned V, unsigned a, unsigned *__restrict__ sz) // sz[V], sz[V+1] = 0
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < V + 2) sz[v] = (v < V && cnt[v] < a) ? cnt[v] : 0u;
+}
+__global__ void k_ix_compact(const int32_t *__restrict__ id, const uint32_t *__restrict__ chr, const uint32_t *__restrict__ pos,
+                             const unsigned *__restrict__ keep, const unsigned *__restrict__ gidx, unsigned n, int32_t *__restrict__ kid,
+                             uint32_t *__restrict__ kbp, uint32_t *__restrict__ kchr, unsigned *__restrict__ key)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || !keep[j]) return;
+    const unsigned g = gidx[j];
+    kid[g] = id[j], kbp[g] = pos[j], kchr[g] = chr[j];
+    key[g] = (unsigned)(id[j] < 0 ? -id[j] : id[j]);
+}
+// rec[g]: id, position, occurrence list of |id|, and the two characters the traversal needs (junctionstorage.h:641-642)
+__global__ void k_ix_rec(const int32_t *__restrict__ kid, const uint32_t *__restrict__ kbp, const uint32_t *__restrict__ kchr, unsigned N,
+                         const uint32_t *__restrict__ vtx_off, const unsigned *__restrict__ cnt, const uint8_t *__restrict__ text,
+                         const uint64_t *__restrict__ goff, int k, int4 *__restrict__ rec, unsigned *__restrict__ too_many)
+{
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const int id = kid[g];
+    const unsigned a = (unsigned)(id < 0 ? -id : id), c = cnt[a];
+    if (c > 65535u) *too_many = 1u;
+    const uint64_t start = goff[kchr[g]], len = goff[kchr[g] + 1] - start - 1;
+    const uint64_t p = kbp[g];
+    auto upper = [](unsigned ch) { return (ch >= 'a' && ch <= 'z') ? ch - 32u : ch; };
+    const unsigned next = p + (uint64_t)k < len ? upper(text[start + p + (uint64_t)k]) : 0u;
+    unsigned prev = 'N';
+    if (p > 0) {
+        const unsigned ch = upper(text[start + p - 1]);
+        prev = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N';
+    }
+    rec[g] = make_int4(id, (int)kbp[g], (int)vtx_off[a], (int)((c << 16) | (next << 8) | prev));
+}
+__global__ void k_ix_occ(const unsigned *__restrict__ perm, const int32_t *__restrict__ kid, const uint32_t *__restrict__ kbp, unsigned N,
+                         int2 *__restrict__ occ)
+{
+    const unsigned o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= N) return;
+    const unsigned g = perm[o];
+    occ[o] = make_int2((int)(g | (kid[g] < 0 ? 0x80000000u : 0u)), (int)kbp[g]);
+}
+// chr_off[c] = first g of chromosome c (pre-filled with N: chromosomes without records own an empty range)
+__global__ void k_ix_chroff(const uint32_t *__restrict__ kchr, unsigned N, uint32_t *__restrict__ chr_off)
+{
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const unsigned c1 = kchr[g];
+    const unsigned c0 = g ? kchr[g - 1] + 1 : 0u;
+    for (unsigned c = c0; c <= c1; c++) chr_off[c] = g;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -823,11 +899,20 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     delete ctx;
 }
 
-extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb_ctx **out)
+namespace {
+
+struct CreateTrace { // LCB_LOAD_TRACE=1: stage timer of lcb_create*
+    bool on = getenv("LCB_LOAD_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void operator()(const char *what) const
+    {
+        if (on) fprintf(stderr, "[create] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
+// parameters, device, stream, events
+int create_begin(lcb_ctx *ctx, const lcb_params *params, const CreateTrace &lap)
 {
-    if (!v || !params || !out) return LCB_ERR_ARG;
-    lcb_ctx *ctx = new lcb_ctx;
-    *out = ctx; // returned even on failure so that lcb_last_error works; caller destroys it
     ctx->prm = *params;
     lcb_params &p = ctx->prm;
     if (p.phase_size <= 0) p.phase_size = 256;
@@ -837,10 +922,6 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     p.window_max = std::min(p.window_max, 1 << 20);
     p.window_max = std::max(p.phase_size, p.window_max / p.phase_size * p.phase_size);
     p.window_init = std::max(p.phase_size, std::min(p.window_init, p.window_max) / p.phase_size * p.phase_size);
-    if (v->n_records < 0 || v->n_records >= (int64_t)0x7FFFFFF0 || v->n_vertices >= (int64_t)0x3FFFFFF0 || v->n_chr < 0) {
-        ctx->error = "index too large for 32-bit device indices";
-        return LCB_ERR_ARG;
-    }
     if (p.k <= 0 || p.max_branch < 0 || p.min_block < 0) {
         ctx->error = "bad parameters";
         return LCB_ERR_ARG;
@@ -851,11 +932,6 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
         return LCB_ERR_CUDA;
     }
     ctx->device = p.device;
-    const bool trace = getenv("LCB_LOAD_TRACE") != nullptr;
-    auto t_create = std::chrono::steady_clock::now();
-    auto lap = [&](const char *what) {
-        if (trace) fprintf(stderr, "[create] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create).count());
-    };
     CUDA_TRY(cudaSetDevice(ctx->device));
     {
         // cudaGetDeviceProperties costs milliseconds per call: query the three attributes that matter instead
@@ -874,9 +950,83 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(cudaEventCreate(&ctx->ev_step0));
     CUDA_TRY(cudaEventCreate(&ctx->ev_step1));
+    lap("stream + events");
+    return LCB_OK;
+}
+
+// window state, pools, arena: everything that does not depend on where the index came from
+int create_end(lcb_ctx *ctx, const CreateTrace &lap)
+{
+    lcb_params &p = ctx->prm;
+    const int64_t N = ctx->ix.N;
+    // ---- window state, pools, arena ----
+    int rc;
+    unsigned W = 256; // ring of per-seed state: a power of two >= the largest active set
+    while (W < (unsigned)p.window_max) W <<= 1;
+    ctx->wmax = W;
+    ctx->win.mask = W - 1;
+    for (int s = 0; s < 2; s++) {
+        if ((rc = dev_alloc(ctx, &ctx->win.res_off[s], W))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->win.res_cnt[s], W))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->win.rs_off[s], W))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->win.rs_cnt[s], W))) return rc;
+    }
+    if ((rc = dev_alloc(ctx, &ctx->win.conf, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.has1, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.blk, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.out_off, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.list0, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_wnext, 8))) return rc;
+    ctx->win.inst_cap = kInstPoolCap;
+    ctx->win.rs_cap = kRsPoolCap;
+    if (const char *e = getenv("LCB_TEST_POOL_ENTRIES")) { // testing aid: tiny result pools force the window-halving retry
+        unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= 1024) ctx->win.inst_cap = std::min(ctx->win.inst_cap, v), ctx->win.rs_cap = std::min(ctx->win.rs_cap, v);
+    }
+    lap("ring arrays");
+    if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.rs_pool, (size_t)ctx->win.rs_cap))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_ctl, 1))) return rc;
+    CUDA_TRY(cached_alloc((void **)&ctx->h_ctl, sizeof(Control), -1, nullptr));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
+    lap("pools + control");
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    ctx->grid_traverse = per_sm * ctx->sms;
+    lap("occupancy query");
+    ctx->arena_stride = arena_stride_bytes();
+    size_t arena_bytes = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock;
+    bool arena_cached = false;
+    if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes, &arena_cached))) return rc;
+    if (!arena_cached) CUDA_TRY(cudaMemsetAsync(ctx->d_arena, 0, arena_bytes, ctx->stream)); // the spill hash must start all-empty
+    if ((rc = dev_alloc(ctx, &ctx->d_out, (size_t)N + 1))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    lap("window state + arena");
+    return LCB_OK;
+}
+
+} // namespace
+
+extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb_ctx **out)
+{
+    if (!v || !params || !out) return LCB_ERR_ARG;
+    lcb_ctx *ctx = new lcb_ctx;
+    *out = ctx; // returned even on failure so that lcb_last_error works; caller destroys it
+    if (v->n_records < 0 || v->n_records >= (int64_t)0x7FFFFFF0 || v->n_vertices >= (int64_t)0x3FFFFFF0 || v->n_chr < 0) {
+        ctx->error = "index too large for 32-bit device indices";
+        return LCB_ERR_ARG;
+    }
+    CreateTrace lap;
+    {
+        const int rc0 = create_begin(ctx, params, lap);
+        if (rc0) return rc0;
+    }
+    lcb_params &p = ctx->prm;
+    (void)p;
     const int64_t N = v->n_records, V = v->n_vertices;
     const int C = v->n_chr;
-    lap("stream + events");
     auto t0 = std::chrono::steady_clock::now();
     // ---- pack + upload the index (8 B + 2 B per record, u32 CSR) ----
     if (v->packed_rec && v->packed_occ) {
@@ -970,52 +1120,131 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     ctx->ix.V = (int)V;
     ctx->st.n_records = (uint64_t)N;
     ctx->st.n_vertices = (uint64_t)V;
-    // ---- window state, pools, arena ----
-    int rc;
-    unsigned W = 256; // ring of per-seed state: a power of two >= the largest active set
-    while (W < (unsigned)p.window_max) W <<= 1;
-    ctx->wmax = W;
-    ctx->win.mask = W - 1;
-    for (int s = 0; s < 2; s++) {
-        if ((rc = dev_alloc(ctx, &ctx->win.res_off[s], W))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->win.res_cnt[s], W))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->win.rs_off[s], W))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->win.rs_cnt[s], W))) return rc;
+    return create_end(ctx, lap);
+}
+
+extern "C" int lcb_create_from_graph(const lcg_graph *graph, lcb_index *index, int abundance, const lcb_params *params, lcb_ctx **out)
+{
+    if (!graph || !index || !params || !out || abundance < 0) return LCB_ERR_ARG;
+    lcb_ctx *ctx = new lcb_ctx;
+    *out = ctx;
+    const lcg::Resident *res = lcg::resident_of(graph);
+    if (!res) {
+        ctx->error = "the graph holds no device-resident data (build it with lcg_build_resident)";
+        return LCB_ERR_STATE;
     }
-    if ((rc = dev_alloc(ctx, &ctx->win.conf, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->win.has1, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->win.blk, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->win.out_off, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->win.list0, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_wnext, 8))) return rc;
-    ctx->win.inst_cap = kInstPoolCap;
-    ctx->win.rs_cap = kRsPoolCap;
-    if (const char *e = getenv("LCB_TEST_POOL_ENTRIES")) { // testing aid: tiny result pools force the window-halving retry
-        unsigned long long v = strtoull(e, nullptr, 10);
-        if (v >= 1024) ctx->win.inst_cap = std::min(ctx->win.inst_cap, v), ctx->win.rs_cap = std::min(ctx->win.rs_cap, v);
+    if (res->n_junctions >= 0x7FFFFFF0ull || res->n_vertices >= 0x3FFFFFF0ull) {
+        ctx->error = "index too large for 32-bit device indices";
+        return LCB_ERR_ARG;
     }
-    lap("ring arrays");
-    if ((rc = dev_alloc(ctx, &ctx->win.inst_pool, (size_t)ctx->win.inst_cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->win.rs_pool, (size_t)ctx->win.rs_cap))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_ctl, 1))) return rc;
-    CUDA_TRY(cached_alloc((void **)&ctx->h_ctl, sizeof(Control), -1, nullptr));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
-    lap("pools + control");
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0));
-    if (per_sm < 1) per_sm = 1;
-    ctx->grid_traverse = per_sm * ctx->sms;
-    lap("occupancy query");
-    ctx->arena_stride = arena_stride_bytes();
-    size_t arena_bytes = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock;
-    bool arena_cached = false;
-    if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes, &arena_cached))) return rc;
-    if (!arena_cached) CUDA_TRY(cudaMemsetAsync(ctx->d_arena, 0, arena_bytes, ctx->stream)); // the spill hash must start all-empty
-    if ((rc = dev_alloc(ctx, &ctx->d_out, (size_t)N + 1))) return rc;
+    if (params->device != res->device || params->k != res->k) {
+        ctx->error = "the graph was built on another device or with another k";
+        return LCB_ERR_ARG;
+    }
+    CreateTrace lap;
+    int rc = create_begin(ctx, params, lap);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    const unsigned nj = (unsigned)res->n_junctions, V = (unsigned)res->n_vertices;
+    const int C = nj ? (int)res->last_chr + 1 : 0;
+    {
+        std::string e;
+        if ((rc = lcb_index_set_chromosomes(index, C, res->k, e))) {
+            ctx->error = e;
+            return rc;
+        }
+    }
+    // temporaries of this function go back to the block cache on every exit path
+    struct Temps {
+        lcb_ctx *c;
+        std::vector<std::pair<void *, size_t>> v;
+        ~Temps()
+        {
+            cudaStreamSynchronize(c->stream);
+            for (auto &b : v) cached_free(b.first, b.second, c->device);
+        }
+    } temps{ctx, {}};
+    auto talloc = [&](auto **p, size_t n) -> int {
+        void *q = nullptr;
+        const size_t bytes = std::max<size_t>(n, 1) * sizeof(**p);
+        CUDA_TRY(cached_alloc(&q, bytes, ctx->device, nullptr));
+        temps.v.emplace_back(q, bytes);
+        *p = (std::remove_reference_t<decltype(**p)> *)q;
+        return LCB_OK;
+    };
+    unsigned *d_cnt = nullptr, *d_keep = nullptr, *d_gidx = nullptr, *d_tile = nullptr, *d_small = nullptr, *d_sz = nullptr;
+    if ((rc = talloc(&d_cnt, (size_t)V + 2))) return rc;
+    if ((rc = talloc(&d_keep, nj))) return rc;
+    if ((rc = talloc(&d_gidx, nj))) return rc;
+    if ((rc = talloc(&d_tile, std::max<size_t>(nj, (size_t)V + 2) / kScanTile + 8))) return rc;
+    if ((rc = talloc(&d_small, 8))) return rc;
+    if ((rc = talloc(&d_sz, (size_t)V + 2))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, ((size_t)V + 2) * sizeof(unsigned), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_small, 0, 8 * sizeof(unsigned), ctx->stream));
+    const unsigned jb = (nj + 255) / 256, vb = (V + 2 + 255) / 256;
+    unsigned N = 0;
+    if (nj) {
+        k_ix_count<<<jb, 256, 0, ctx->stream>>>(res->d_id, nj, d_cnt);
+        k_ix_keep<<<jb, 256, 0, ctx->stream>>>(res->d_id, nj, d_cnt, (unsigned)abundance, d_keep);
+        if ((rc = exclusive_scan(ctx, d_keep, d_gidx, nj, d_small, d_tile))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(&N, d_small, sizeof N, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    k_ix_vsize<<<vb, 256, 0, ctx->stream>>>(d_cnt, V, (unsigned)abundance, d_sz);
+    if ((rc = exclusive_scan(ctx, d_sz, ctx->d_vtx_off, (size_t)V + 2, d_small + 1, d_tile))) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    lap("window state + arena");
-    return LCB_OK;
+    CUDA_TRY(cudaGetLastError());
+    lap("count + filter");
+    int32_t *d_kid = nullptr;
+    uint32_t *d_kbp = nullptr, *d_kchr = nullptr;
+    unsigned *d_key = nullptr, *d_perm = nullptr, *d_tmp = nullptr, *d_hist = nullptr;
+    if ((rc = talloc(&d_kid, N))) return rc;
+    if ((rc = talloc(&d_kbp, N))) return rc;
+    if ((rc = talloc(&d_kchr, N))) return rc;
+    if ((rc = talloc(&d_key, N))) return rc;
+    if ((rc = talloc(&d_perm, N))) return rc;
+    if ((rc = talloc(&d_tmp, N))) return rc;
+    const unsigned sblocks = (N + kSortTile - 1) / kSortTile;
+    if ((rc = talloc(&d_hist, (size_t)256 * sblocks + ((size_t)256 * sblocks) / kScanTile + 8))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_rec, (size_t)N))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_occ, (size_t)N))) return rc;
+    for (int e = 0; e < 2; e++)
+        if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
+    k_fill_u32<<<(unsigned)((C + 1 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_chr_off, (size_t)C + 1, N);
+    if (N) {
+        const unsigned nbk = (N + 255) / 256;
+        k_ix_compact<<<jb, 256, 0, ctx->stream>>>(res->d_id, res->d_chr, res->d_pos, d_keep, d_gidx, nj, d_kid, d_kbp, d_kchr, d_key);
+        k_ix_rec<<<nbk, 256, 0, ctx->stream>>>(d_kid, d_kbp, d_kchr, N, ctx->d_vtx_off, d_cnt, res->d_text, res->d_goff, res->k, ctx->d_rec, d_small + 2);
+        k_ix_chroff<<<nbk, 256, 0, ctx->stream>>>(d_kchr, N, ctx->d_chr_off);
+        // occurrence lists: stable sort of g by |id| leaves every list in (chr, idx) order (junctionstorage.h:646-649)
+        k_iota<<<nbk, 256, 0, ctx->stream>>>(d_perm, N);
+        int bits = 8;
+        while (bits < 32 && (V >> bits)) bits += 8;
+        if ((rc = radix_sort_word<unsigned>(ctx, &d_perm, &d_tmp, d_key, bits, false, N, d_hist, d_small + 4))) return rc;
+        k_ix_occ<<<nbk, 256, 0, ctx->stream>>>(d_perm, d_kid, d_kbp, N, ctx->d_occ);
+    }
+    unsigned flags[8] = {0};
+    CUDA_TRY(cudaMemcpyAsync(flags, d_small, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    if (flags[2]) {
+        ctx->error = "a junction occurs more than 65535 times: lower the abundance threshold (-a)";
+        return LCB_ERR_ARG;
+    }
+    lap("device index build");
+    ctx->st.ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->st.h2d_bytes = 0;
+    ctx->ix.rec = ctx->d_rec;
+    ctx->ix.vtx_off = ctx->d_vtx_off;
+    ctx->ix.occ = ctx->d_occ;
+    ctx->ix.chr_off = ctx->d_chr_off;
+    ctx->ix.C = C;
+    ctx->ix.N = (int)N;
+    ctx->ix.V = (int)V;
+    ctx->st.n_records = N;
+    ctx->st.n_vertices = V;
+    return create_end(ctx, lap);
 }
 
 extern "C" int lcb_comm_unique_id(void *id_bytes)

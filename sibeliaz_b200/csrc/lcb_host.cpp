@@ -8,6 +8,7 @@
 #include "sibeliaz_lcb.h"
 
 #include "host_common.h"
+#include "lcb_internal.h"
 
 #include <algorithm>
 #include <chrono>
@@ -33,6 +34,8 @@ struct lcb_index {
     std::vector<uint32_t> pos_bp;
     std::vector<uint8_t> next_ch, prev_rc;
     std::vector<int32_t> packed_rec, packed_occ; // 4 / 2 words per record (lcb_index_pack)
+    std::vector<const uint8_t *> seq_ptr;        // lcb_index_get_sequences
+    std::vector<uint64_t> seq_len;
     FastaRecords fasta;
     std::string error;
 };
@@ -241,6 +244,78 @@ extern "C" int lcb_index_load(const char *graph_file, const char *const *fasta_f
         return LCB_ERR_IO;
     }
     *out = ix;
+    return LCB_OK;
+}
+
+extern "C" int lcb_index_load_fasta(const char *const *fasta_files, int n_fasta, int k, lcb_index **out, char *err, size_t errlen)
+{
+    if (!out || n_fasta < 0 || (n_fasta && !fasta_files) || k <= 0) return LCB_ERR_ARG;
+    lcb_index *ix = new lcb_index;
+    ix->k = k;
+    std::vector<FastaRecords> per_file((size_t)n_fasta);
+    std::vector<std::string> ferr((size_t)n_fasta);
+    std::vector<int> fcode((size_t)n_fasta, LCB_OK);
+    {
+        const unsigned T = WorkerCount(), per = std::max(1u, T / (unsigned)std::max(1, n_fasta));
+        std::vector<std::thread> pool;
+        for (int i = 0; i < n_fasta; i++)
+            pool.emplace_back([&, i]() {
+                try {
+                    ParseFastaParallel(fasta_files[i], per_file[(size_t)i], per);
+                } catch (Failure &e) {
+                    fcode[(size_t)i] = e.code;
+                    ferr[(size_t)i] = e.what();
+                } catch (std::exception &e) {
+                    fcode[(size_t)i] = LCB_ERR_IO;
+                    ferr[(size_t)i] = e.what();
+                }
+            });
+        for (auto &t : pool) t.join();
+    }
+    for (int i = 0; i < n_fasta; i++)
+        if (fcode[(size_t)i] != LCB_OK) {
+            if (err && errlen) snprintf(err, errlen, "%s", ferr[(size_t)i].c_str());
+            const int code = fcode[(size_t)i];
+            delete ix;
+            return code;
+        }
+    for (auto &pf : per_file)
+        for (size_t r = 0; r < pf.seq.size(); r++) {
+            ix->fasta.name.push_back(std::move(pf.name[r]));
+            ix->fasta.seq.push_back(std::move(pf.seq[r]));
+        }
+    ix->chr_off.assign(1, 0);
+    ix->vtx_off.assign(1, 0);
+    *out = ix;
+    return LCB_OK;
+}
+
+extern "C" int32_t lcb_index_get_sequences(const lcb_index *cix, const uint8_t *const **seq, const uint64_t **len)
+{
+    if (!cix) return 0;
+    lcb_index *ix = const_cast<lcb_index *>(cix); // lazily built accessor arrays
+    if (ix->seq_ptr.size() != ix->fasta.seq.size()) {
+        ix->seq_ptr.clear();
+        ix->seq_len.clear();
+        for (const std::string &s : ix->fasta.seq) {
+            ix->seq_ptr.push_back((const uint8_t *)s.data());
+            ix->seq_len.push_back(s.size());
+        }
+    }
+    if (seq) *seq = ix->seq_ptr.data();
+    if (len) *len = ix->seq_len.data();
+    return (int32_t)ix->fasta.seq.size();
+}
+
+int lcb_index_set_chromosomes(lcb_index *ix, int32_t n_chr, int k, std::string &err)
+{
+    if (!ix || n_chr < 0) return LCB_ERR_ARG;
+    if ((size_t)n_chr > ix->fasta.seq.size()) {
+        err = "the graph refers to more sequences than the FASTA files contain";
+        return LCB_ERR_FORMAT;
+    }
+    ix->C = n_chr;
+    ix->k = k;
     return LCB_OK;
 }
 

@@ -1,6 +1,8 @@
 // sibeliaz-lcb (B200): drop-in for the reference binary invoked at SibeliaZ-LCB/sibeliaz:146.
 // Same flags, defaults, stdout lines and exit codes as SibeliaZ-LCB/sibeliaz.cpp:37-157; the work is done
-// by libsibeliaz_lcb through its C ABI (include/sibeliaz_lcb.h).  Additive flags: --gpu, --window, --stats, --sync-exit.
+// by libsibeliaz_lcb through its C ABI (include/sibeliaz_lcb.h).  Additive flags: --gpu, --window, --stats, --sync-exit,
+// --construct (fused pipeline: the junctions are found on the GPU from the FASTA files, no --graph file).
+#include "sibeliaz_graph.h"
 #include "sibeliaz_lcb.h"
 
 #include <chrono>
@@ -19,7 +21,7 @@ namespace {
 struct Options {
     unsigned k = 25, b = 200, m = 200, t = 1, a = 150, chunks = 0;
     std::string graph, outdir;
-    bool noseq = false, have_graph = false, stats = false, sync_exit = false;
+    bool noseq = false, have_graph = false, stats = false, sync_exit = false, construct = false;
     int gpu = 0, window = 0;
     std::vector<std::string> fasta;
 };
@@ -29,7 +31,7 @@ void Usage(FILE *f)
     fprintf(f,
             "USAGE:\n   sibeliaz-lcb  [--chunks <integer>] [--noseq] [-o <directory name>] --graph <file name>\n"
             "                 [-a <integer>] [-t <integer>] [-m <integer>] [-b <integer>] [-k <oddc>]\n"
-            "                 [--gpu <ordinal>] [--window <seeds>] [--stats] [--sync-exit] [--] [--version] [-h]\n"
+            "                 [--gpu <ordinal>] [--window <seeds>] [--stats] [--sync-exit] [--construct] [--] [--version] [-h]\n"
             "                 <fasta files with genomes> ...\n\n"
             "   SibeliaZ-LCB, a program for construction of locally-collinear blocks from complete genomes\n"
             "   (B200-native implementation; flags and outputs follow SibeliaZ-LCB 1.2.7)\n");
@@ -119,6 +121,8 @@ int Parse(int argc, char **argv, Options &o)
             o.stats = true;
         } else if (arg == "--sync-exit") {
             o.sync_exit = true;
+        } else if (arg == "--construct") {
+            o.construct = true; // no junction file: find the junctions on the GPU too (the twopaco step, fused)
         } else if (arg == "--gpu") {
             unsigned g = 0;
             if (!number("--gpu", g)) return 1;
@@ -132,7 +136,7 @@ int Parse(int argc, char **argv, Options &o)
             return 1;
         }
     }
-    if (!o.have_graph) {
+    if (!o.have_graph && !o.construct) {
         fprintf(stderr, "error: Required argument missing: graph for arg --graph\n");
         return 1;
     }
@@ -172,9 +176,10 @@ int Run(const Options &o, Done done)
     std::vector<const char *> files;
     for (auto &f : o.fasta) files.push_back(f.c_str());
     lcb_index *index = nullptr;
-    int load_rc = lcb_index_load(o.graph.c_str(), files.data(), (int)files.size(), (int)o.k, (int)o.a, &index, err, sizeof err);
+    int load_rc = o.construct ? lcb_index_load_fasta(files.data(), (int)files.size(), (int)o.k, &index, err, sizeof err)
+                              : lcb_index_load(o.graph.c_str(), files.data(), (int)files.size(), (int)o.k, (int)o.a, &index, err, sizeof err);
     auto t_parsed = std::chrono::steady_clock::now();
-    if (!load_rc) lcb_index_pack(index); // device record layout, built while the context is still coming up (optional step)
+    if (!load_rc && !o.construct) lcb_index_pack(index); // device record layout, built while the context is still coming up (optional step)
     auto t_packed = std::chrono::steady_clock::now();
     warm.join();
     if (load_rc) {
@@ -185,7 +190,8 @@ int Run(const Options &o, Done done)
     printf("Analyzing the graph...\n");
     fflush(stdout);
     lcb_index_view view;
-    lcb_index_get_view(index, &view);
+    memset(&view, 0, sizeof view);
+    if (!o.construct) lcb_index_get_view(index, &view);
     lcb_params p;
     lcb_default_params(&p);
     p.k = (int)o.k;
@@ -195,7 +201,23 @@ int Run(const Options &o, Done done)
     p.device = device;
     if (o.window > 0) p.window_init = p.window_max = o.window;
     lcb_ctx *ctx = nullptr;
-    int rc = lcb_create(&view, &p, &ctx);
+    int rc;
+    lcg_graph *graph = nullptr;
+    double ms_graph = 0;
+    if (o.construct) {
+        const uint8_t *const *seq = nullptr;
+        const uint64_t *len = nullptr;
+        const int32_t n_rec = lcb_index_get_sequences(index, &seq, &len);
+        rc = lcg_build_resident(seq, len, n_rec, (int)o.k, UINT64_MAX, device, &graph, err, sizeof err);
+        if (rc) {
+            fprintf(stderr, "error: %s\n", err);
+            return done(1);
+        }
+        ms_graph = Ms(t1, std::chrono::steady_clock::now());
+        rc = lcb_create_from_graph(graph, index, (int)o.a, &p, &ctx);
+    } else {
+        rc = lcb_create(&view, &p, &ctx);
+    }
     auto t_created = std::chrono::steady_clock::now();
     uint64_t n_seeds = 0;
     if (!rc) rc = lcb_enumerate_seeds(ctx, &n_seeds);
@@ -234,12 +256,12 @@ int Run(const Options &o, Done done)
         fprintf(stderr,
                 "{\"records\": %llu, \"vertices\": %llu, \"seeds\": %llu, \"block_instances\": %llu, \"windows\": %llu, "
                 "\"rounds\": %llu, \"traversals_first\": %llu, \"traversals_rerun\": %llu, \"kernel_launches\": %llu, "
-                "\"ms_parse\": %.3f, \"ms_pack\": %.3f, \"ms_warmup_thread\": %.3f, \"ms_load\": %.3f, \"ms_create\": %.3f, \"ms_create_enumerate_find\": %.3f, \"ms_enumerate\": %.3f, \"ms_find\": %.3f, "
+                "\"ms_parse\": %.3f, \"ms_pack\": %.3f, \"ms_graph\": %.3f, \"ms_warmup_thread\": %.3f, \"ms_load\": %.3f, \"ms_create\": %.3f, \"ms_create_enumerate_find\": %.3f, \"ms_enumerate\": %.3f, \"ms_find\": %.3f, "
                 "\"ms_traverse_kernels\": %.3f, \"ms_output\": %.3f, \"ms_total\": %.3f, \"junctions_per_sec\": %.1f}\n",
                 (unsigned long long)st.n_records, (unsigned long long)st.n_vertices, (unsigned long long)st.n_seeds,
                 (unsigned long long)st.n_block_instances, (unsigned long long)st.windows, (unsigned long long)st.rounds,
                 (unsigned long long)st.traversals_first, (unsigned long long)st.traversals_rerun,
-                (unsigned long long)st.kernel_launches, Ms(t0, t_parsed), Ms(t_parsed, t_packed), ms_warm, Ms(t0, t1), Ms(t1, t_created), Ms(t1, t2), st.ms_enumerate, st.ms_find,
+                (unsigned long long)st.kernel_launches, Ms(t0, t_parsed), Ms(t_parsed, t_packed), ms_graph, ms_warm, Ms(t0, t1), Ms(t1, t_created), Ms(t1, t2), st.ms_enumerate, st.ms_find,
                 st.ms_traverse_kernels, Ms(t2, t3), Ms(t0, t3),
                 (st.ms_enumerate + st.ms_find) > 0 ? 1000.0 * (double)st.n_records / (st.ms_enumerate + st.ms_find) : 0.0);
     }

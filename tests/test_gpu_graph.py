@@ -77,3 +77,54 @@ def test_pipeline_twopaco_then_lcb_reproduces_reference_blocks(star_small, tmp_p
                         "-t", "4", "--abundance", "150", "--noseq"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(os.path.join(out, "blocks_coords.gff"), "rb").read() == open(star_small.ref_gff, "rb").read()
+
+
+# ---- fused pipeline: FASTA -> junctions -> junction index -> blocks, all on the device -------------------------------
+def _fused_vs_file_path(fastas, k, a, m, b, tmp_path):
+    """Blocks of the fused pipeline == blocks of the file path on the junction file of the same graph (same vertex ids),
+    seed list included: the device-built index is the host loader's index."""
+    g = sb.JunctionGraph(fastas, k)
+    dbg = g.write(str(tmp_path / "g.dbg"))
+    st = sb.JunctionStorage(dbg, fastas, k, a)
+    bf = sb.BlocksFinder(st, k)
+    blocks = bf.find_blocks(m, b)
+    seeds = bf.seeds()
+    fs = sb.FusedStorage(fastas, k, a)
+    ff = sb.BlocksFinder(fs, k)
+    fblocks = ff.find_blocks(m, b)
+    fseeds = ff.seeds()
+    assert ff.stats["n_records"] == st.n_records and ff.stats["n_vertices"] == st.n_vertices
+    for key in ("vid", "ch", "count", "rank", "res_pos", "res_chr"):
+        assert np.array_equal(seeds[key], fseeds[key]), key
+    assert len(blocks) == len(fblocks) > 0 and blocks.tobytes() == fblocks.tobytes()
+    return ff, fs
+
+
+def test_fused_pipeline_star(star_small, tmp_path):
+    ff, fs = _fused_vs_file_path(star_small.fastas, star_small.k, star_small.a, star_small.m, star_small.b, tmp_path)
+    out = str(tmp_path / "out")
+    ff.generate_output(out, False, 0)
+    assert open(os.path.join(out, "blocks_coords.gff"), "rb").read() == open(star_small.ref_gff, "rb").read()
+
+
+@pytest.mark.parametrize("which", ["k15", "k25"])
+def test_fused_pipeline_examples(examples, which, tmp_path):
+    case = examples[which]
+    ff, fs = _fused_vs_file_path(case.fastas, case.k, case.a, case.m, case.b, tmp_path)
+    out = str(tmp_path / "out")
+    ff.generate_output(out, False, 0)
+    assert open(os.path.join(out, "blocks_coords.gff"), "rb").read() == open(case.ref_gff, "rb").read()
+
+
+def test_fused_pipeline_abundance_and_nrich(star_small, tmp_path):
+    _fused_vs_file_path(star_small.fastas, star_small.k, 4, star_small.m, star_small.b, tmp_path)   # filter bites
+    (tmp_path / "n").mkdir()
+    _fused_vs_file_path(write_nrich(str(tmp_path / "n")), 15, 150, 50, 200, tmp_path / "n")
+
+
+def test_fused_cli(star_small, tmp_path):
+    out = str(tmp_path / "out")
+    r = subprocess.run([sb.CLI_PATH, "--construct"] + star_small.fastas + ["-k", str(star_small.k), "-b", "200", "-o", out, "-m", "50",
+                        "--abundance", "150", "--noseq", "--stats"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(os.path.join(out, "blocks_coords.gff"), "rb").read() == open(star_small.ref_gff, "rb").read()
