@@ -684,10 +684,16 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     // ---- results
     const auto t_d2h = std::chrono::steady_clock::now();
     out.n = nj; // plain arrays: a std::vector would zero-fill 180 MB on 4x100 Mbp before the copy overwrites it
-    out.chr.reset(new uint32_t[std::max<size_t>(nj, 1)]);
-    out.pos.reset(new uint32_t[std::max<size_t>(nj, 1)]);
-    out.id.reset(new int32_t[std::max<size_t>(nj, 1)]);
-    if (nj) {
+    uint32_t last_chr = 0;
+    if (in.keep_on_device) { // the fused pipeline reads the records where they are; a host copy is made on demand (download)
+        if (nj) CU(cudaMemcpyAsync(&last_chr, d_jchr + (nj - 1), sizeof last_chr, cudaMemcpyDeviceToHost, sc.stream));
+        CU(cudaStreamSynchronize(sc.stream));
+    } else {
+        out.chr.reset(new uint32_t[std::max<size_t>(nj, 1)]);
+        out.pos.reset(new uint32_t[std::max<size_t>(nj, 1)]);
+        out.id.reset(new int32_t[std::max<size_t>(nj, 1)]);
+    }
+    if (nj && !in.keep_on_device) {
         CU(cudaMemcpyAsync(out.chr.get(), d_jchr, (size_t)nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc.stream));
         CU(cudaMemcpyAsync(out.pos.get(), d_jpos, (size_t)nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc.stream));
         CU(cudaMemcpyAsync(out.id.get(), d_jid, (size_t)nj * sizeof(int32_t), cudaMemcpyDeviceToHost, sc.stream));
@@ -701,12 +707,48 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         r.d_text = d_text, r.d_goff = d_goff, r.d_chr = d_jchr, r.d_pos = d_jpos, r.d_id = d_jid;
         r.n_junctions = nj;
         r.n_vertices = (ns ? (uint64_t)nb + 42 + ns - 1 : (uint64_t)nb) + 1;
-        r.last_chr = nj ? out.chr[nj - 1] : 0;
+        r.last_chr = last_chr;
         for (void *keep : {(void *)d_text, (void *)d_goff, (void *)d_jchr, (void *)d_jpos, (void *)d_jid})
             sc.dev.erase(std::remove(sc.dev.begin(), sc.dev.end(), keep), sc.dev.end());
     }
     st.ms_total = ms_since(t_begin);
     return LCG_OK;
+}
+
+int download(const Resident &r, uint32_t *chr, uint32_t *pos, int32_t *id, std::string &err)
+{
+    CU(cudaSetDevice(r.device));
+    const size_t n = (size_t)r.n_junctions;
+    if (n && chr) CU(cudaMemcpy(chr, r.d_chr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (n && pos) CU(cudaMemcpy(pos, r.d_pos, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (n && id) CU(cudaMemcpy(id, r.d_id, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return LCG_OK;
+}
+
+void preload_kernels()
+{
+    // CUDA loads kernels lazily, on first use: a host that knows it will build a graph touches them off the critical path
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_table_init);
+    cudaFuncGetAttributes(&fa, k_pack);
+    cudaFuncGetAttributes(&fa, k_edges);
+    cudaFuncGetAttributes(&fa, k_candidates);
+    cudaFuncGetAttributes(&fa, k_mark_stubs);
+    cudaFuncGetAttributes(&fa, k_decide<false>);
+    cudaFuncGetAttributes(&fa, k_decide<true>);
+    cudaFuncGetAttributes(&fa, k_assign_ids);
+    cudaFuncGetAttributes(&fa, k_flag_count);
+    cudaFuncGetAttributes(&fa, k_flag_write);
+    cudaFuncGetAttributes(&fa, k_emit_ids);
+    cudaFuncGetAttributes(&fa, k_final_count);
+    cudaFuncGetAttributes(&fa, k_final_write);
+    cudaFuncGetAttributes(&fa, k_iota);
+    cudaFuncGetAttributes(&fa, k_scan_tiles);
+    cudaFuncGetAttributes(&fa, k_scan_sums);
+    cudaFuncGetAttributes(&fa, k_scan_add);
+    cudaFuncGetAttributes(&fa, k_radix_hist<uint64_t>);
+    cudaFuncGetAttributes(&fa, k_radix_scatter<uint64_t>);
+    cudaFuncGetAttributes(&fa, k_gather<uint64_t>);
 }
 
 void free_resident(Resident &r)

@@ -18,6 +18,20 @@ struct lcg_graph {
     ~lcg_graph() { lcg::free_resident(resident); }
 };
 
+namespace {
+// a resident graph keeps its records on the device; the host copy appears when somebody asks for it
+int EnsureHostCopy(const lcg_graph *cg, std::string &err)
+{
+    lcg_graph *g = const_cast<lcg_graph *>(cg);
+    if (g->chr || !g->resident.d_text) return LCG_OK;
+    const size_t n = std::max<size_t>((size_t)g->n, 1);
+    g->chr.reset(new uint32_t[n]);
+    g->pos.reset(new uint32_t[n]);
+    g->id.reset(new int32_t[n]);
+    return lcg::download(g->resident, g->chr.get(), g->pos.get(), g->id.get(), err);
+}
+} // namespace
+
 const lcg::Resident *lcg::resident_of(const lcg_graph *g) { return g && g->resident.d_text ? &g->resident : nullptr; }
 
 namespace {
@@ -125,6 +139,11 @@ extern "C" uint64_t lcg_num_junctions(const lcg_graph *g) { return g ? g->n : 0;
 extern "C" int lcg_get_junctions(const lcg_graph *g, uint32_t *chr, uint32_t *pos, int64_t *id)
 {
     if (!g) return LCG_ERR_ARG;
+    {
+        std::string e;
+        const int rc = EnsureHostCopy(g, e);
+        if (rc) return rc;
+    }
     const size_t n = (size_t)g->n;
     if (chr) memcpy(chr, g->chr.get(), n * sizeof(uint32_t));
     if (pos) memcpy(pos, g->pos.get(), n * sizeof(uint32_t));
@@ -136,6 +155,14 @@ extern "C" int lcg_get_junctions(const lcg_graph *g, uint32_t *chr, uint32_t *po
 extern "C" int lcg_write_junction_file(const lcg_graph *g, const char *path, char *err, size_t errlen)
 {
     if (!g || !path) return LCG_ERR_ARG;
+    {
+        std::string e;
+        const int rc = EnsureHostCopy(g, e);
+        if (rc) {
+            if (err && errlen) snprintf(err, errlen, "%s", e.c_str());
+            return rc;
+        }
+    }
     // 12-byte records {u32 pos; i64 id}; {0xFFFFFFFF, INT64_MAX} once per chromosome change (junctionapi.h:117-131)
     std::string buf;
     buf.reserve((size_t)g->n * 12 + 1024);

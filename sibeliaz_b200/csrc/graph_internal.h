@@ -47,6 +47,8 @@ struct DeviceOutput {
 
 int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err);
 void free_resident(Resident &r);
+int download(const Resident &r, uint32_t *chr, uint32_t *pos, int32_t *id, std::string &err); // junction records -> host
+void preload_kernels();
 const Resident *resident_of(const lcg_graph *g); // nullptr when the graph was built without keep_on_device
 
 } // namespace lcg

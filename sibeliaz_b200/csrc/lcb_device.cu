@@ -866,6 +866,7 @@ extern "C" int lcb_warmup(int device)
         cudaFuncGetAttributes(&fa, k_gather<unsigned>);
         cudaFuncGetAttributes(&fa, k_gather<unsigned char>);
         cudaFuncGetAttributes(&fa, k_gather<unsigned long long>);
+        if (getenv("LCB_WARM_GRAPH")) lcg::preload_kernels(); // set by hosts that will also find the junctions (--construct)
         lap("kernel preload");
     }
     {

@@ -167,6 +167,7 @@ int Run(const Options &o, Done done)
         setenv("CUDA_VISIBLE_DEVICES", std::to_string(o.gpu).c_str(), 1);
         device = 0;
     }
+    if (o.construct) setenv("LCB_WARM_GRAPH", "1", 1);
     double ms_warm = 0;
     std::thread warm([device, &ms_warm]() { // CUDA context + scratch while the files are parsed
         auto a = std::chrono::steady_clock::now();

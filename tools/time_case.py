@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--dir", default="/tmp/lcb_time")
     ap.add_argument("--dbg", default=None, help="junction file made earlier by the reference twopaco for exactly this synthetic")
+    ap.add_argument("--construct", action="store_true", help="fused pipeline: junctions found on the GPU, no reference twopaco run")
     a = ap.parse_args()
     import numpy as np
     import sibeliaz_b200 as sb
@@ -39,12 +40,22 @@ def main():
     fas = generate(d, a.kind, a.genomes, a.length, a.rate, a.seed)
     if a.dbg:
         dbg = a.dbg
+    if a.construct:
+        t = time.time()
+        g = sb.JunctionGraph(fas, a.k)
+        g.write(dbg)
+        print("junction finder (GPU) %.2fs" % (time.time() - t), {k_: (round(v, 1) if isinstance(v, float) else v) for k_, v in g.stats.items()}, flush=True)
+        g.close()
     if not os.path.exists(dbg):
         run_twopaco(fas, a.k, dbg, threads=min(16, os.cpu_count() or 1))
     print("input ready in %.1fs" % (time.time() - t), flush=True)
     t = time.time()
-    st = sb.JunctionStorage(dbg, fas, a.k, 150)
-    print("load %.2fs  records %d vertices %d" % (time.time() - t, st.n_records, st.n_vertices), flush=True)
+    if a.construct:
+        st = sb.FusedStorage(fas, a.k, 150)
+        print("fused storage %.2fs" % (time.time() - t), flush=True)
+    else:
+        st = sb.JunctionStorage(dbg, fas, a.k, 150)
+        print("load %.2fs  records %d vertices %d" % (time.time() - t, st.n_records, st.n_vertices), flush=True)
     for rep in range(a.reps):
         bf = sb.BlocksFinder(st, a.k, window_init=a.window, window_max=a.wmax or a.window, collect_counters=(2 if os.environ.get('LCB_TRACE_ROUNDS') else True))
         t = time.time()
@@ -58,7 +69,7 @@ def main():
         t_find = time.time() - t
         s = bf.stats
         print(json.dumps(dict(rep=rep, create_s=round(t_create, 3), enum_s=round(t_enum, 3), find_s=round(t_find, 3),
-                              jps=round(st.n_records / (t_enum + t_find)), **{k: (round(v, 2) if isinstance(v, float) else v) for k, v in s.items()})), flush=True)
+                              jps=round(s["n_records"] / (t_enum + t_find)), **{k: (round(v, 2) if isinstance(v, float) else v) for k, v in s.items()})), flush=True)
         bf.close()
     if a.oracle:
         t = time.time()
