@@ -31,7 +31,7 @@ extern "C" {
 #define LCB_ERR_IO 2       /* file could not be read or written (reference: runtime_error)    */
 #define LCB_ERR_FORMAT 3   /* malformed FASTA / junction file                                  */
 #define LCB_ERR_CUDA 4     /* CUDA / NCCL failure, or no usable device                         */
-#define LCB_ERR_CAPACITY 5 /* a per-seed device buffer overflowed its hard cap                 */
+#define LCB_ERR_CAPACITY 5 /* a per-seed device buffer overflowed its hard cap (big arena slot) */
 #define LCB_ERR_STATE 6    /* call sequence violated (e.g. find_blocks before create)          */
 
 /* ------------------------------------------------------------------------------------------------
@@ -120,6 +120,7 @@ typedef struct lcb_stats {
                                               find_blocks on the library's stream (when find_blocks enumerates)  */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t pool_restarts;                /* active sets abandoned because a result pool ran full */
+    uint64_t big_arena_runs;               /* evaluations that outgrew the per-warp scratch and were re-run in a big slot */
 } lcb_stats;
 
 void lcb_default_params(lcb_params *p);

@@ -232,8 +232,12 @@ struct lcbo {
         }
     }
 
+    uint64_t mx[3] = {0, 0, 0}; // diagnostics: largest path (vertices), instance table and good list seen at a Clear
     void PathClear() // Path::Clear, path.h:650-677
     {
+        mx[0] = std::max<uint64_t>(mx[0], left_body.size() + right_body.size() + 1);
+        mx[1] = std::max<uint64_t>(mx[1], inst.size());
+        mx[2] = std::max<uint64_t>(mx[2], good.size());
         for (auto &pt : left_body) DistUnset(pt.e.sv);
         for (auto &pt : right_body) DistUnset(pt.e.ev);
         left_body.clear();
@@ -823,6 +827,9 @@ extern "C" int64_t lcbo_find_blocks(lcbo *L, int min_block, int max_branch, int 
         }
         invalid_chr.clear();
     }
+    if (getenv("LCBO_MAXIMA"))
+        fprintf(stderr, "oracle maxima: path %llu vertices, %llu instances, %llu good instances\n",
+                (unsigned long long)L->mx[0], (unsigned long long)L->mx[1], (unsigned long long)L->mx[2]);
     return (int64_t)L->blocks.size();
 }
 

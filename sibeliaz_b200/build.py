@@ -13,6 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 BINDIR = os.path.join(HERE, "bin")
 LIB = os.path.join(LIBDIR, "libsibeliaz_lcb.so")
+LIB_TINY = os.path.join(LIBDIR, "libsibeliaz_lcb_tiny.so")
 CLI = os.path.join(BINDIR, "sibeliaz-lcb")
 CLI_GRAPH = os.path.join(BINDIR, "twopaco")
 SOURCES = ("lcb_device.cu", "lcb_host.cpp", "graph_device.cu", "graph_host.cpp")
@@ -104,6 +105,9 @@ def build(force=False, verbose=False):
     if os.path.exists(main_src) and (force or _newer(CLI, [main_src, LIB])):
         _run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, main_src, "-o", CLI, "-L", LIBDIR, "-lsibeliaz_lcb",
               "-Wl,-rpath,$ORIGIN/../lib"])
+    # test build with tiny per-warp arenas (tests/test_gpu_parity.py::test_big_arena_rerun): same sources, -DLCB_TINY_ARENA
+    if force or _newer(LIB_TINY, deps):
+        build_selfcheck(verbose=verbose, defines=("-DLCB_TINY_ARENA",), name=os.path.basename(LIB_TINY))
     graph_src = os.path.join(CSRC, "twopaco_main.cpp")
     if os.path.exists(graph_src) and (force or _newer(CLI_GRAPH, [graph_src, LIB])):
         _run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, graph_src, "-o", CLI_GRAPH, "-L", LIBDIR, "-lsibeliaz_lcb",

@@ -68,6 +68,8 @@ struct Control { // device-resident round state, mirrored to pinned host memory 
     unsigned long long runs0, runs1;
     unsigned blocks_done, out_done; // emit: blocks / instances committed so far
     unsigned long long dbg[6];
+    unsigned big_runs;            // evaluations that outgrew the per-warp arena and ran in a big slot
+    unsigned big_lock[kBigSlots]; // 1 = big arena slot taken (always released by its holder)
 };
 
 struct Window { // per-seed arrays of the active seeds, ring-indexed by j = seed & mask
@@ -165,7 +167,8 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
                                                         const unsigned char *__restrict__ seed_ch,
                                                         unsigned phase, int force_slot, const unsigned *__restrict__ list,
                                                         const unsigned *__restrict__ n_ptr, Window win, Control *ctl,
-                                                        unsigned char *arena_base, size_t arena_stride, int collect)
+                                                        unsigned char *arena_base, size_t arena_stride, unsigned char *big_base,
+                                                        int collect)
 {
     __shared__ WarpSmem smem[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -181,19 +184,8 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
     c.ct.walk = c.ct.occ = c.ct.scan = c.ct.score = 0;
     c.ct.pushes = c.ct.mpv_fast = c.ct.mpv_mid = c.ct.mpv_slow = c.ct.push_par = c.ct.push_ser = 0;
     c.vote_clean = false;
-    {
-        unsigned char *p = arena_base + warp_global * arena_stride;
-        c.ar.inst = (Inst *)p, p += sizeof(Inst) * kInstMax;
-        c.ar.best = (int4 *)p, p += sizeof(int4) * kInstMax;
-        c.ar.hash = (int2 *)p, p += sizeof(int2) * kHashMax;
-        c.ar.redge = (int4 *)p, p += sizeof(int4) * kPathMax;
-        c.ar.vote = (int2 *)p, p += sizeof(int2) * kVoteMax;
-        c.ar.vlast = (unsigned *)p, p += sizeof(unsigned) * kVoteMax;
-        c.ar.rs = (int2 *)p, p += sizeof(int2) * kReadSetMax;
-        c.ar.hslot = (int *)p, p += sizeof(int) * kPathMax;
-        c.ar.ord = (unsigned short *)p, p += sizeof(unsigned short) * kInstMax;
-        c.ar.good = (unsigned short *)p, p += sizeof(unsigned short) * kInstMax;
-    }
+    arena_bind(c, arena_base + warp_global * arena_stride, false);
+    int big_slot = -1; // >= 0: this warp holds that big arena slot
     const unsigned n = *n_ptr;
     unsigned done = 0, done1 = 0;
     unsigned long long longest = 0;
@@ -212,6 +204,25 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
             c.thresh = slot == 0 ? (i / phase) * phase : i;
             const unsigned long long t_begin = global_ns();
             process_seed(c, seed_vid[i], seed_ch[i]);
+            if ((c.err & 0xFF) == LCB_ERR_CAPACITY && big_slot < 0) {
+                // the seed outgrew the per-warp arena: leave that arena clean (spill hash all-empty), take one of the few big
+                // slots (their holders wait for nothing, so waiting here cannot deadlock) and evaluate the seed again
+                hash_clear(c);
+                if (lane == 0) {
+                    unsigned s = (unsigned)warp_global % kBigSlots;
+                    while (atomicCAS(&ctl->big_lock[s], 0u, 1u) != 0u) {
+                        s = (s + 1) % kBigSlots;
+                        __nanosleep(200);
+                    }
+                    __threadfence();
+                    big_slot = (int)s;
+                    atomicAdd(&ctl->big_runs, 1u);
+                }
+                big_slot = __shfl_sync(kFull, big_slot, 0);
+                arena_bind(c, big_base + (size_t)big_slot * arena_stride_of(true), true);
+                c.err = 0;
+                continue; // same call site, big arena
+            }
             longest = max(longest, global_ns() - t_begin);
             if (c.err) break;
             // publish bestInstance and the read-set
@@ -233,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
                 break;
             }
             for (int t = lane; t < c.nbest; t += 32) win.inst_pool[io + t] = c.best[t];
-            for (int t = lane; t < c.nrs; t += 32) win.rs_pool[ro + t] = c.ar.rs[t];
+            for (int t = lane; t < c.nrs; t += 32) win.rs_pool[ro + t] = c.ar.rs()[t];
             if (lane == 0) {
                 win.res_off[slot][j] = (unsigned)io;
                 win.res_cnt[slot][j] = (unsigned)c.nbest;
@@ -261,6 +272,16 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
             }
             if (!conf) break;
             slot = 1;
+        }
+        if (big_slot >= 0) { // results are published (or the run failed): hand the big slot back
+            if (c.err) hash_clear(c);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(&ctl->big_lock[big_slot], 0u);
+            }
+            big_slot = -1;
+            arena_bind(c, arena_base + warp_global * arena_stride, false);
         }
         if (c.err) {
             if (lane == 0) atomicCAS(&ctl->err, 0u, (unsigned)c.err);
@@ -675,6 +696,7 @@ struct lcb_ctx {
     Control *d_ctl = nullptr, *h_ctl = nullptr;
     unsigned char *d_arena = nullptr;
     size_t arena_stride = 0;
+    size_t d_big = 0;
     int grid_traverse = 0;
     lcb_block_instance *d_out = nullptr;
     lcb_stats st{};
@@ -709,42 +731,47 @@ ncclComm_t g_comm = nullptr; // reused by every context of this process (lcb_com
 int g_comm_dev = -1, g_comm_rank = -1, g_comm_size = 0;
 #endif
 
-cudaError_t cached_alloc(void **p, size_t bytes, int device, bool *was_cached)
+// `want_zeroed`: the caller needs the arena invariant (null: any block will do).  A block tagged zeroed is handed
+// only to such callers while an untagged one of the right size exists; *want_zeroed tells whether the invariant
+// holds for the block returned (false: the caller clears it).
+cudaError_t cached_alloc(void **p, size_t bytes, int device, bool *want_zeroed)
 {
     bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         int best = -1;
+        auto better = [&](const CachedBlock &a, const CachedBlock &b) { // is a the better choice than b?
+            const bool wa = a.zeroed == (want_zeroed != nullptr), wb = b.zeroed == (want_zeroed != nullptr);
+            if (wa != wb) return wa;
+            return a.bytes < b.bytes;
+        };
         for (size_t i = 0; i < g_cache.size(); i++)
             if (g_cache[i].device == device && g_cache[i].bytes >= bytes && g_cache[i].bytes <= bytes + bytes / 4 + 4096 &&
-                (best < 0 || g_cache[i].bytes < g_cache[(size_t)best].bytes))
+                (best < 0 || better(g_cache[i], g_cache[(size_t)best])))
                 best = (int)i;
         if (best >= 0) {
             *p = g_cache[(size_t)best].p;
+            if (want_zeroed) *want_zeroed = g_cache[(size_t)best].zeroed;
             g_cache.erase(g_cache.begin() + best);
-            if (was_cached) *was_cached = true;
             return cudaSuccess;
         }
     }
-    if (was_cached) *was_cached = false;
+    if (want_zeroed) *want_zeroed = false;
     return device < 0 ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes);
 }
 
-void cached_free(void *p, size_t bytes, int device)
+void cached_free(void *p, size_t bytes, int device, bool zeroed = false)
 {
     bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    g_cache.push_back(CachedBlock{p, bytes, device, false});
+    g_cache.push_back(CachedBlock{p, bytes, device, zeroed});
 }
 
 constexpr unsigned long long kInstPoolCap = 16ull << 20, kRsPoolCap = 128ull << 20;
 
-size_t arena_stride_bytes()
-{
-    size_t s = sizeof(Inst) * kInstMax + sizeof(int4) * kInstMax + sizeof(int2) * kHashMax + sizeof(int4) * kPathMax +
-               sizeof(int2) * kVoteMax + sizeof(unsigned) * kVoteMax + sizeof(int2) * kReadSetMax + sizeof(int) * kPathMax + 2 * sizeof(unsigned short) * kInstMax;
-    return (s + 255) & ~(size_t)255;
-}
+size_t arena_stride_bytes() { return arena_stride_of(false); }
+// one allocation: a per-warp arena for every resident warp, then the big slots
+size_t arena_total_bytes(size_t warps) { return arena_stride_of(false) * warps + arena_stride_of(true) * (size_t)kBigSlots; }
 
 template <typename T>
 int dev_alloc(lcb_ctx *ctx, T **p, size_t n, bool *was_cached = nullptr)
@@ -829,8 +856,7 @@ extern "C" int lcb_warmup(int device)
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const size_t stride = arena_stride_bytes();
-    const size_t arena_bytes = stride * (size_t)per_sm * (size_t)sms * kWarpsPerBlock;
+    const size_t arena_bytes = arena_total_bytes((size_t)per_sm * (size_t)sms * kWarpsPerBlock);
     void *arena = nullptr, *ip = nullptr, *rp = nullptr;
     bool cached = false;
     if (cached_alloc(&arena, arena_bytes, device, &cached) != cudaSuccess) return LCB_ERR_CUDA;
@@ -869,11 +895,7 @@ extern "C" int lcb_warmup(int device)
         if (getenv("LCB_WARM_GRAPH")) lcg::preload_kernels(); // set by hosts that will also find the junctions (--construct)
         lap("kernel preload");
     }
-    {
-        std::lock_guard<std::mutex> lk(g_cache_mu);
-        size_t ab = (arena_bytes + 511) & ~(size_t)511;
-        g_cache.push_back(CachedBlock{arena, ab, device, true});
-    }
+    cached_free(arena, arena_bytes, device, true);
     cached_free(ip, sizeof(int4) * kInstPoolCap, device);
     cached_free(rp, sizeof(int2) * kRsPoolCap, device);
     return LCB_OK;
@@ -887,8 +909,9 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (size_t i = 0; i < ctx->allocs.size(); i++) {
-        if (ctx->allocs[i] == (void *)ctx->d_arena && ctx->arena_dirty) cudaFree(ctx->allocs[i]); // invariant broken: do not recycle
-        else cached_free(ctx->allocs[i], ctx->alloc_bytes[i], ctx->device);
+        // the arena goes back tagged "spill hash all-empty" unless a failed traversal left it in an unknown state
+        const bool arena = ctx->allocs[i] == (void *)ctx->d_arena;
+        cached_free(ctx->allocs[i], ctx->alloc_bytes[i], ctx->device, arena && !ctx->arena_dirty);
     }
     for (size_t i = 0; i < ctx->seed_allocs.size(); i++) cached_free(ctx->seed_allocs[i], ctx->seed_alloc_bytes[i], ctx->device);
     if (ctx->ev_step0) cudaEventDestroy(ctx->ev_step0);
@@ -925,6 +948,10 @@ int create_begin(lcb_ctx *ctx, const lcb_params *params, const CreateTrace &lap)
     p.window_init = std::max(p.phase_size, std::min(p.window_init, p.window_max) / p.phase_size * p.phase_size);
     if (p.k <= 0 || p.max_branch < 0 || p.min_block < 0) {
         ctx->error = "bad parameters";
+        return LCB_ERR_ARG;
+    }
+    if ((long long)p.max_branch + p.looking_depth >= 65536) { // a look-ahead walk has at most -b + depth junctions: 16 bits in the vote
+        ctx->error = "max_branch + looking_depth must stay below 65536";
         return LCB_ERR_ARG;
     }
     int ndev = 0;
@@ -998,7 +1025,8 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
     ctx->grid_traverse = per_sm * ctx->sms;
     lap("occupancy query");
     ctx->arena_stride = arena_stride_bytes();
-    size_t arena_bytes = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock;
+    const size_t arena_bytes = arena_total_bytes((size_t)ctx->grid_traverse * kWarpsPerBlock);
+    ctx->d_big = ctx->arena_stride * (size_t)ctx->grid_traverse * kWarpsPerBlock; // offset of the big slots inside the arena
     bool arena_cached = false;
     if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes, &arena_cached))) return rc;
     if (!arena_cached) CUDA_TRY(cudaMemsetAsync(ctx->d_arena, 0, arena_bytes, ctx->stream)); // the spill hash must start all-empty
@@ -1457,12 +1485,12 @@ int launch_traverse(lcb_ctx *ctx, const uint32_t *E, int slot, const unsigned *l
     if (ctx->prm.collect_counters)
         k_traverse<true><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
                                                                            (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
-                                                                           ctx->d_ctl, ctx->d_arena, ctx->arena_stride,
+                                                                           ctx->d_ctl, ctx->d_arena, ctx->arena_stride, ctx->d_arena + ctx->d_big,
                                                                            ctx->prm.collect_counters);
     else
         k_traverse<false><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
                                                                             (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
-                                                                            ctx->d_ctl, ctx->d_arena, ctx->arena_stride, 0);
+                                                                            ctx->d_ctl, ctx->d_arena, ctx->arena_stride, ctx->d_arena + ctx->d_big, 0);
     ctx->st.kernel_launches++;
     ctx->st.traverse_launches++;
     return LCB_OK;
@@ -1571,7 +1599,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             CUDA_TRY(cudaMemcpyAsync(local, ctx->d_wnext, sizeof local, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             first_dirty = ~local[0];
-            if (local[1] && !h.err) h.err = LCB_ERR_CAPACITY;
+            if (local[1] && !h.err) h.err = local[1];
             h.pool_overflow = local[2];
             drain = local[3] != 0;
             next_delta = local[4];
@@ -1583,8 +1611,12 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
                     100.0 * h.inst_used / ctx->win.inst_cap, 100.0 * h.rs_used / ctx->win.rs_cap);
         if (h.err) {
             ctx->arena_dirty = true;
-            ctx->error = "a per-seed device buffer overflowed its hard cap (path, instance or read-set too large)";
-            return (int)h.err;
+            // (the per-warp arena's smaller caps are not errors: such seeds are re-run in a big arena slot)
+            static const char *const what[] = {"a per-seed buffer", "path vertices (cap 524288)", "read-set intervals (cap 1048576)",
+                                               "path instances (cap 32768)", "look-ahead vote table (cap 262144 vertices)"};
+            const unsigned w = std::min(h.err >> 8, 4u);
+            ctx->error = std::string("a per-seed device buffer overflowed its hard cap: ") + what[w];
+            return (int)(h.err & 0xFF);
         }
         if (h.pool_overflow) {
             // a result pool ran full: forget the active set (committed seeds are final), halve it and start again
@@ -1650,6 +1682,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     ctx->st.n_block_instances = out_done;
     ctx->st.n_blocks = blocks_done;
     ctx->st.traversals_first = ctx->h_ctl->runs0;
+    ctx->st.big_arena_runs = ctx->h_ctl->big_runs;
     ctx->st.traversals_rerun = ctx->h_ctl->runs1;
     ctx->st.t_walk = ctx->h_ctl->ct_walk;
     ctx->st.t_occ = ctx->h_ctl->ct_occ;

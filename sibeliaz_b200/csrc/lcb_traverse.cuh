@@ -27,13 +27,48 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // ---- capacities -----------------------------------------------------------------------------------
 constexpr int kInstSmem = 32;      // instances kept in shared memory
-constexpr int kInstMax = 4096;     // hard cap (HBM arena)
 constexpr int kHashSmem = 256;     // path hash slots in shared memory (<=128 vertices)
-constexpr int kHashMax = 65536;    // hard cap: 32768 path vertices
-constexpr int kPathMax = 32768;
 constexpr int kVoteSmem = 128;     // vote table slots in shared memory
+#ifndef LCB_TINY_ARENA
+// per-warp arena; a seed that outgrows any of these is re-run in a big arena slot
+constexpr int kInstMax = 4096;
+constexpr int kHashMax = 65536;
+constexpr int kPathMax = 32768;    // path vertices (half the hash slots)
 constexpr int kVoteMax = 8192;
 constexpr int kReadSetMax = 65536; // read-set intervals per traversal
+#else
+// test build (build.py --tiny-arena): ordinary fixtures outgrow the per-warp arena all the time, so the GPU suite
+// exercises the big-slot re-run
+constexpr int kInstMax = 64;
+constexpr int kHashMax = 1024;
+constexpr int kPathMax = 512;
+constexpr int kVoteMax = 1024;
+constexpr int kReadSetMax = 512;
+#endif
+// big arena slots (a few per device, taken on demand): the hard caps
+constexpr int kBigInstMax = 32768;
+constexpr int kBigHashMax = 1 << 20; // 20 hash bits (hash_of >> 12)
+constexpr int kBigPathMax = 1 << 19;
+constexpr int kBigVoteMax = 1 << 18;
+constexpr int kBigReadSetMax = 1 << 20;
+constexpr int kBigSlots = 64;
+constexpr int kSmallInstMax = kInstMax, kSmallHashMax = kHashMax, kSmallPathMax = kPathMax, kSmallVoteMax = kVoteMax,
+              kSmallReadSetMax = kReadSetMax;
+
+struct Caps { // capacities of the arena a traversal currently runs in
+    int inst, hash, path, vote, rs;
+};
+__host__ __device__ __forceinline__ Caps caps_of(bool big)
+{
+    return big ? Caps{kBigInstMax, kBigHashMax, kBigPathMax, kBigVoteMax, kBigReadSetMax}
+               : Caps{kInstMax, kHashMax, kPathMax, kVoteMax, kReadSetMax};
+}
+struct Ctx;
+__device__ __forceinline__ int cap_inst(const Ctx &c);
+__device__ __forceinline__ int cap_hash(const Ctx &c);
+__device__ __forceinline__ int cap_path(const Ctx &c);
+__device__ __forceinline__ int cap_vote(const Ctx &c);
+__device__ __forceinline__ int cap_rs(const Ctx &c);
 
 struct Inst { // Path::Instance (path.h:53-181) with cached end-point data; 56 bytes
     int fg, bg;         // front_/back_ : global record index
@@ -81,17 +116,39 @@ struct WarpSmem { // ~5 KB per warp
     unsigned short s_good[kInstSmem];
 };
 
-struct WarpArena { // per-warp HBM scratch (spill + variable-length logs)
-    Inst *inst;           // kInstMax
-    int4 *best;           // kInstMax
-    unsigned short *ord;  // kInstMax
-    unsigned short *good; // kInstMax
-    int2 *hash;           // kHashMax
-    int *hslot;           // kPathMax: slots occupied in the HBM hash (for O(path) clearing)
-    int4 *redge;          // kPathMax: successful right edges {end vertex, length, source g | strand << 31, path distance}
-    int2 *vote;           // kVoteMax
-    unsigned *vlast;      // kVoteMax
-    int2 *rs;             // kReadSetMax: read-set intervals [lo, hi] over epoch indices
+struct WarpArena { // HBM scratch of one traversal (per-warp arena or big slot): spill space + variable-length logs.
+    // One base pointer and one flag live in registers; the arrays are base + a constant offset per arena kind.
+    unsigned char *base;
+    bool big;
+    __device__ __forceinline__ size_t pick(size_t small_off, size_t big_off) const { return big ? big_off : small_off; }
+#define LCB_AR_OFF(K)                                                                                                   \
+    static constexpr size_t o_inst_##K = 0;                                                                             \
+    static constexpr size_t o_best_##K = o_inst_##K + sizeof(Inst) * (size_t)k##K##InstMax;                             \
+    static constexpr size_t o_hash_##K = o_best_##K + sizeof(int4) * (size_t)k##K##InstMax;                             \
+    static constexpr size_t o_redge_##K = o_hash_##K + sizeof(int2) * (size_t)k##K##HashMax;                            \
+    static constexpr size_t o_vote_##K = o_redge_##K + sizeof(int4) * (size_t)k##K##PathMax;                            \
+    static constexpr size_t o_rs_##K = o_vote_##K + sizeof(int2) * (size_t)k##K##VoteMax;                               \
+    static constexpr size_t o_vlast_##K = o_rs_##K + sizeof(int2) * (size_t)k##K##ReadSetMax;                           \
+    static constexpr size_t o_hslot_##K = o_vlast_##K + sizeof(unsigned) * (size_t)k##K##VoteMax;                       \
+    static constexpr size_t o_ord_##K = o_hslot_##K + sizeof(int) * (size_t)k##K##PathMax;                              \
+    static constexpr size_t o_good_##K = o_ord_##K + sizeof(unsigned short) * (size_t)k##K##InstMax;                    \
+    static constexpr size_t o_end_##K = o_good_##K + sizeof(unsigned short) * (size_t)k##K##InstMax;
+    LCB_AR_OFF(Small)
+    LCB_AR_OFF(Big)
+#undef LCB_AR_OFF
+    __device__ __forceinline__ Inst *inst() const { return (Inst *)(base + pick(o_inst_Small, o_inst_Big)); }            // cap_inst
+    __device__ __forceinline__ int4 *best() const { return (int4 *)(base + pick(o_best_Small, o_best_Big)); }            // cap_inst
+    __device__ __forceinline__ int2 *hash() const { return (int2 *)(base + pick(o_hash_Small, o_hash_Big)); }            // cap_hash
+    // successful right edges {end vertex, length, source g | strand << 31, path distance}
+    __device__ __forceinline__ int4 *redge() const { return (int4 *)(base + pick(o_redge_Small, o_redge_Big)); }         // cap_path
+    __device__ __forceinline__ int2 *vote() const { return (int2 *)(base + pick(o_vote_Small, o_vote_Big)); }            // cap_vote
+    // read-set intervals [lo, hi] over epoch indices
+    __device__ __forceinline__ int2 *rs() const { return (int2 *)(base + pick(o_rs_Small, o_rs_Big)); }                  // cap_rs
+    __device__ __forceinline__ unsigned *vlast() const { return (unsigned *)(base + pick(o_vlast_Small, o_vlast_Big)); } // cap_vote
+    // slots occupied in the HBM hash (for O(path) clearing)
+    __device__ __forceinline__ int *hslot() const { return (int *)(base + pick(o_hslot_Small, o_hslot_Big)); }           // cap_path
+    __device__ __forceinline__ unsigned short *ord() const { return (unsigned short *)(base + pick(o_ord_Small, o_ord_Big)); }
+    __device__ __forceinline__ unsigned short *good() const { return (unsigned short *)(base + pick(o_good_Small, o_good_Big)); }
 };
 
 struct Counters {
@@ -120,7 +177,7 @@ struct Ctx { // warp-uniform traversal state (registers)
     int right_flank, left_flank; // rightBodyFlank_, leftBodyFlank_
     int nright, nleft;           // successful pushes
     int ninst, ngood, nbest, hcount, nrs;
-    int err; // 0 or LCB_ERR_CAPACITY
+    int err; // 0 or LCB_ERR_CAPACITY | (which cap << 8): 1 path vertices, 2 read-set intervals, 3 instances, 4 vote table
     bool collect; // count walk/occurrence/scan/score steps (diagnostics; off on the timed path)
     bool vote_clean; // the shared-memory vote table is all-empty (mpv_mid leaves it so, the general path does not)
     // shadow state (WarpSmem::s_*)
@@ -128,6 +185,26 @@ struct Ctx { // warp-uniform traversal state (registers)
     int snap_ninst, snap_ngood, snap_hcount, snap_right_flank, snap_right_vertex, snap_nright;
     Counters ct;
 };
+
+// one flag in registers instead of five capacities
+__device__ __forceinline__ int cap_inst(const Ctx &c) { return c.ar.big ? kBigInstMax : kInstMax; }
+__device__ __forceinline__ int cap_hash(const Ctx &c) { return c.ar.big ? kBigHashMax : kHashMax; }
+__device__ __forceinline__ int cap_path(const Ctx &c) { return c.ar.big ? kBigPathMax : kPathMax; }
+__device__ __forceinline__ int cap_vote(const Ctx &c) { return c.ar.big ? kBigVoteMax : kVoteMax; }
+__device__ __forceinline__ int cap_rs(const Ctx &c) { return c.ar.big ? kBigReadSetMax : kReadSetMax; }
+
+// bytes of one arena (per-warp or big slot)
+__host__ __device__ __forceinline__ size_t arena_stride_of(bool big)
+{
+    const size_t s = big ? WarpArena::o_end_Big : WarpArena::o_end_Small;
+    return (s + 255) & ~(size_t)255;
+}
+
+__device__ __forceinline__ void arena_bind(Ctx &c, unsigned char *p, bool big)
+{
+    c.ar.base = p;
+    c.ar.big = big;
+}
 
 __device__ __forceinline__ int ffs_lane(unsigned m) { return __ffs((int)m) - 1; }
 
@@ -183,7 +260,7 @@ __device__ __forceinline__ void ctx_reset_storage(Ctx &c)
 __device__ __forceinline__ void hash_clear(Ctx &c)
 {
     if (c.hbig) { // only the slots the path occupied
-        for (int i = c.lane; i < c.hcount; i += 32) c.ar.hash[c.ar.hslot[i]].x = 0;
+        for (int i = c.lane; i < c.hcount; i += 32) c.ar.hash()[c.ar.hslot()[i]].x = 0;
     } else {
         for (int i = c.lane; i < kHashSmem; i += 32) c.hash[i] = make_int2(0, 0);
     }
@@ -192,7 +269,7 @@ __device__ __forceinline__ void hash_clear(Ctx &c)
 }
 
 // move the shared-memory path hash into the (all-zero) arena table; returns nothing, caller repoints
-__device__ __noinline__ void hash_migrate(const int2 *src, int2 *dst, int *hslot, int lane)
+__device__ __noinline__ void hash_migrate(const int2 *src, int2 *dst, int *hslot, int lane, unsigned dmask)
 {
     int n = 0;
     for (int base = 0; base < kHashSmem; base += 32) {
@@ -200,8 +277,8 @@ __device__ __noinline__ void hash_migrate(const int2 *src, int2 *dst, int *hslot
         bool live = kv.x != 0;
         unsigned m = __ballot_sync(kFull, live);
         if (live) {
-            unsigned s = (hash_of(kv.x) >> 12) & (unsigned)(kHashMax - 1);
-            while (atomicCAS(&dst[s].x, 0, kv.x) != 0) s = (s + 1) & (unsigned)(kHashMax - 1);
+            unsigned s = (hash_of(kv.x) >> 12) & dmask;
+            while (atomicCAS(&dst[s].x, 0, kv.x) != 0) s = (s + 1) & dmask;
             dst[s].y = kv.y;
             hslot[n + __popc(m & ((1u << lane) - 1))] = (int)s;
         }
@@ -214,20 +291,20 @@ __device__ __noinline__ void hash_migrate(const int2 *src, int2 *dst, int *hslot
 __device__ __forceinline__ void hash_insert(Ctx &c, int key, int val)
 {
     if (!c.hbig && (c.hcount + 1) * 2 > kHashSmem) {
-        hash_migrate(c.hash, c.ar.hash, c.ar.hslot, c.lane);
-        c.hash = c.ar.hash;
-        c.hmask = kHashMax - 1;
+        hash_migrate(c.hash, c.ar.hash(), c.ar.hslot(), c.lane, (unsigned)(cap_hash(c) - 1));
+        c.hash = c.ar.hash();
+        c.hmask = cap_hash(c) - 1;
         c.hbig = true;
     }
-    if (c.hbig && c.hcount + 1 > kPathMax) {
-        c.err = LCB_ERR_CAPACITY;
+    if (c.hbig && c.hcount + 1 > cap_path(c)) {
+        c.err = LCB_ERR_CAPACITY | (1 << 8);
         return;
     }
     if (c.lane == 0) {
         unsigned s = (hash_of(key) >> 12) & (unsigned)c.hmask;
         while (c.hash[s].x != 0) s = (s + 1) & (unsigned)c.hmask;
         c.hash[s] = make_int2(key, val);
-        if (c.hbig) c.ar.hslot[c.hcount] = (int)s;
+        if (c.hbig) c.ar.hslot()[c.hcount] = (int)s;
     }
     c.hcount++;
     __syncwarp();
@@ -235,11 +312,11 @@ __device__ __forceinline__ void hash_insert(Ctx &c, int key, int val)
 
 __device__ __forceinline__ void rs_add(Ctx &c, int lo, int hi) // uniform
 {
-    if (c.nrs >= kReadSetMax) {
-        c.err = LCB_ERR_CAPACITY;
+    if (c.nrs >= cap_rs(c)) {
+        c.err = LCB_ERR_CAPACITY | (2 << 8);
         return;
     }
-    if (c.lane == 0) c.ar.rs[c.nrs] = make_int2(lo, hi);
+    if (c.lane == 0) c.ar.rs()[c.nrs] = make_int2(lo, hi);
     c.nrs++;
 }
 
@@ -253,26 +330,26 @@ __device__ __forceinline__ void inst_extend_reads(Inst &I, int lo, int hi) // si
 __device__ __noinline__ void inst_spill(const WarpSmem *sm, WarpArena ar, int ninst, int ngood, int nbest, int lane)
 {
     for (int i = lane; i < ninst; i += 32) {
-        ar.inst[i] = sm->inst[i];
-        ar.ord[i] = sm->ord[i];
+        ar.inst()[i] = sm->inst[i];
+        ar.ord()[i] = sm->ord[i];
     }
-    for (int i = lane; i < ngood; i += 32) ar.good[i] = sm->good[i];
-    for (int i = lane; i < nbest; i += 32) ar.best[i] = sm->best[i];
+    for (int i = lane; i < ngood; i += 32) ar.good()[i] = sm->good[i];
+    for (int i = lane; i < nbest; i += 32) ar.best()[i] = sm->best[i];
     __syncwarp();
 }
 
 __device__ __forceinline__ void inst_grow(Ctx &c)
 {
     if (c.icap != kInstSmem) {
-        c.err = LCB_ERR_CAPACITY;
+        c.err = LCB_ERR_CAPACITY | (3 << 8);
         return;
     }
     inst_spill(c.sm, c.ar, c.ninst, c.ngood, c.nbest, c.lane);
-    c.inst = c.ar.inst;
-    c.ord = c.ar.ord;
-    c.good = c.ar.good;
-    c.best = c.ar.best;
-    c.icap = kInstMax;
+    c.inst = c.ar.inst();
+    c.ord = c.ar.ord();
+    c.good = c.ar.good();
+    c.best = c.ar.best();
+    c.icap = cap_inst(c);
 }
 
 // position of the first instance (multiset order) whose key > `key`  (std::multiset::upper_bound)
@@ -336,11 +413,11 @@ __device__ __forceinline__ void path_clear(Ctx &c)
         bool live = lo <= hi;
         unsigned m = __ballot_sync(kFull, live);
         int n = __popc(m);
-        if (c.nrs + n > kReadSetMax) {
-            c.err = LCB_ERR_CAPACITY;
+        if (c.nrs + n > cap_rs(c)) {
+            c.err = LCB_ERR_CAPACITY | (2 << 8);
             break;
         }
-        if (live) c.ar.rs[c.nrs + __popc(m & ((1u << c.lane) - 1))] = make_int2(lo, hi);
+        if (live) c.ar.rs()[c.nrs + __popc(m & ((1u << c.lane) - 1))] = make_int2(lo, hi);
         c.nrs += n;
     }
     hash_clear(c);
@@ -356,7 +433,7 @@ __device__ __forceinline__ void path_clear(Ctx &c)
         __syncwarp();
         ctx_reset_storage(c);
     } else if (c.icap != kInstSmem) {
-        c.inst = c.ar.inst; // stay in the arena
+        c.inst = c.ar.inst(); // stay in the arena
     }
     c.ninst = c.ngood = 0;
     c.nright = c.nleft = 0;
@@ -408,7 +485,7 @@ __device__ __forceinline__ void restore_state(Ctx &c)
     } else { // same insertion order as Init + the pushes it replaces: origin, then every successful right edge
         hash_insert(c, c.origin, 0);
         for (int i = 0; i < c.snap_nright && !c.err; i++) {
-            const int4 e = c.ar.redge[i];
+            const int4 e = c.ar.redge()[i];
             hash_insert(c, e.x, e.w);
         }
     }
@@ -607,11 +684,11 @@ __device__ __forceinline__ bool push_parallel(Ctx &c, const bool BACK, int v, in
     c.ngood += __popc(gm);
     const unsigned om = __ballot_sync(kFull, outcome == 3);
     if (om) {
-        if (c.nrs + __popc(om) > kReadSetMax) {
-            c.err = LCB_ERR_CAPACITY;
+        if (c.nrs + __popc(om) > cap_rs(c)) {
+            c.err = LCB_ERR_CAPACITY | (2 << 8);
             return true;
         }
-        if (outcome == 3) c.ar.rs[c.nrs + __popc(om & lt)] = make_int2(q.flag, q.flag);
+        if (outcome == 3) c.ar.rs()[c.nrs + __popc(om & lt)] = make_int2(q.flag, q.flag);
         c.nrs += __popc(om);
     }
     __syncwarp();
@@ -753,11 +830,11 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
         }
     }
     if (BACK) {
-        if (c.nright >= kPathMax) {
-            c.err = LCB_ERR_CAPACITY;
+        if (c.nright >= cap_path(c)) {
+            c.err = LCB_ERR_CAPACITY | (1 << 8);
             return true;
         }
-        if (c.lane == 0) c.ar.redge[c.nright] = make_int4(v, len, e_ch_g | (e_ch_pos ? (int)0x80000000 : 0), dist);
+        if (c.lane == 0) c.ar.redge()[c.nright] = make_int4(v, len, e_ch_g | (e_ch_pos ? (int)0x80000000 : 0), dist);
         c.nright++;
         c.right_flank = dist;
         c.right_vertex = v;
@@ -840,7 +917,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
     unsigned *last = c.sm->vlast;
     int cap = kVoteSmem;
     c.vote_clean = false;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0;; attempt++) {
         for (int i = c.lane; i < cap; i += 32) tab[i] = make_int2(0, 0), last[i] = 0u;
         __syncwarp();
         int distinct = 0;
@@ -923,7 +1000,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
                             sl = (sl + 1) & (unsigned)(cap - 1);
                         }
                         atomicAdd((unsigned *)&tab[sl].y, weight);
-                        atomicMax(&last[sl], (qord << 20) | (unsigned)d);
+                        atomicMax(&last[sl], (qord << 16) | (unsigned)d); // list position < 65536; d <= -b + depth < 65536 (checked at create)
                     }
                     distinct += __popc(__ballot_sync(kFull, fresh));
                     { // loop-body executions and the epochs each walk depended on
@@ -950,11 +1027,12 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
             }
         }
         if (!overflow) break;
-        if (attempt == 1 || cap == kVoteMax) {
-            c.err = LCB_ERR_CAPACITY;
+        if (cap >= cap_vote(c)) {
+            c.err = LCB_ERR_CAPACITY | (4 << 8);
             return best;
         }
-        tab = c.ar.vote, last = c.ar.vlast, cap = kVoteMax; // start over with the big table
+        // start over with the arena's table: 8192 slots first, then (big arena slots only) up to eight times more each time
+        tab = c.ar.vote(), last = c.ar.vlast(), cap = cap == kVoteSmem ? kVoteMax : min(cap * 8, cap_vote(c));
     }
     __syncwarp();
     // ---- resolve
@@ -973,7 +1051,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
         bool pos = false;
         if (cand) {
             ev = last[base + c.lane];
-            const int q = (int)(ev >> 20);
+            const int q = (int)(ev >> 16);
             const Inst &I = c.inst[use_good ? (int)c.good[q] : q];
             pos = (I.flags & kPos) != 0;
             og = forward ? I.bg : I.fg;
@@ -988,7 +1066,7 @@ __device__ __forceinline__ Next most_popular_vertex(Ctx &c, bool forward, bool t
             best.vid = __shfl_sync(kFull, e.x, wl);
             best.og = __shfl_sync(kFull, og, wl);
             best.opos = __shfl_sync(kFull, (int)pos, wl) != 0;
-            best.d = (int)(emin & 0xFFFFFu);
+            best.d = (int)(emin & 0xFFFFu);
         }
     }
     return best;
@@ -1366,7 +1444,7 @@ __device__ __forceinline__ bool extend_path(Ctx &c, const bool FORWARD, int &bes
 }
 
 // ProcessVertex::Process (blocksfinder.h:228-310).  On return c.best[0..nbest) is bestInstance and
-// c.ar.rs[0..nrs) the read-set.
+// c.ar.rs()[0..nrs) the read-set.
 __device__ __forceinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
 {
     c.hbig = false;
@@ -1397,7 +1475,7 @@ __device__ __forceinline__ void process_seed(Ctx &c, int vid, unsigned char ch)
             } else { // big paths: re-play the best right part (blocksfinder.h:271-284)
                 path_init(c, vid, ch);
                 for (int i = 0; i < replay && !c.err; i++) {
-                    int4 e = c.ar.redge[i];
+                    int4 e = c.ar.redge()[i];
                     path_push(c, true, e.x, e.y, e.z & 0x7FFFFFFF, e.z < 0, 0, -1, -1);
                 }
                 if (c.err) return;

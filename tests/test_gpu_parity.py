@@ -215,3 +215,26 @@ def test_pool_overflow_retries_with_smaller_window(star_small, tmp_path, monkeyp
     orc, st, bf = _oracle_and_product(star_small, tmp_path, window=8192)
     _check_blocks(orc, bf, star_small)
     assert bf.stats["pool_restarts"] > 0 and bf.stats["windows"] > 2
+
+
+@pytest.mark.parametrize("which", ["star", "examples_k15"])
+def test_big_arena_rerun(star_small, examples, which):
+    """Seeds that outgrow the per-warp scratch arena are evaluated again in one of the big arena slots.  The
+    -DLCB_TINY_ARENA build of the same sources (64 instances / 512 path vertices / 512 read-set intervals per warp) makes
+    ordinary fixtures take that route all the time; the result must still be the oracle's."""
+    import json
+    import subprocess
+    import sys
+    from sibeliaz_b200.build import LIB_TINY
+    assert os.path.exists(LIB_TINY), "run __graft_entry__.build() first"
+    case = star_small if which == "star" else examples["k15"]
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "variant_runner.py"), case.graph, str(case.k), str(case.a), str(case.m),
+                        str(case.b)] + list(case.fastas), env=dict(os.environ, LCB_LIB_PATH=LIB_TINY), stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    v = json.loads(r.stdout.strip().splitlines()[-1])
+    assert v["library"] == LIB_TINY
+    assert v["same"] and v["n"] > 0
+    if which == "examples_k15":
+        assert v["big_arena_runs"] > 0
