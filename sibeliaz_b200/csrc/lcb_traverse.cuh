@@ -353,7 +353,34 @@ __device__ __forceinline__ void inst_grow(Ctx &c)
 }
 
 // position of the first instance (multiset order) whose key > `key`  (std::multiset::upper_bound)
+// `ord` is sorted by key at all times: an instance changes its key only to the position of an occurrence that was found
+// right next to it in this order (ChangeBack on a + instance / ChangeFront on a - instance take the multiset neighbour,
+// path.h:446-470,515-540), so the order the reference's tree relies on is the order of this array.  Big tables are
+// searched 32 ways per step (three dependent probes for 32768 instances) instead of front to back.
 __device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
+{
+    int lo = 0, hi = c.ninst; // every position < lo has key <= `key`, every position >= hi has key > `key`
+    while (hi - lo > 64) {
+        const int step = (hi - lo + 31) >> 5;
+        const int i = lo + (c.lane + 1) * step - 1;
+        const bool gt = i >= hi || c.inst[c.ord[i]].key > key;
+        const unsigned m = __ballot_sync(kFull, gt);
+        if (!m) return hi; // cannot happen (lane 31 probes hi - 1 or beyond), kept for safety
+        const int f = ffs_lane(m);
+        const int nhi = min(hi, lo + (f + 1) * step - 1);
+        lo += f * step;
+        hi = nhi;
+    }
+    for (int base = lo; base < hi; base += 32) {
+        int i = base + c.lane;
+        bool gt = i < hi && c.inst[c.ord[i]].key > key;
+        unsigned m = __ballot_sync(kFull, gt);
+        if (m) return base + ffs_lane(m);
+    }
+    return hi;
+}
+#ifdef LCB_CHECK_MPV
+__device__ __forceinline__ int ord_upper_bound_linear(const Ctx &c, int key)
 {
     for (int base = 0; base < c.ninst; base += 32) {
         int i = base + c.lane;
@@ -363,6 +390,7 @@ __device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
     }
     return c.ninst;
 }
+#endif
 
 // Instance(it, distance) + multiset insert + allInstance_.push_back   (path.h:82-91, :43, :492, :561)
 __device__ __forceinline__ void inst_insert(Ctx &c, int at, int g, bool pos, int v, unsigned bp, int dist, int flag_idx,
@@ -747,6 +775,9 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
             const int flag = __shfl_sync(kFull, q.flag, j);
             const int clo = __shfl_sync(kFull, q.clo, j), chi = __shfl_sync(kFull, q.chi, j);
             const int ub = ord_upper_bound(c, g);
+#ifdef LCB_CHECK_MPV
+            if (ub != ord_upper_bound_linear(c, g)) c.err = 91;
+#endif
             int hi_id = -1, lo_id = -1; // neighbours inside this chromosome's multiset
             if (ub < c.ninst) {
                 int id = c.ord[ub];
