@@ -157,7 +157,7 @@ def main():
             t_find += time_reference(dbg, fas, k, host_threads)[0]
         value = steps * n_records / t_find
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": min(warmup, 1),
-                "ms_per_step": 1000.0 * t_find / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64",
+                "ms_per_step": 1000.0 * t_find / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/int64",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads, "kind": "reference",
                                  "sample": "whole workload per step: unmodified reference sibeliaz-lcb -t %d, FindBlocks span" % host_threads},

@@ -690,6 +690,7 @@ struct lcb_ctx {
     unsigned char *d_seed_ch = nullptr;
     unsigned *d_seed_count = nullptr, *d_seed_res_pos = nullptr, *d_seed_res_chr = nullptr;
     unsigned long long *d_seed_rank = nullptr;
+    unsigned max_seed_count = 0; // count of the first (= most abundant) bundle
     // window
     Window win{};
     unsigned wmax = 0;
@@ -1432,6 +1433,8 @@ extern "C" int lcb_enumerate_seeds(lcb_ctx *ctx, uint64_t *n_seeds)
     ctx->d_seed_rank = srt.rank;
     ctx->d_seed_res_pos = srt.res_pos;
     ctx->d_seed_res_chr = srt.res_chr;
+    ctx->max_seed_count = 0;
+    if (S) CUDA_TRY(cudaMemcpyAsync(&ctx->max_seed_count, srt.count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream)); // sorted: count desc
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
@@ -1542,7 +1545,14 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     unsigned n0 = 0;                                     // this rank's work list 0 as left by the last validation
     unsigned delta = (unsigned)ctx->prm.window_init;     // seeds admitted per round (adapted)
     unsigned cap = (unsigned)ctx->prm.window_max;        // bound on the active set (halved by pool overflows)
+    // Bundles are sorted by abundance.  When the first ones have dozens of occurrences (repeat-rich input, small k) their
+    // speculative evaluations against the still empty epochs are the most expensive of the whole run and nearly all of
+    // them will be thrown away: admit no more than one wave of resident warps to begin with (the rule below takes over).
+    if (ctx->max_seed_count >= 32)
+        delta = std::min(delta, std::max(phase, (unsigned)(ctx->grid_traverse * kWarpsPerBlock) / phase * phase));
     bool drain = false;                                  // result pools half full: stop admitting until the set is empty
+    bool hold = false;                                   // heavy re-evaluations keep every warp busy: admit nothing this round
+    const double heavy_ms = getenv("LCB_HEAVY_MS") ? atof(getenv("LCB_HEAVY_MS")) : 20.0;
     while (c0 < S) {
         // ---- admission
         if (c0 == c1) { // nothing active: no pool entry is referenced any more
@@ -1552,7 +1562,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             ctx->st.windows++;
         }
         unsigned admit = 0;
-        if (!drain && c1 < S && c1 - c0 < cap) admit = std::min(std::min(delta, S - c1), cap - (c1 - c0));
+        if (!drain && !(hold && c1 > c0) && c1 < S && c1 - c0 < cap) admit = std::min(std::min(delta, S - c1), cap - (c1 - c0));
         if (admit) {
             k_admit<<<(admit + 255) / 256, 256, 0, ctx->stream>>>(c1, admit, R, me, n0, ctx->win, ctx->d_ctl);
             ctx->st.kernel_launches++;
@@ -1589,6 +1599,13 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             const double longest_ms = h.max_ns * 1e-6;
             if (ms < grow_below * longest_ms || ms < min_round_ms) next_delta = (unsigned)std::min<unsigned long long>((unsigned long long)ctx->prm.window_max, 2ull * delta);
             else if (ms > shrink_above * longest_ms && ms > 2 * min_round_ms) next_delta = std::max(phase, delta / 2 / phase * phase);
+            // Heavy evaluations (repeat-rich input): a warp that re-evaluates an invalidated seed is busy for about as long as
+            // the whole round, so fresh seeds are free only while warps are left over
+            if (longest_ms > heavy_ms) {
+                const unsigned warps = (unsigned)(ctx->grid_traverse * kWarpsPerBlock);
+                if (h.n0 + phase / R > warps) next_delta |= 0x80000000u; // hold
+                else next_delta = std::min(next_delta, std::max(phase, (warps - h.n0) * R / phase * phase));
+            }
         }
         unsigned first_dirty = h.first_dirty;
 #ifdef LCB_WITH_NCCL
@@ -1605,6 +1622,8 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             next_delta = local[4];
         }
 #endif
+        hold = (next_delta >> 31) != 0;
+        next_delta &= 0x7FFFFFFFu;
         if (trace_rounds)
             fprintf(stderr, "[round] %llu active [%u,%u) admitted %u traverse=%.3f ms longest=%.3f ms next: n0=%u dirty=%u first=%u delta=%u pools %.1f%% %.1f%%\n",
                     (unsigned long long)ctx->st.rounds, c0, c1, admit, ms, h.max_ns * 1e-6, h.n0, h.dirty, first_dirty, next_delta,

@@ -360,6 +360,7 @@ __device__ __forceinline__ void inst_grow(Ctx &c)
 __device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
 {
     int lo = 0, hi = c.ninst; // every position < lo has key <= `key`, every position >= hi has key > `key`
+#ifndef LCB_UB_OLD
     while (hi - lo > 64) {
         const int step = (hi - lo + 31) >> 5;
         const int i = lo + (c.lane + 1) * step - 1;
@@ -371,6 +372,7 @@ __device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
         lo += f * step;
         hi = nhi;
     }
+#endif
     for (int base = lo; base < hi; base += 32) {
         int i = base + c.lane;
         bool gt = i < hi && c.inst[c.ord[i]].key > key;
@@ -596,7 +598,7 @@ __device__ __forceinline__ bool scan_used(Ctx &c, int lo, int hi)
 // Path::PointPushBack / PointPushFront with their workers (path.h:430-602).  BACK: `v` = e.GetEndVertex(),
 // FRONT: `v` = e.GetStartVertex().  e_ch_g/e_ch_pos locate the junction whose char is e.GetChar();
 // e_other is e.GetEndVertex() for FRONT (the far-branch test `start1.GetVertexId() != e.GetEndVertex()`).
-// Fast path of the PointPush* workers: all occurrences of the pushed vertex (<= 32) lie on distinct chromosomes,
+// Fast path of the PointPush* workers (straight-line code, the common case): all occurrences of the pushed vertex (<= 32) lie on distinct chromosomes,
 // so they cannot see each other's effects inside this push; every lane evaluates one occurrence against the
 // pre-push state (multiset neighbours, Within, Compatible incl. its epoch scan), then the effects are applied in
 // occurrence order (goodInstance_ appends, new instances).  Returns false when the precondition does not hold.
@@ -629,11 +631,13 @@ __device__ __forceinline__ bool push_parallel(Ctx &c, const bool BACK, int v, in
         hi_cand = __shfl_sync(kFull, ordreg, hs), hi_key = __shfl_sync(kFull, keyreg, hs);
         lo_cand = __shfl_sync(kFull, ordreg, ls), lo_key = __shfl_sync(kFull, keyreg, ls);
     } else if (live) {
-        for (int p = 0; p < n; p++)
-            if (c.inst[c.ord[p]].key > q.g) {
-                ub = p;
-                break;
-            }
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (c.inst[c.ord[mid]].key > q.g) hi = mid;
+            else lo = mid + 1;
+        }
+        ub = lo;
         if (ub < n) hi_cand = c.ord[ub], hi_key = c.inst[hi_cand].key;
         if (ub > 0) lo_cand = c.ord[ub - 1], lo_key = c.inst[lo_cand].key;
     }
@@ -736,6 +740,172 @@ __device__ __forceinline__ bool push_parallel(Ctx &c, const bool BACK, int v, in
     return true;
 }
 
+// The PointPush* workers for a GROUP of occurrences of the pushed vertex: the longest prefix of [o0, o0 + cnt) (at most
+// 32) whose members cannot see each other's effects inside this push.  Every lane evaluates one occurrence against the
+// state before the group (multiset neighbours, Within, Compatible incl. its epoch scan), then the effects are applied in
+// occurrence order (goodInstance_ appends, new instances).  Returns the number of occurrences consumed (>= 1); the caller
+// goes on with the next group against the updated state.
+// Two occurrences X < Y (the list is sorted by (chr, idx), i.e. by g) interact only if X changes or creates a multiset
+// neighbour of Y: they fall into the same gap of the same chromosome's multiset, or X's upper neighbour is Y's lower one.
+// Upper bounds are monotone in g, so it is enough to compare every occurrence with its predecessor; occurrences on
+// different chromosomes (the common case) never interact.
+__device__ __forceinline__ int push_group(Ctx &c, const bool BACK, int v, int dist, unsigned o0, unsigned cnt, int e_ch_g,
+                                          bool e_ch_pos, int e_other)
+{
+    bool live = (unsigned)c.lane < cnt;
+    Occ q;
+    q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = -1 - c.lane, q.chi = 0, q.v_id = 0;
+    if (live) q = load_occurrence(c, o0 + (unsigned)c.lane, v);
+    // multiset neighbours of every occurrence: lane p holds the p-th instance (id, key) of the multiset order, every lane
+    // finds its upper_bound by shuffles instead of chasing ord[] -> inst[].key through shared memory
+    const int n = c.ninst;
+    int ub = n, hi_cand = -1, lo_cand = -1, hi_key = 0, lo_key = 0;
+    if (n <= 32) {
+        int ordreg = 0, keyreg = 0x7FFFFFFF;
+        if (c.lane < n) {
+            ordreg = c.ord[c.lane];
+            keyreg = c.inst[ordreg].key;
+        }
+        for (int p = n - 1; p >= 0; p--) {
+            const int kp = __shfl_sync(kFull, keyreg, p);
+            if (kp > q.g) ub = p;
+        }
+        const int hs = min(ub, 31), ls = max(ub - 1, 0);
+        hi_cand = __shfl_sync(kFull, ordreg, hs), hi_key = __shfl_sync(kFull, keyreg, hs);
+        lo_cand = __shfl_sync(kFull, ordreg, ls), lo_key = __shfl_sync(kFull, keyreg, ls);
+    } else if (live) { // every lane bisects the order on its own (`ord` is sorted by key, see ord_upper_bound)
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (c.inst[c.ord[mid]].key > q.g) hi = mid;
+            else lo = mid + 1;
+        }
+        ub = lo;
+        if (ub < n) hi_cand = c.ord[ub], hi_key = c.inst[hi_cand].key;
+        if (ub > 0) lo_cand = c.ord[ub - 1], lo_key = c.inst[lo_cand].key;
+    }
+#ifdef LCB_CHECK_MPV
+    { // self-check build: the bisection / shuffle search against a front-to-back scan
+        int ref = n;
+        if (live)
+            for (int p = n - 1; p >= 0; p--)
+                if (c.inst[c.ord[p]].key > q.g) ref = p;
+        if (__any_sync(kFull, live && ref != ub)) c.err = 91;
+    }
+#endif
+    int hi_id = -1, lo_id = -1;
+    if (live) {
+        if (ub < n && hi_key < q.chi) hi_id = hi_cand;
+        if (ub > 0 && lo_key >= q.clo) lo_id = lo_cand;
+    }
+    int take = (int)min(cnt, 32u);
+    { // cut the group in front of the first occurrence that could see the effects of its predecessor
+        const int prev_clo = __shfl_up_sync(kFull, q.clo, 1), prev_ub = __shfl_up_sync(kFull, ub, 1);
+        const int prev_hi = __shfl_up_sync(kFull, hi_id, 1);
+        const bool clash = live && c.lane > 0 && prev_clo == q.clo && (prev_ub == ub || (prev_hi >= 0 && prev_hi == lo_id));
+        const unsigned cm = __ballot_sync(kFull, clash);
+        if (cm) take = ffs_lane(cm);
+        live = c.lane < take;
+    }
+    int outcome = 0, cand = -1, scan_lo = 0, scan_hi = -1; // 0 skip, 1 extend, 2 new instance, 3 found used
+    if (live) {
+        bool within = false;
+        if (hi_id >= 0) {
+            int a = c.inst[hi_id].fg, b = c.inst[hi_id].bg;
+            within = q.g >= min(a, b) && q.g <= max(a, b);
+        }
+        if (!within) {
+            cand = (q.pos == BACK) ? lo_id : hi_id;
+            bool extend = false;
+            int cend_v = 0;
+            if (cand >= 0) {
+                const Inst &I = c.inst[cand];
+                const bool cpos = (I.flags & kPos) != 0;
+                const int cg = BACK ? I.bg : I.fg;
+                const unsigned cbp = BACK ? I.bbp : I.fbp;
+                const int cdist = BACK ? I.bdist : I.fdist;
+                cend_v = BACK ? I.bv : I.fv;
+                if (cpos == q.pos) {
+                    long long rd = BACK ? (long long)q.bp - (long long)cbp : (long long)cbp - (long long)q.bp;
+                    if (!q.pos) rd = -rd;
+                    const long long ad = BACK ? (long long)dist - cdist : (long long)cdist - dist;
+                    bool ok = rd >= 0;
+                    if (ok && (rd > c.pr.b || ad > c.pr.b)) {
+                        const int step = q.pos ? 1 : -1;
+                        ok = BACK ? (q.g == cg + step) : (cg == q.g + step);
+                        if (ok) {
+                            const int4 ce = __ldg(c.ix.rec + e_ch_g), cs = __ldg(c.ix.rec + (BACK ? cg : q.g));
+                            ok = (q.pos ? rec_next_ch(cs) : rec_prev_rc(cs)) == (e_ch_pos ? rec_next_ch(ce) : rec_prev_rc(ce));
+                            if (!BACK) ok = ok && I.fv == e_other;
+                        }
+                    }
+                    if (ok) {
+                        scan_lo = min(cg, q.g);
+                        scan_hi = max(cg, q.g) - 1;
+                        for (int f = scan_lo; f <= scan_hi && ok; f++) ok = !(__ldg(c.E + f) < c.thresh);
+                    }
+                    extend = ok;
+                }
+            }
+            outcome = (extend && cend_v != v) ? 1 : (!q.used ? 2 : 3);
+        }
+    }
+    if (c.collect) c.ct.scan += (unsigned long long)__reduce_add_sync(kFull, scan_lo <= scan_hi ? (unsigned)(scan_hi - scan_lo + 1) : 0u);
+    // ---- apply.  Candidates of different lanes are different instances (see the group rule above).
+    bool newly_good = false;
+    if (live && cand >= 0 && scan_lo <= scan_hi) inst_extend_reads(c.inst[cand], scan_lo, scan_hi);
+    if (outcome == 1) {
+        Inst &I = c.inst[cand];
+        const unsigned fin = BACK ? kBFin : kFFin;
+        if (!(I.flags & fin)) {
+            unsigned a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
+            const bool prev_good = (long long)a >= c.pr.m;
+            if (BACK) {
+                I.bg = q.g, I.bv = v, I.bbp = q.bp, I.bdist = dist;
+                if (q.pos) I.key = q.g;
+            } else {
+                I.fg = q.g, I.fv = v, I.fbp = q.bp, I.fdist = dist;
+                if (!q.pos) I.key = q.g;
+            }
+            a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
+            newly_good = !prev_good && (long long)a >= c.pr.m;
+            if (q.flag >= 0) inst_extend_reads(I, q.flag, q.flag);
+            if (q.used) I.flags |= fin;
+        }
+    }
+    const unsigned lt = (1u << c.lane) - 1u;
+    const unsigned gm = __ballot_sync(kFull, newly_good);
+    if (newly_good) c.good[c.ngood + __popc(gm & lt)] = (unsigned short)cand;
+    c.ngood += __popc(gm);
+    const unsigned om = __ballot_sync(kFull, outcome == 3);
+    if (om) {
+        if (c.nrs + __popc(om) > cap_rs(c)) {
+            c.err = LCB_ERR_CAPACITY | (2 << 8);
+            return take;
+        }
+        if (outcome == 3) c.ar.rs()[c.nrs + __popc(om & lt)] = make_int2(q.flag, q.flag);
+        c.nrs += __popc(om);
+    }
+    __syncwarp();
+    unsigned nm = __ballot_sync(kFull, outcome == 2);
+    while (nm) { // allInstance_ order == occurrence order
+        const int src = ffs_lane(nm);
+        nm &= nm - 1;
+        const int g = __shfl_sync(kFull, q.g, src);
+        const bool pos = __shfl_sync(kFull, (int)q.pos, src);
+        const unsigned bp = __shfl_sync(kFull, q.bp, src);
+        const int flag = __shfl_sync(kFull, q.flag, src);
+        const int clo = __shfl_sync(kFull, q.clo, src), chi = __shfl_sync(kFull, q.chi, src);
+        const int at = ord_upper_bound(c, g);
+#ifdef LCB_CHECK_MPV
+        if (at != ord_upper_bound_linear(c, g)) c.err = 91;
+#endif
+        inst_insert(c, at, g, pos, v, bp, dist, flag, clo, chi);
+        if (c.err) return take;
+    }
+    return take;
+}
+
 // occ_first/occ_count: the pushed vertex's occurrence range when the caller already holds it (rec[g].z/.w), else -1
 __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int len, int e_ch_g, bool e_ch_pos, int e_other,
                                           int occ_first, int occ_count)
@@ -761,6 +931,7 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
             else c.ct.push_ser++;
         }
     }
+#ifdef LCB_PUSH_OLD
     for (unsigned base = o0; base < o1 && !handled; base += 32) {
         unsigned o = base + (unsigned)c.lane;
         Occ q;
@@ -860,6 +1031,14 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
             __syncwarp();
         }
     }
+#else
+    // everything else (a chromosome that carries the vertex twice, more than 32 occurrences): conflict-free groups
+    for (unsigned o = o0; o < o1 && !handled;) {
+        const int took = push_group(c, BACK, v, dist, o, o1 - o, e_ch_g, e_ch_pos, e_other);
+        if (c.err) return true;
+        o += (unsigned)took;
+    }
+#endif
     if (BACK) {
         if (c.nright >= cap_path(c)) {
             c.err = LCB_ERR_CAPACITY | (1 << 8);
