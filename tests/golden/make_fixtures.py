@@ -38,6 +38,8 @@ def main():
     for f in fas:
         xz(f, os.path.join(ex, os.path.basename(f) + ".xz"))
     xz(os.path.join(REF, "sibeliaz_out", "blocks_coords.gff"), os.path.join(ex, "golden_k25_blocks_coords.gff.xz"))
+    # the alignment stage's golden: 1332 MAF paragraphs made by the reference pipeline (spoa per block)
+    xz(os.path.join(REF, "sibeliaz_out", "alignment.maf"), os.path.join(ex, "golden_k25_alignment.maf.xz"))
     with tempfile.TemporaryDirectory() as tmp:
         for k in (25, 15):
             dbg = run_twopaco(fas, k, os.path.join(tmp, "k%d.dbg" % k), threads=1)

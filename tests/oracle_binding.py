@@ -12,6 +12,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liblcb_oracle.so")
 REF_LCB = os.path.join(ORACLE_DIR, "_ref", "sibeliaz-lcb-ref")
 REF_TWOPACO = os.path.join(ORACLE_DIR, "_ref", "twopaco")
+REF_SPOA = os.path.join(ORACLE_DIR, "_ref", "spoa-ref")  # the reference's spoa library behind oracle/spoa_driver.cpp
 
 _lib = None
 
@@ -163,3 +164,34 @@ def canonical_junctions(path, out=None):
         raise RuntimeError("cannot canonicalise " + path)
     with open(out, "rb") as f:
         return f.read()
+
+
+def maf_paragraphs(path_or_text, is_text=False):
+    """{key: paragraph} of a MAF file; key = the (name, start, length, strand) tuples of its rows, paragraph = its `s` lines."""
+    text = path_or_text if is_text else open(path_or_text).read()
+    out, cur = {}, None
+    for line in text.splitlines():
+        if line.startswith("a"):
+            cur = []
+        elif line.startswith("s ") and cur is not None:
+            cur.append(line)
+        elif cur:
+            out[tuple(tuple(x.split(" ")[1:5]) for x in cur)] = cur
+            cur = None
+    if cur:
+        out[tuple(tuple(x.split(" ")[1:5]) for x in cur)] = cur
+    return out
+
+
+def reference_global_alignment(outdir, cmd, chunk_files=None):
+    """The wrapper's global_alignment() (SibeliaZ-LCB/sibeliaz:118-134) with the reference's spoa library: every line of
+    every <i>.tmp chunk is one block, aligned by `spoa -l 1 -r 1 -e -8`; the per-chunk results are concatenated in the
+    C-locale order of the file names behind the three header lines.  Returns the MAF text.  `chunk_files` restricts the
+    run to some chunk files (tests)."""
+    names = sorted(n for n in os.listdir(outdir) if n.endswith(".tmp")) if chunk_files is None else list(chunk_files)
+    text = "##maf version=1\n# sibeliaz v1.2.7 \n# cmd=%s\n" % cmd
+    for n in sorted(names):  # Python compares str by code point == LC_ALL=C for these ASCII names
+        r = subprocess.run([REF_SPOA, "--chunk", os.path.join(outdir, n), "-l", "1", "-r", "1", "-e", "-8"], check=True,
+                           stdout=subprocess.PIPE, text=True)
+        text += r.stdout
+    return text
