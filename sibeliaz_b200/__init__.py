@@ -430,3 +430,93 @@ class FusedStorage:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Alignment stage (include/sibeliaz_align.h): `spoa` per block -> alignment.maf, on the GPU
+class AlignParams(C.Structure):
+    _fields_ = [("match", C.c_int), ("mismatch", C.c_int), ("gap", C.c_int), ("device", C.c_int)]
+
+
+class AlignStats(C.Structure):
+    # keep in sync with lca_stats in include/sibeliaz_align.h
+    _fields_ = [("n_blocks", C.c_uint64), ("n_copies", C.c_uint64), ("n_bases", C.c_uint64), ("cells", C.c_uint64),
+                ("blocks_level", C.c_uint64 * 3), ("kernel_launches", C.c_uint64), ("ms_kernels", C.c_double),
+                ("ms_total", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "blocks_level"}
+        d["blocks_level"] = list(self.blocks_level)
+        return d
+
+
+def _align_lib():
+    lib = load_library()
+    if not getattr(lib, "_lca_ready", False):
+        lib.lca_default_params.argtypes = [C.POINTER(AlignParams)]
+        lib.lca_default_params.restype = None
+        lib.lca_align.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(AlignParams),
+                                  C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+        lib.lca_rows.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint64))]
+        lib.lca_rows.restype = C.POINTER(C.c_uint8)
+        lib.lca_block_columns.argtypes = [C.c_void_p, C.c_uint32]
+        lib.lca_block_columns.restype = C.c_uint32
+        lib.lca_get_stats.argtypes = [C.c_void_p, C.POINTER(AlignStats)]
+        lib.lca_get_stats.restype = None
+        lib.lca_free.argtypes = [C.c_void_p]
+        lib.lca_free.restype = None
+        lib.lca_align_chunk_files.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.POINTER(AlignParams),
+                                              C.POINTER(AlignStats), C.c_char_p, C.c_size_t]
+        lib._lca_ready = True
+    return lib
+
+
+def align_blocks(blocks, match=5, mismatch=-4, gap=-8, device=0):
+    """MSA rows of every block (reference: `spoa <block.fa> -l 1 -r 1 -e -8`, one run per block).
+    blocks: list of lists of bytes (the copies of a block in file order).  Returns (rows, stats): rows[b][k] = bytes."""
+    lib = _align_lib()
+    copies = [c for b in blocks for c in b]
+    seq = np.frombuffer(b"".join(copies), dtype=np.uint8) if copies else np.zeros(0, np.uint8)
+    copy_off = np.zeros(len(copies) + 1, np.uint64)
+    if copies:
+        copy_off[1:] = np.cumsum([len(c) for c in copies])
+    block_off = np.zeros(len(blocks) + 1, np.uint32)
+    if blocks:
+        block_off[1:] = np.cumsum([len(b) for b in blocks])
+    p = AlignParams()
+    lib.lca_default_params(C.byref(p))
+    p.match, p.mismatch, p.gap, p.device = match, mismatch, gap, device
+    res, err = C.c_void_p(), C.create_string_buffer(1024)
+    rc = lib.lca_align(seq.ctypes.data, copy_off.ctypes.data, len(copies), block_off.ctypes.data, len(blocks), C.byref(p), C.byref(res),
+                       err, len(err))
+    if rc:
+        raise LcbError(rc, err.value.decode(errors="replace"))
+    try:
+        roff = C.POINTER(C.c_uint64)()
+        rows = lib.lca_rows(res, C.byref(roff))
+        off = np.ctypeslib.as_array(roff, shape=(len(copies) + 1,)).copy() if copies else np.zeros(1, np.uint64)
+        total = int(off[-1])
+        flat = bytes(np.ctypeslib.as_array(rows, shape=(total,))) if total else b""
+        out, c = [], 0
+        for b in blocks:
+            out.append([flat[int(off[c + k]):int(off[c + k + 1])] for k in range(len(b))])
+            c += len(b)
+        st = AlignStats()
+        lib.lca_get_stats(res, C.byref(st))
+        return out, st.as_dict()
+    finally:
+        lib.lca_free(res)
+
+
+def global_alignment(chunk_files, cmd, out_maf, match=5, mismatch=-4, gap=-8, device=0):
+    """The wrapper's global_alignment() (SibeliaZ-LCB/sibeliaz:118-134): <i>.tmp chunk files -> alignment.maf."""
+    lib = _align_lib()
+    p = AlignParams()
+    lib.lca_default_params(C.byref(p))
+    p.match, p.mismatch, p.gap, p.device = match, mismatch, gap, device
+    files = (C.c_char_p * len(chunk_files))(*[os.fsencode(f) for f in chunk_files])
+    st, err = AlignStats(), C.create_string_buffer(1024)
+    rc = lib.lca_align_chunk_files(files, len(chunk_files), cmd.encode(), os.fsencode(out_maf), C.byref(p), C.byref(st), err, len(err))
+    if rc:
+        raise LcbError(rc, err.value.decode(errors="replace"))
+    return st.as_dict()

@@ -16,8 +16,8 @@ LIB = os.path.join(LIBDIR, "libsibeliaz_lcb.so")
 LIB_TINY = os.path.join(LIBDIR, "libsibeliaz_lcb_tiny.so")
 CLI = os.path.join(BINDIR, "sibeliaz-lcb")
 CLI_GRAPH = os.path.join(BINDIR, "twopaco")
-SOURCES = ("lcb_device.cu", "lcb_host.cpp", "graph_device.cu", "graph_host.cpp")
-HEADERS = ("lcb_traverse.cuh", "device_prims.cuh", "host_common.h", "graph_internal.h")
+SOURCES = ("lcb_device.cu", "lcb_host.cpp", "graph_device.cu", "graph_host.cpp", "poa_device.cu")
+HEADERS = ("lcb_traverse.cuh", "device_prims.cuh", "host_common.h", "graph_internal.h", "poa_core.cuh")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-pthread"]
@@ -89,7 +89,7 @@ def build(force=False, verbose=False):
     os.makedirs(BINDIR, exist_ok=True)
     inc = os.path.join(ROOT, "include")
     srcs = [os.path.join(CSRC, f) for f in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(inc, "sibeliaz_lcb.h"), os.path.join(inc, "sibeliaz_graph.h"), __file__]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(inc, "sibeliaz_lcb.h"), os.path.join(inc, "sibeliaz_graph.h"), os.path.join(inc, "sibeliaz_align.h"), __file__]
     nvcc = _nvcc()
     if force or _newer(LIB, deps):
         cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-ccbin", _host_cxx(), "-I", inc, "-shared", "-o", LIB] + srcs

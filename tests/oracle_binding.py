@@ -12,6 +12,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liblcb_oracle.so")
 REF_LCB = os.path.join(ORACLE_DIR, "_ref", "sibeliaz-lcb-ref")
 REF_TWOPACO = os.path.join(ORACLE_DIR, "_ref", "twopaco")
+POA_ORACLE = os.path.join(ORACLE_DIR, "poa_oracle")  # CPU restatement of the alignment stage (oracle/poa_oracle.cpp)
 REF_SPOA = os.path.join(ORACLE_DIR, "_ref", "spoa-ref")  # the reference's spoa library behind oracle/spoa_driver.cpp
 
 _lib = None
@@ -195,3 +196,18 @@ def reference_global_alignment(outdir, cmd, chunk_files=None):
                            stdout=subprocess.PIPE, text=True)
         text += r.stdout
     return text
+
+
+def poa_oracle_text(chunk_file):
+    """MAF paragraphs of every block of one chunk file, by the CPU restatement (oracle/poa_oracle.cpp)."""
+    if not os.path.exists(POA_ORACLE):
+        build_oracle()
+    return subprocess.run([POA_ORACLE, "--chunk", chunk_file], check=True, stdout=subprocess.PIPE, text=True).stdout
+
+
+def write_chunk(path, blocks):
+    """An LCB chunk file (blocksfinder.h:533-582) from [[(header, sequence), ...], ...]; header e.g. 'g0.chr1;10;4;+;100'."""
+    with open(path, "w") as f:
+        for b in blocks:
+            f.write("".join("> %s@%s@" % (h, s) for h, s in b) + "\n")
+    return path

@@ -36,3 +36,52 @@ def test_spoa_reference_reproduces_golden_paragraphs(examples, tmp_path):
             assert rows == golden[key]
             checked += 1
     assert checked >= 30 and checked >= len(mine) - 2
+
+
+SLICE = (3, 7, 11, 42, 100, 200, 255)
+
+
+@pytest.fixture(scope="module")
+def example_chunks(examples, tmp_path_factory):
+    case = examples["k25"]
+    orc = Oracle(case.graph, case.fastas, case.k, case.a)
+    orc.find_blocks(case.m, case.b)
+    out = str(tmp_path_factory.mktemp("lcb_chunks"))
+    orc.generate_output(out, True, 256, case.m)
+    return out
+
+
+@needs_spoa
+def test_poa_restatement_equals_reference_spoa(example_chunks):
+    """oracle/poa_oracle.cpp (the restatement a device kernel is checked against) == the reference's spoa library,
+    byte for byte (all 1350 blocks of the examples agree; the test runs a slice)."""
+    from oracle_binding import poa_oracle_text
+    import subprocess
+    for i in SLICE:
+        f = os.path.join(example_chunks, "%d.tmp" % i)
+        ref = subprocess.run([REF_SPOA, "--chunk", f, "-l", "1", "-r", "1", "-e", "-8"], check=True, stdout=subprocess.PIPE, text=True).stdout
+        assert poa_oracle_text(f) == ref and ref.count("\na\n") >= 4
+
+
+def test_poa_core_host_build_equals_restatement(example_chunks, tmp_path):
+    """The product's POA core (sibeliaz_b200/csrc/poa_core.cuh: graph update, topological sort, traceback, MSA -- the code the
+    kernel runs, row recurrence in scalar form) compiled for the host == the restatement, at every arena level, and on edge
+    cases (one copy, one character, unequal lengths, other alphabets)."""
+    import subprocess
+    from oracle_binding import poa_oracle_text, write_chunk
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "poa_core_host")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(here, "poa_core_host.cpp")], check=True)
+    edge = write_chunk(str(tmp_path / "edge.tmp"), [
+        [("a;0;4;+;9", "ACGT")],
+        [("a;0;1;+;9", "A"), ("b;0;1;+;9", "C"), ("c;0;1;+;9", "A")],
+        [("a;0;8;+;9", "ACGTACGT"), ("b;0;3;+;9", "CGT"), ("c;0;12;-;30", "TTACGTACGTTT"), ("d;0;8;+;9", "ACGAACGT")],
+        [("a;0;6;+;9", "acgtNN"), ("b;0;6;+;9", "ACGTNN"), ("c;0;7;+;9", "acgRtNN")],
+        [("a;0;5;+;9", "AAAAA"), ("b;0;5;+;9", "TTTTT"), ("c;0;5;+;9", "AATTA"), ("d;0;5;+;9", "TTAAT"), ("e;0;5;+;9", "ATATA")],
+    ])
+    files = [edge] + [os.path.join(example_chunks, "%d.tmp" % i) for i in SLICE[:4]]
+    for f in files:
+        want = poa_oracle_text(f)
+        for level in (0, 2):
+            got = subprocess.run([exe, "--chunk", f, "--level", str(level)], check=True, stdout=subprocess.PIPE, text=True).stdout
+            assert got == want, (f, level)

@@ -28,6 +28,10 @@ def test_library_exports_every_declared_symbol():
     gdecl = set(re.findall(r"\b(lcg_[a-z_0-9]+)\s*\(", ghdr))
     assert len(gdecl) >= 7
     assert not [s for s in sorted(gdecl) if not hasattr(lib, s)]
+    ahdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "sibeliaz_align.h")).read(), flags=re.S)
+    adecl = set(re.findall(r"\b(lca_[a-z_0-9]+)\s*\(", ahdr))
+    assert len(adecl) >= 7
+    assert not [s for s in sorted(adecl) if not hasattr(lib, s)]
     assert b"1.2.7" in ctypes.cast(sb.load_library().lcb_version(), ctypes.c_char_p).value
 
 
