@@ -391,6 +391,7 @@ class JunctionGraph:
 
 
 GRAPH_CLI_PATH = os.path.join(_HERE, "bin", "twopaco")
+ALIGN_CLI_PATH = os.path.join(_HERE, "bin", "sibeliaz-align")
 
 
 class FusedStorage:

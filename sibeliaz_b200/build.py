@@ -16,6 +16,7 @@ LIB = os.path.join(LIBDIR, "libsibeliaz_lcb.so")
 LIB_TINY = os.path.join(LIBDIR, "libsibeliaz_lcb_tiny.so")
 CLI = os.path.join(BINDIR, "sibeliaz-lcb")
 CLI_GRAPH = os.path.join(BINDIR, "twopaco")
+CLI_ALIGN = os.path.join(BINDIR, "sibeliaz-align")
 SOURCES = ("lcb_device.cu", "lcb_host.cpp", "graph_device.cu", "graph_host.cpp", "poa_device.cu")
 HEADERS = ("lcb_traverse.cuh", "device_prims.cuh", "host_common.h", "graph_internal.h", "poa_core.cuh")
 
@@ -111,6 +112,10 @@ def build(force=False, verbose=False):
     graph_src = os.path.join(CSRC, "twopaco_main.cpp")
     if os.path.exists(graph_src) and (force or _newer(CLI_GRAPH, [graph_src, LIB])):
         _run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, graph_src, "-o", CLI_GRAPH, "-L", LIBDIR, "-lsibeliaz_lcb",
+              "-Wl,-rpath,$ORIGIN/../lib"])
+    align_src = os.path.join(CSRC, "sibeliaz_align_main.cpp")
+    if os.path.exists(align_src) and (force or _newer(CLI_ALIGN, [align_src, LIB])):
+        _run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, align_src, "-o", CLI_ALIGN, "-L", LIBDIR, "-lsibeliaz_lcb",
               "-Wl,-rpath,$ORIGIN/../lib"])
     return LIB
 

@@ -368,41 +368,60 @@ POA_HD void dp_init(Work &w, const Params &pr, uint32_t len, int lane, int lanes
 }
 
 #if defined(__CUDA_ARCH__)
-// One row of H (sisd_alignment_engine.cpp:318-352), the whole warp: lane l owns column base + l + 1.
+// One row of H (sisd_alignment_engine.cpp:318-352), the whole warp.  A step covers 4 x 32 columns: lane l owns columns
+// base + 32 k + l + 1 (k = 0..3), so that the loads of four chunks are in flight together; the four max-scans then run one
+// after the other because each needs the carry of the one before.  The first two predecessor rows are kept as pointers
+// (almost every node has one or two in-edges), further ones are reached through the edge list.
 __device__ __forceinline__ void dp_row(Work &w, const Params &pr, const uint8_t *s, uint32_t len, uint32_t i, int lane)
 {
     const uint64_t W = (uint64_t)len + 1;
     const int it = w.rank_to_node[i - 1];
     const uint8_t ch = w.decoder[w.code[it]];
     int32_t *row = w.H + (uint64_t)i * W;
+    const int e0 = w.in_first[it];
+    const int e1 = e0 >= 0 ? w.edge_next_in[e0] : -1;
+    const int e2 = e1 >= 0 ? w.edge_next_in[e1] : -1;
+    const int32_t *pred0 = e0 >= 0 ? w.H + ((uint64_t)w.rank[w.edge_tail[e0]] + 1) * W : w.H; // no predecessor: row 0 (:321-323)
+    const int32_t *pred1 = e1 >= 0 ? w.H + ((uint64_t)w.rank[w.edge_tail[e1]] + 1) * W : nullptr;
     int32_t carry = row[0]; // H[i][base] - base * g with base = 0
-    for (uint32_t base = 0; base < len; base += 32) {
-        const uint32_t j = base + (uint32_t)lane + 1;
-        const bool on = j <= len;
-        int32_t M = kNegInf;
-        if (on) {
-            const int32_t sc = s[j - 1] == ch ? pr.m : pr.n;
-            if (w.in_first[it] < 0) { // no predecessor: row 0 (:321-323)
-                const int32_t a = w.H[j - 1] + sc, b = w.H[j] + pr.g;
+    for (uint32_t base = 0; base < len; base += 128) {
+        int32_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = base + 32u * (uint32_t)k + (uint32_t)lane + 1;
+            int32_t M = kNegInf;
+            if (j <= len) {
+                const int32_t sc = s[j - 1] == ch ? pr.m : pr.n;
+                const int32_t a = pred0[j - 1] + sc, b = pred0[j] + pr.g;
                 M = a > b ? a : b;
-            } else {
-                for (int e = w.in_first[it]; e >= 0; e = w.edge_next_in[e]) {
-                    const int32_t *pred = w.H + ((uint64_t)w.rank[w.edge_tail[e]] + 1) * W;
-                    const int32_t a = pred[j - 1] + sc, b = pred[j] + pr.g;
-                    const int32_t v = a > b ? a : b;
-                    M = v > M ? v : M;
+                if (pred1) {
+                    const int32_t a1 = pred1[j - 1] + sc, b1 = pred1[j] + pr.g;
+                    const int32_t v1 = a1 > b1 ? a1 : b1;
+                    M = v1 > M ? v1 : M;
+                    for (int e = e2; e >= 0; e = w.edge_next_in[e]) {
+                        const int32_t *pred = w.H + ((uint64_t)w.rank[w.edge_tail[e]] + 1) * W;
+                        const int32_t a2 = pred[j - 1] + sc, b2 = pred[j] + pr.g;
+                        const int32_t v2 = a2 > b2 ? a2 : b2;
+                        M = v2 > M ? v2 : M;
+                    }
                 }
+                M -= (int32_t)j * pr.g;
             }
+            x[k] = M;
         }
         // H[j] = max(M[j], H[j-1] + g)  <=>  H[j] - j g = max(M[j] - j g, H[j-1] - (j-1) g): inclusive max-scan + carry
-        int32_t x = on ? M - (int32_t)j * pr.g : kNegInf;
-        for (int d = 1; d < 32; d <<= 1) {
-            const int32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-            if (lane >= d) x = y > x ? y : x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = base + 32u * (uint32_t)k + (uint32_t)lane + 1;
+            int32_t v = x[k];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                if (lane >= d) v = y > v ? y : v;
+            }
+            v = v > carry ? v : carry;
+            if (j <= len) row[j] = v + (int32_t)j * pr.g;
+            carry = __shfl_sync(0xFFFFFFFFu, v, 31);
         }
-        x = x > carry ? x : carry;
-        if (on) row[j] = x + (int32_t)j * pr.g;
-        carry = __shfl_sync(0xFFFFFFFFu, x, 31);
     }
     __syncwarp();
 }

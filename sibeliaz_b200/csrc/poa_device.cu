@@ -201,13 +201,15 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
     // one launch over `list` (block ids) at `level` with arenas of `stride` bytes
     auto launch = [&](const std::vector<uint32_t> &list, int level, uint64_t stride) {
         uint64_t warps = std::min<uint64_t>(std::min<uint64_t>(list.size(), resident_warps), std::max<uint64_t>(budget / stride, 1));
-        const unsigned ctas = (unsigned)((warps + kPoaWarps - 1) / kPoaWarps);
+        // never more arenas than the budget holds: whole CTAs, or one partial CTA
+        const unsigned ctas = warps >= (uint64_t)kPoaWarps ? (unsigned)(warps / kPoaWarps) : 1u;
+        const unsigned threads = warps >= (uint64_t)kPoaWarps ? kPoaWarps * 32u : (unsigned)warps * 32u;
         DevBuf<uint8_t> arena;
-        arena.alloc((size_t)ctas * kPoaWarps * stride);
+        arena.alloc((size_t)ctas * (threads / 32) * stride);
         CU(cudaMemcpyAsync(d_list.p, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         CU(cudaMemsetAsync(&d_q.p->head, 0, sizeof(unsigned), stream));
         CU(cudaEventRecord(ev0, stream));
-        k_poa<<<ctas, kPoaWarps * 32, 0, stream>>>(d_seq.p, d_copy_off.p, d_block_off.p, d_list.p, (unsigned)list.size(), level, arena.p,
+        k_poa<<<ctas, threads, 0, stream>>>(d_seq.p, d_copy_off.p, d_block_off.p, d_list.p, (unsigned)list.size(), level, arena.p,
                                                    (unsigned long long)stride, pr, d_q.p, d_rows.p, (unsigned long long)rows_cap,
                                                    d_row_off.p, d_cols.p, d_status.p);
         CU(cudaEventRecord(ev1, stream));
@@ -228,7 +230,7 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
         std::vector<uint32_t> next;
         std::sort(todo.begin(), todo.end(), [&](uint32_t a, uint32_t b2) { return need(a, level) < need(b2, level); });
         size_t at = 0;
-        uint64_t class_cap = 16ull << 20;
+        uint64_t class_cap = 1ull << 20;
         while (at < todo.size()) {
             while (need(todo[at], level) > class_cap) class_cap *= 4;
             size_t end = at;
@@ -290,6 +292,7 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
             o += res.cols[b];
         }
     res.row_off[n_copies] = o;
+    res.rows.resize((size_t)o);
     res.st.ms_kernels = ms_kernels;
     res.st.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 }

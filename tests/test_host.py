@@ -135,3 +135,17 @@ def test_product_fails_loudly_without_gpu(star_small):
     with pytest.raises(sb.LcbError) as e:
         sb.BlocksFinder(st, star_small.k).find_blocks(50, 200)
     assert e.value.code == 4 and "no CPU fallback" in str(e.value)
+
+
+def test_align_cli_error_contract(tmp_path):
+    """sibeliaz-align: rc 1 + `error: <message>` on stderr (like sibeliaz.cpp:145-154); without a GPU it must refuse, not
+    fall back to a CPU path."""
+    import subprocess
+    r = subprocess.run([sb.ALIGN_CLI_PATH, "--cmd", "x"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("error: missing -o")
+    import torch
+    if not torch.cuda.is_available():
+        chunk = tmp_path / "0.tmp"
+        chunk.write_text("> a;0;4;+;9@ACGT@> b;0;4;+;9@ACGA@\n")
+        r = subprocess.run([sb.ALIGN_CLI_PATH, "--cmd", "x", "-o", str(tmp_path / "a.maf"), str(chunk)], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr and not (tmp_path / "a.maf").exists()
