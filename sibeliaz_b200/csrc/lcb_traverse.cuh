@@ -360,7 +360,6 @@ __device__ __forceinline__ void inst_grow(Ctx &c)
 __device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
 {
     int lo = 0, hi = c.ninst; // every position < lo has key <= `key`, every position >= hi has key > `key`
-#ifndef LCB_UB_OLD
     while (hi - lo > 64) {
         const int step = (hi - lo + 31) >> 5;
         const int i = lo + (c.lane + 1) * step - 1;
@@ -372,7 +371,6 @@ __device__ __forceinline__ int ord_upper_bound(const Ctx &c, int key)
         lo += f * step;
         hi = nhi;
     }
-#endif
     for (int base = lo; base < hi; base += 32) {
         int i = base + c.lane;
         bool gt = i < hi && c.inst[c.ord[i]].key > key;
@@ -931,114 +929,12 @@ __device__ __forceinline__ bool path_push(Ctx &c, const bool BACK, int v, int le
             else c.ct.push_ser++;
         }
     }
-#ifdef LCB_PUSH_OLD
-    for (unsigned base = o0; base < o1 && !handled; base += 32) {
-        unsigned o = base + (unsigned)c.lane;
-        Occ q;
-        q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = 0, q.chi = 0;
-        if (o < o1) q = load_occurrence(c, o, v);
-        int cnt = (int)min(32u, o1 - base);
-        for (int j = 0; j < cnt; j++) {
-            const int g = __shfl_sync(kFull, q.g, j);
-            const bool pos = __shfl_sync(kFull, (int)q.pos, j);
-            const bool used = __shfl_sync(kFull, (int)q.used, j);
-            const unsigned bp = __shfl_sync(kFull, q.bp, j);
-            const int flag = __shfl_sync(kFull, q.flag, j);
-            const int clo = __shfl_sync(kFull, q.clo, j), chi = __shfl_sync(kFull, q.chi, j);
-            const int ub = ord_upper_bound(c, g);
-#ifdef LCB_CHECK_MPV
-            if (ub != ord_upper_bound_linear(c, g)) c.err = 91;
-#endif
-            int hi_id = -1, lo_id = -1; // neighbours inside this chromosome's multiset
-            if (ub < c.ninst) {
-                int id = c.ord[ub];
-                if (c.inst[id].key < chi) hi_id = id;
-            }
-            if (ub > 0) {
-                int id = c.ord[ub - 1];
-                if (c.inst[id].key >= clo) lo_id = id;
-            }
-            if (hi_id >= 0) { // Instance::Within, path.h:170-175
-                int a = c.inst[hi_id].fg, b = c.inst[hi_id].bg;
-                if (g >= min(a, b) && g <= max(a, b)) continue;
-            }
-            // BACK: + occurrences look at the predecessor, - at upper_bound; FRONT: the other way round
-            const int cand = (pos == BACK) ? lo_id : hi_id;
-            bool extend = false;
-            int scan_lo = 0, scan_hi = -1;
-            if (cand >= 0) { // Path::Compatible (path.h:380-428), pure tests first, epoch scan last
-                const Inst I = c.inst[cand];
-                const bool cpos = (I.flags & kPos) != 0;
-                const int cg = BACK ? I.bg : I.fg;
-                const unsigned cbp = BACK ? I.bbp : I.fbp;
-                const int cdist = BACK ? I.bdist : I.fdist;
-                if (cpos == pos) {
-                    long long rd = BACK ? (long long)bp - (long long)cbp : (long long)cbp - (long long)bp;
-                    if (!pos) rd = -rd;
-                    const long long ad = BACK ? (long long)dist - cdist : (long long)cdist - dist;
-                    bool ok = rd >= 0;
-                    if (ok && (rd > c.pr.b || ad > c.pr.b)) {
-                        // only the exact next junction along the strand may continue the instance
-                        const int step = pos ? 1 : -1;
-                        const bool adjacent = BACK ? (g == cg + step) : (cg == g + step);
-                        ok = adjacent;
-                        if (ok) {
-                            const int4 ce = __ldg(c.ix.rec + e_ch_g), cs = __ldg(c.ix.rec + (BACK ? cg : g));
-                            unsigned char ech = e_ch_pos ? rec_next_ch(ce) : rec_prev_rc(ce);
-                            unsigned char sch = pos ? rec_next_ch(cs) : rec_prev_rc(cs);
-                            ok = sch == ech;
-                            if (!BACK) ok = ok && I.fv == e_other;
-                        }
-                    }
-                    if (ok) {
-                        scan_lo = min(cg, g);
-                        scan_hi = max(cg, g) - 1;
-                        ok = !scan_used(c, scan_lo, scan_hi);
-                    }
-                    extend = ok;
-                }
-            }
-            const int cend_v = cand >= 0 ? (BACK ? c.inst[cand].bv : c.inst[cand].fv) : 0;
-            if (cand >= 0 && scan_lo <= scan_hi && c.lane == 0) inst_extend_reads(c.inst[cand], scan_lo, scan_hi);
-            if (extend && cend_v != v) {
-                const unsigned fin = BACK ? kBFin : kFFin;
-                if (c.lane == 0 && !(c.inst[cand].flags & fin)) {
-                    Inst &I = c.inst[cand];
-                    unsigned a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
-                    bool prev_good = (long long)a >= c.pr.m; // IsGoodInstance, path.h:645-648
-                    if (BACK) { // ChangeBack, path.h:124-133
-                        I.bg = g, I.bv = v, I.bbp = bp, I.bdist = dist;
-                        if (pos) I.key = g;
-                    } else { // ChangeFront, path.h:113-122
-                        I.fg = g, I.fv = v, I.fbp = bp, I.fdist = dist;
-                        if (!pos) I.key = g;
-                    }
-                    a = I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp;
-                    if (!prev_good && (long long)a >= c.pr.m) c.good[c.ngood] = (unsigned short)cand, c.ngood |= 0x40000000;
-                    if (flag >= 0) inst_extend_reads(I, flag, flag);
-                    if (used) I.flags |= fin;
-                }
-                // lane 0 flagged a goodInstance_ append in bit 30; make the count uniform again
-                int ng = __shfl_sync(kFull, c.ngood, 0);
-                c.ngood = (ng & 0x40000000) ? (ng & 0x3FFFFFFF) + 1 : ng;
-                __syncwarp();
-            } else if (!used) {
-                inst_insert(c, ub, g, pos, v, bp, dist, flag, clo, chi);
-                if (c.err) return true;
-            } else if (flag >= 0) {
-                rs_add(c, flag, flag);
-            }
-            __syncwarp();
-        }
-    }
-#else
     // everything else (a chromosome that carries the vertex twice, more than 32 occurrences): conflict-free groups
     for (unsigned o = o0; o < o1 && !handled;) {
         const int took = push_group(c, BACK, v, dist, o, o1 - o, e_ch_g, e_ch_pos, e_other);
         if (c.err) return true;
         o += (unsigned)took;
     }
-#endif
     if (BACK) {
         if (c.nright >= cap_path(c)) {
             c.err = LCB_ERR_CAPACITY | (1 << 8);
