@@ -604,43 +604,64 @@ extern "C" int lcb_write_output(const lcb_index *ix, const lcb_block_instance *b
             // blocksfinder.h:533-582: one line per block, blocks dealt round-robin over `chunks` files
             std::vector<OutBlock> rows(kept);
             std::sort(rows.begin(), rows.end(), by_id);
-            std::vector<TextBuffer> chunk((size_t)chunks);
-            size_t which = 0;
+            // block g goes to chunk file g % chunks; thread t formats and writes the files with (index % T) == t
+            std::vector<std::pair<size_t, size_t>> groups;
             for (size_t lo = 0; lo < rows.size();) {
                 size_t hi = lo;
                 while (hi < rows.size() && !by_id(rows[lo], rows[hi])) ++hi;
-                TextBuffer &t = chunk[which];
-                for (size_t i = lo; i < hi; i++) {
-                    const OutBlock &b = rows[i];
-                    const std::string &s = ix->fasta.seq[b.chr];
-                    uint64_t len = b.end - b.start;
-                    t.put("> ", 2);
-                    t.put(ix->fasta.name[b.chr]);
-                    t.put(';');
-                    if (b.id > 0) {
-                        t.num(b.start);
-                        t.put(';');
-                        t.num(len);
-                        t.put(";+;", 3);
-                        t.num(s.size());
-                        t.put('@');
-                        t.put(s.data() + b.start, (size_t)len);
-                    } else {
-                        t.num(s.size() - b.end);
-                        t.put(';');
-                        t.num(len);
-                        t.put(";-;", 3);
-                        t.num(s.size());
-                        t.put('@');
-                        for (uint64_t j = 0; j < len; j++) t.put((char)Complement((uint8_t)s[b.end - 1 - j]));
-                    }
-                    t.put('@');
-                }
-                t.put('\n');
-                which = (which + 1) % (size_t)chunks;
+                groups.emplace_back(lo, hi);
                 lo = hi;
             }
-            for (int i = 0; i < chunks; i++) WriteFile(std::string(out_dir) + "/" + std::to_string(i) + ".tmp", chunk[(size_t)i].s);
+            const unsigned T = std::max(1u, std::min<unsigned>(WorkerCount(), (unsigned)chunks));
+            std::vector<std::string> failed(T);
+            Parallel(T, [&](unsigned tt, unsigned TT) {
+                try {
+                    std::vector<TextBuffer> chunk;
+                    std::vector<size_t> mine; // chunk indices of this thread
+                    for (size_t c = tt; c < (size_t)chunks; c += TT) mine.push_back(c);
+                    chunk.resize(mine.size());
+                    for (size_t g = 0; g < groups.size(); g++) {
+                        const size_t which = g % (size_t)chunks;
+                        if (which % TT != tt) continue;
+                        TextBuffer &t = chunk[which / TT];
+                        for (size_t i = groups[g].first; i < groups[g].second; i++) {
+                            const OutBlock &b = rows[i];
+                            const std::string &s = ix->fasta.seq[b.chr];
+                            uint64_t len = b.end - b.start;
+                            t.put("> ", 2);
+                            t.put(ix->fasta.name[b.chr]);
+                            t.put(';');
+                            if (b.id > 0) {
+                                t.num(b.start);
+                                t.put(';');
+                                t.num(len);
+                                t.put(";+;", 3);
+                                t.num(s.size());
+                                t.put('@');
+                                t.put(s.data() + b.start, (size_t)len);
+                            } else {
+                                t.num(s.size() - b.end);
+                                t.put(';');
+                                t.num(len);
+                                t.put(";-;", 3);
+                                t.num(s.size());
+                                t.put('@');
+                                const size_t at = t.s.size();
+                                t.s.resize(at + (size_t)len);
+                                char *w = &t.s[at];
+                                for (uint64_t j = 0; j < len; j++) w[j] = (char)Complement((uint8_t)s[b.end - 1 - j]);
+                            }
+                            t.put('@');
+                        }
+                        t.put('\n');
+                    }
+                    for (size_t k = 0; k < mine.size(); k++) WriteFile(std::string(out_dir) + "/" + std::to_string(mine[k]) + ".tmp", chunk[k].s);
+                } catch (std::exception &e) {
+                    failed[tt] = e.what();
+                }
+            });
+            for (const std::string &f : failed)
+                if (!f.empty()) throw Failure(LCB_ERR_IO, f);
         }
     } catch (Failure &e) {
         if (err && errlen) snprintf(err, errlen, "%s", e.what());
