@@ -21,6 +21,17 @@
 #else
 #define POA_HD inline
 #endif
+// The warp-level code is compiled for the device -- and for the host under POA_WARP_EMULATION, where tests/poa_warp_emu.cpp
+// supplies __shfl_up_sync / __shfl_sync / __syncwarp for 32 host threads in lockstep, so that the row kernel below is
+// exercised exactly as written without a GPU.
+#if defined(__CUDA_ARCH__) || defined(POA_WARP_EMULATION)
+#define POA_WARP_CODE 1
+#endif
+#if defined(__CUDA_ARCH__)
+#define POA_DEV __device__ __forceinline__
+#else
+#define POA_DEV inline
+#endif
 
 namespace poa {
 
@@ -362,17 +373,17 @@ POA_HD void dp_init(Work &w, const Params &pr, uint32_t len, int lane, int lanes
             w.H[(uint64_t)i * W] = penalty + pr.g;
         }
     }
-#if defined(__CUDA_ARCH__)
+#if defined(POA_WARP_CODE)
     __syncwarp();
 #endif
 }
 
-#if defined(__CUDA_ARCH__)
+#if defined(POA_WARP_CODE)
 // One row of H (sisd_alignment_engine.cpp:318-352), the whole warp.  A step covers 4 x 32 columns: lane l owns columns
 // base + 32 k + l + 1 (k = 0..3), so that the loads of four chunks are in flight together; the four max-scans then run one
 // after the other because each needs the carry of the one before.  The first two predecessor rows are kept as pointers
 // (almost every node has one or two in-edges), further ones are reached through the edge list.
-__device__ __forceinline__ void dp_row(Work &w, const Params &pr, const uint8_t *s, uint32_t len, uint32_t i, int lane)
+POA_DEV void dp_row(Work &w, const Params &pr, const uint8_t *s, uint32_t len, uint32_t i, int lane)
 {
     const uint64_t W = (uint64_t)len + 1;
     const int it = w.rank_to_node[i - 1];
@@ -516,7 +527,7 @@ POA_HD uint32_t traceback(Work &w, const Params &pr, const uint8_t *s, uint32_t 
 // ---- one block -------------------------------------------------------------------------------------------------------------
 POA_HD void poa_sync()
 {
-#if defined(__CUDA_ARCH__)
+#if defined(POA_WARP_CODE)
     __syncwarp();
 #endif
 }

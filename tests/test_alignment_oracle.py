@@ -85,3 +85,44 @@ def test_poa_core_host_build_equals_restatement(example_chunks, tmp_path):
         for level in (0, 2):
             got = subprocess.run([exe, "--chunk", f, "--level", str(level)], check=True, stdout=subprocess.PIPE, text=True).stdout
             assert got == want, (f, level)
+
+
+def test_warp_row_kernel_under_emulation(tmp_path):
+    """The device row kernel AS WRITTEN (poa_core.cuh: four 32-column chunks per step, predecessor rows as pointers, the
+    max-scan with its carry through __shfl_up_sync / __shfl_sync, the __syncwarp placement) run by 32 host threads in
+    lockstep (tests/poa_warp_emu.cpp) == the restatement: edge cases and blocks of 130-333 bp with substitutions and indels
+    (nodes with several predecessors, columns beyond one 128-column step)."""
+    import random
+    import subprocess
+    from oracle_binding import poa_oracle_text, write_chunk
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "poa_warp_emu")
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-o", exe, os.path.join(here, "poa_warp_emu.cpp")], check=True)
+    rnd = random.Random(5)
+
+    def mutate(s, rate):
+        out = []
+        for ch in s:
+            r = rnd.random()
+            if r < rate / 3:
+                continue
+            if r < 2 * rate / 3:
+                out += [rnd.choice("ACGT"), ch]
+            elif r < rate:
+                out.append(rnd.choice("ACGT"))
+            else:
+                out.append(ch)
+        return "".join(out)
+
+    blocks = [
+        [("a;0;4;+;9", "ACGT")],
+        [("a;0;1;+;9", "A"), ("b;0;1;+;9", "C"), ("c;0;1;+;9", "A")],
+        [("a;0;8;+;9", "ACGTACGT"), ("b;0;3;+;9", "CGT"), ("c;0;12;-;30", "TTACGTACGTTT"), ("d;0;8;+;9", "ACGAACGT")],
+        [("a;0;6;+;9", "acgtNN"), ("b;0;6;+;9", "ACGTNN"), ("c;0;7;+;9", "acgRtNN")],
+    ]
+    for n, length, rate in ((5, 200, 0.08), (3, 333, 0.15), (8, 130, 0.05), (4, 257, 0.3)):
+        anc = "".join(rnd.choice("ACGT") for _ in range(length))
+        blocks.append([("c%d;0;%d;+;999" % (i, length), mutate(anc, rate)) for i in range(n)])
+    f = write_chunk(str(tmp_path / "emu.tmp"), blocks)
+    got = subprocess.run([exe, "--chunk", f], check=True, stdout=subprocess.PIPE, text=True, timeout=600).stdout
+    assert got == poa_oracle_text(f)
