@@ -577,4 +577,150 @@ POA_HD void write_row(const Work &w, uint32_t k, uint8_t *out, int lane, int lan
     poa_sync();
 }
 
+// ---- long blocks: one block per CTA ------------------------------------------------------------------------------------------
+// A row of a long block (tens of thousands of columns) is hundreds of independent 128-column pieces: here the warps of a
+// whole CTA share one row.  A step covers nwarps x 128 columns; warp v scans its 128 columns without a carry (pass 1),
+// publishes the maximum of its piece, and after one CTA barrier every warp folds the carry of the step and the maxima of
+// the warps before it into its own columns (pass 2) -- max is associative, so this is the same H as the one-warp scan.
+// Thread 0 of the CTA runs the sequential parts.  (Compiled as warp code: device, or host under POA_WARP_EMULATION.)
+#if defined(POA_WARP_CODE)
+POA_DEV void cta_sync() { __syncthreads(); }
+
+// seg: 2 x 32 ints of shared memory (double-buffered by step parity, so one barrier per step is enough)
+POA_DEV void dp_row_cta(Work &w, const Params &pr, const uint8_t *s, uint32_t len, uint32_t i, int lane, int warp, int nwarps,
+                        int32_t *seg)
+{
+    const uint64_t W = (uint64_t)len + 1;
+    const int it = w.rank_to_node[i - 1];
+    const uint8_t ch = w.decoder[w.code[it]];
+    int32_t *row = w.H + (uint64_t)i * W;
+    const int e0 = w.in_first[it];
+    const int e1 = e0 >= 0 ? w.edge_next_in[e0] : -1;
+    const int e2 = e1 >= 0 ? w.edge_next_in[e1] : -1;
+    const int32_t *pred0 = e0 >= 0 ? w.H + ((uint64_t)w.rank[w.edge_tail[e0]] + 1) * W : w.H;
+    const int32_t *pred1 = e1 >= 0 ? w.H + ((uint64_t)w.rank[w.edge_tail[e1]] + 1) * W : nullptr;
+    int32_t carry = row[0]; // of the step: H[i][base] - base * g
+    const uint32_t span = 128u * (uint32_t)nwarps;
+    int parity = 0;
+    for (uint32_t base = 0; base < len; base += span, parity ^= 1) {
+        const uint32_t wbase = base + 128u * (uint32_t)warp;
+        int32_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = wbase + 32u * (uint32_t)k + (uint32_t)lane + 1;
+            int32_t M = kNegInf;
+            if (j <= len) {
+                const int32_t sc = s[j - 1] == ch ? pr.m : pr.n;
+                const int32_t a = pred0[j - 1] + sc, b = pred0[j] + pr.g;
+                M = a > b ? a : b;
+                if (pred1) {
+                    const int32_t a1 = pred1[j - 1] + sc, b1 = pred1[j] + pr.g;
+                    const int32_t v1 = a1 > b1 ? a1 : b1;
+                    M = v1 > M ? v1 : M;
+                    for (int e = e2; e >= 0; e = w.edge_next_in[e]) {
+                        const int32_t *pred = w.H + ((uint64_t)w.rank[w.edge_tail[e]] + 1) * W;
+                        const int32_t a2 = pred[j - 1] + sc, b2 = pred[j] + pr.g;
+                        const int32_t v2 = a2 > b2 ? a2 : b2;
+                        M = v2 > M ? v2 : M;
+                    }
+                }
+                M -= (int32_t)j * pr.g;
+            }
+            x[k] = M;
+        }
+        // pass 1: inclusive max-scan of the warp's 128 columns, no carry from outside the warp
+        int32_t inner = kNegInf;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int32_t v = x[k];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t y = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                if (lane >= d) v = y > v ? y : v;
+            }
+            v = v > inner ? v : inner;
+            x[k] = v;
+            inner = __shfl_sync(0xFFFFFFFFu, v, 31);
+        }
+        if (lane == 0) seg[parity * 32 + warp] = inner; // maximum of the warp's piece
+        cta_sync();
+        // pass 2: carry of the step + the pieces of the warps before this one; every warp also learns the step's carry-out
+        int32_t before = kNegInf, all = kNegInf;
+        for (int v = 0; v < nwarps; v++) {
+            const int32_t t = seg[parity * 32 + v];
+            if (v < warp) before = t > before ? t : before;
+            all = t > all ? t : all;
+        }
+        const int32_t cin = before > carry ? before : carry;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = wbase + 32u * (uint32_t)k + (uint32_t)lane + 1;
+            const int32_t v = x[k] > cin ? x[k] : cin;
+            if (j <= len) row[j] = v + (int32_t)j * pr.g;
+        }
+        carry = all > carry ? all : carry;
+    }
+    cta_sync(); // the row is complete before any warp starts the next one
+}
+
+// run_block for a CTA: tid = thread index in the CTA, nthreads = CTA size (a multiple of 32, at most 1024)
+POA_DEV void run_block_cta(Work &w, const Params &pr, const uint8_t *seq, const uint64_t *copy_off, uint32_t c0, uint32_t c1, int tid,
+                          int nthreads, int32_t *seg)
+{
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    if (tid == 0) graph_reset(w);
+    cta_sync();
+    for (uint32_t c = c0; c < c1; c++) {
+        const uint8_t *s = seq + copy_off[c];
+        const uint32_t len = (uint32_t)(copy_off[c + 1] - copy_off[c]);
+        const uint32_t nodes = w.n_nodes;
+        if (nodes != 0 && len != 0) {
+            if ((uint64_t)(nodes + 1) * ((uint64_t)len + 1) > w.cap.max_cells || nodes + len + 2 > w.cap.max_align) {
+                cta_sync(); // every thread has read w.n_nodes / w.cap before the flag is written
+                if (tid == 0) w.err = 1;
+                cta_sync();
+                return;
+            }
+            { // dp_init: row 0 by all threads, column 0 by thread 0
+                const uint64_t W = (uint64_t)len + 1;
+                for (uint64_t j = (uint64_t)tid; j < W; j += (uint64_t)nthreads) w.H[j] = (int32_t)j * pr.g;
+                cta_sync();
+                if (tid == 0) {
+                    for (uint32_t i = 1; i <= nodes; i++) {
+                        const int it = w.rank_to_node[i - 1];
+                        int32_t penalty = w.in_first[it] < 0 ? 0 : kNegInf;
+                        for (int e = w.in_first[it]; e >= 0; e = w.edge_next_in[e]) {
+                            const int32_t v = w.H[((uint64_t)w.rank[w.edge_tail[e]] + 1) * W];
+                            penalty = v > penalty ? v : penalty;
+                        }
+                        w.H[(uint64_t)i * W] = penalty + pr.g;
+                    }
+                }
+                cta_sync();
+            }
+            for (uint32_t i = 1; i <= nodes; i++) dp_row_cta(w, pr, s, len, i, lane, warp, nwarps, seg);
+            if (tid == 0) w.n_pairs = traceback(w, pr, s, len);
+        } else if (tid == 0) {
+            w.n_pairs = 0;
+        }
+        cta_sync();
+        if (tid == 0 && !w.err) add_alignment(w, w.al_pairs, w.n_pairs, s, len);
+        cta_sync();
+        if (w.err) return;
+    }
+    if (tid == 0) w.n_columns = msa_columns(w);
+    cta_sync();
+}
+
+POA_DEV void write_row_cta(const Work &w, uint32_t k, uint8_t *out, int tid, int nthreads)
+{
+    for (uint32_t j = (uint32_t)tid; j < w.n_columns; j += (uint32_t)nthreads) out[j] = '-';
+    cta_sync();
+    for (uint32_t t = w.path_off[k] + (uint32_t)tid; t < w.path_off[k + 1]; t += (uint32_t)nthreads) {
+        const int node = w.path[t];
+        out[w.column[node]] = w.decoder[w.code[node]];
+    }
+    cta_sync();
+}
+#endif
+
 } // namespace poa

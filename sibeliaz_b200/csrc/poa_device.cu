@@ -81,6 +81,67 @@ __global__ void __launch_bounds__(kPoaWarps * 32) k_poa(const uint8_t *__restric
     if (lane == 0 && cells) atomicAdd(&q->cells, cells);
 }
 
+// Long blocks: one block per CTA (poa_core.cuh, run_block_cta); CTAs pull blocks from the same kind of queue, the arena of
+// CTA c is arena_base + c * arena_stride.
+constexpr int kCtaThreads = 1024;
+__global__ void __launch_bounds__(kCtaThreads) k_poa_cta(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ copy_off,
+                                                         const uint32_t *__restrict__ block_off, const uint32_t *__restrict__ list,
+                                                         unsigned n_list, int level, uint8_t *arena_base, unsigned long long arena_stride,
+                                                         poa::Params pr, Queue *q, uint8_t *rows, unsigned long long rows_cap,
+                                                         unsigned long long *row_off, uint32_t *block_cols, uint8_t *status)
+{
+#if defined(__CUDA_ARCH__) // (the team code of poa_core.cuh exists for the device pass only)
+    __shared__ poa::Work w;
+    __shared__ int32_t seg[64];
+    __shared__ unsigned s_idx;
+    __shared__ unsigned long long s_off, s_mx;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    unsigned long long cells = 0;
+    while (true) {
+        if (tid == 0) s_idx = atomicAdd(&q->head, 1u), s_mx = 0;
+        __syncthreads();
+        const unsigned idx = s_idx;
+        if (idx >= n_list) break;
+        const uint32_t b = list[idx];
+        const uint32_t c0 = block_off[b], c1 = block_off[b + 1];
+        unsigned long long mx = 0;
+        for (uint32_t c = c0 + (uint32_t)tid; c < c1; c += (uint32_t)nthreads) mx = max(mx, (unsigned long long)(copy_off[c + 1] - copy_off[c]));
+        if (mx) atomicMax(&s_mx, mx);
+        __syncthreads();
+        mx = s_mx;
+        const unsigned long long sum = copy_off[c1] - copy_off[c0];
+        if (tid == 0) poa::poa_bind(w, arena_base + (size_t)blockIdx.x * arena_stride, poa::poa_caps_for(sum, mx, level), c1 - c0);
+        __syncthreads();
+        poa::run_block_cta(w, pr, seq, copy_off, c0, c1, tid, nthreads, seg);
+        if (w.err) {
+            if (tid == 0) status[b] = (uint8_t)w.err;
+            __syncthreads();
+            continue;
+        }
+        const unsigned long long need = (unsigned long long)(c1 - c0) * w.n_columns;
+        if (tid == 0) s_off = atomicAdd(&q->rows_used, need);
+        __syncthreads();
+        const unsigned long long off = s_off;
+        if (off + need > rows_cap) {
+            if (tid == 0) status[b] = kPoolFull;
+            __syncthreads();
+            continue;
+        }
+        for (uint32_t k = 0; k < c1 - c0; k++) {
+            poa::write_row_cta(w, k, rows + off + (unsigned long long)k * w.n_columns, tid, nthreads);
+            if (tid == 0) row_off[c0 + k] = off + (unsigned long long)k * w.n_columns;
+        }
+        if (tid == 0) {
+            block_cols[b] = w.n_columns;
+            status[b] = kDone;
+            cells += (unsigned long long)w.n_nodes * (mx + 1);
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && cells) atomicAdd(&q->cells, cells);
+#endif
+}
+
 struct Fail {
     int code;
     std::string msg;
@@ -198,8 +259,32 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
     std::vector<uint8_t> status(n_blocks, kPending);
     float ms_kernels = 0;
 
+    // Blocks whose longest copy has at least this many characters are given a whole CTA (run_block_cta) instead of a warp.
+    // OFF unless LCA_CTA_ROWS is set (to the threshold, e.g. 2048): the CTA variant is validated under the lockstep emulator
+    // (tests/poa_warp_emu.cpp --cta) but has not yet run on a GPU.
+    const uint64_t cta_from = getenv("LCA_CTA_ROWS") ? std::max<uint64_t>(strtoull(getenv("LCA_CTA_ROWS"), nullptr, 10), 256) : ~0ull;
+    auto launch_cta = [&](const std::vector<uint32_t> &list, int level, uint64_t stride) {
+        const unsigned ctas = (unsigned)std::min<uint64_t>(std::min<uint64_t>(list.size(), (uint64_t)sms), std::max<uint64_t>(budget / stride, 1));
+        DevBuf<uint8_t> arena;
+        arena.alloc((size_t)ctas * stride);
+        CU(cudaMemcpyAsync(d_list.p, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemsetAsync(&d_q.p->head, 0, sizeof(unsigned), stream));
+        CU(cudaEventRecord(ev0, stream));
+        k_poa_cta<<<ctas, kCtaThreads, 0, stream>>>(d_seq.p, d_copy_off.p, d_block_off.p, d_list.p, (unsigned)list.size(), level, arena.p,
+                                                    (unsigned long long)stride, pr, d_q.p, d_rows.p, (unsigned long long)rows_cap,
+                                                    d_row_off.p, d_cols.p, d_status.p);
+        CU(cudaEventRecord(ev1, stream));
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(status.data(), d_status.p, n_blocks, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        ms_kernels += ms;
+        res.st.kernel_launches++;
+    };
     // one launch over `list` (block ids) at `level` with arenas of `stride` bytes
     auto launch = [&](const std::vector<uint32_t> &list, int level, uint64_t stride) {
+        if (!list.empty() && mx[list[0]] >= cta_from) return launch_cta(list, level, stride);
         uint64_t warps = std::min<uint64_t>(std::min<uint64_t>(list.size(), resident_warps), std::max<uint64_t>(budget / stride, 1));
         // never more arenas than the budget holds: whole CTAs, or one partial CTA
         const unsigned ctas = warps >= (uint64_t)kPoaWarps ? (unsigned)(warps / kPoaWarps) : 1u;
@@ -234,7 +319,8 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
         while (at < todo.size()) {
             while (need(todo[at], level) > class_cap) class_cap *= 4;
             size_t end = at;
-            while (end < todo.size() && need(todo[end], level) <= class_cap) end++;
+            const bool long_class = mx[todo[at]] >= cta_from; // a launch is either all-warp or all-CTA
+            while (end < todo.size() && need(todo[end], level) <= class_cap && (mx[todo[end]] >= cta_from) == long_class) end++;
             std::vector<uint32_t> list(todo.begin() + (long)at, todo.begin() + (long)end);
             const uint64_t stride = (need(list.back(), level) + 255) & ~255ull;
             if (stride > budget) { // not even one arena of this size: try the next level only if it is smaller (it is not)

@@ -3,39 +3,44 @@
 // lanes of one warp and meet in a barrier at every __shfl_*_sync / __syncwarp, which is the lockstep the hardware gives.
 // A missing synchronisation in the device code shows up here as a data race between free-running threads (wrong output
 // or a failing run), an index slip in the scan as a wrong MSA.  Not a product path.
-//   poa_warp_emu --chunk <file.tmp>     MAF paragraphs, as oracle/poa_oracle prints them
+//   poa_warp_emu --chunk <file.tmp> [--cta <warps>]     MAF paragraphs, as oracle/poa_oracle prints them
+// --cta: the one-block-per-CTA variant for long blocks (run_block_cta: <warps> x 32 threads share every row)
 #include <barrier>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
 
 namespace emu {
-std::barrier<> *bar;
-int32_t slot[32];
-thread_local int lane;
+constexpr int kMaxWarps = 32;
+std::barrier<> *warp_bar[kMaxWarps]; // one per warp: __shfl_*_sync, __syncwarp
+std::barrier<> *cta_bar;             // __syncthreads
+int32_t slot[kMaxWarps][32];
+thread_local int lane, warp;
 } // namespace emu
 
 inline int32_t __shfl_up_sync(unsigned, int32_t v, int d)
 {
-    emu::slot[emu::lane] = v;
-    emu::bar->arrive_and_wait();
-    const int32_t r = emu::lane >= d ? emu::slot[emu::lane - d] : v;
-    emu::bar->arrive_and_wait();
+    emu::slot[emu::warp][emu::lane] = v;
+    emu::warp_bar[emu::warp]->arrive_and_wait();
+    const int32_t r = emu::lane >= d ? emu::slot[emu::warp][emu::lane - d] : v;
+    emu::warp_bar[emu::warp]->arrive_and_wait();
     return r;
 }
 inline int32_t __shfl_sync(unsigned, int32_t v, int src)
 {
-    emu::slot[emu::lane] = v;
-    emu::bar->arrive_and_wait();
-    const int32_t r = emu::slot[src & 31];
-    emu::bar->arrive_and_wait();
+    emu::slot[emu::warp][emu::lane] = v;
+    emu::warp_bar[emu::warp]->arrive_and_wait();
+    const int32_t r = emu::slot[emu::warp][src & 31];
+    emu::warp_bar[emu::warp]->arrive_and_wait();
     return r;
 }
-inline void __syncwarp() { emu::bar->arrive_and_wait(); }
+inline void __syncwarp() { emu::warp_bar[emu::warp]->arrive_and_wait(); }
+inline void __syncthreads() { emu::cta_bar->arrive_and_wait(); }
 
 #define POA_WARP_EMULATION 1
 #include "../sibeliaz_b200/csrc/poa_core.cuh"
@@ -44,12 +49,19 @@ int main(int argc, char **argv)
 {
     std::string chunk;
     poa::Params pr{5, -4, -8};
-    for (int i = 1; i < argc; i++)
+    int cta_warps = 0;
+    for (int i = 1; i < argc; i++) {
         if (std::string(argv[i]) == "--chunk" && i + 1 < argc) chunk = argv[++i];
+        else if (std::string(argv[i]) == "--cta" && i + 1 < argc) cta_warps = atoi(argv[++i]);
+    }
     std::ifstream in(chunk);
-    if (chunk.empty() || !in) return 1;
-    std::barrier<> bar(32);
-    emu::bar = &bar;
+    if (chunk.empty() || !in || cta_warps < 0 || cta_warps > emu::kMaxWarps) return 1;
+    const int nwarps = cta_warps ? cta_warps : 1, nthreads = nwarps * 32;
+    std::vector<std::unique_ptr<std::barrier<>>> wb;
+    for (int v = 0; v < nwarps; v++) wb.emplace_back(new std::barrier<>(32)), emu::warp_bar[v] = wb.back().get();
+    std::barrier<> cb(nthreads);
+    emu::cta_bar = &cb;
+    int32_t seg[64];
     std::string line;
     while (std::getline(in, line)) {
         std::vector<std::string> header;
@@ -86,15 +98,25 @@ int main(int argc, char **argv)
         poa::poa_bind(w, arena.data(), caps, copies);
         std::vector<std::string> rows(copies);
         std::vector<std::thread> lanes;
-        for (int l = 0; l < 32; l++)
-            lanes.emplace_back([&, l]() {
-                emu::lane = l;
-                poa::run_block(w, pr, seq.data(), off.data(), 0, copies, l, 32);
+        for (int t = 0; t < nthreads; t++)
+            lanes.emplace_back([&, t]() {
+                emu::lane = t & 31, emu::warp = t >> 5;
+                if (cta_warps) {
+                    poa::run_block_cta(w, pr, seq.data(), off.data(), 0, copies, t, nthreads, seg);
+                    if (w.err) return;
+                    for (uint32_t k = 0; k < copies; k++) {
+                        if (t == 0) rows[k].assign(w.n_columns, '?');
+                        __syncthreads();
+                        poa::write_row_cta(w, k, (uint8_t *)&rows[k][0], t, nthreads);
+                    }
+                    return;
+                }
+                poa::run_block(w, pr, seq.data(), off.data(), 0, copies, t, 32);
                 if (w.err) return; // uniform: every lane sees the same flag after the last barrier
                 for (uint32_t k = 0; k < copies; k++) {
-                    if (l == 0) rows[k].assign(w.n_columns, '?');
+                    if (t == 0) rows[k].assign(w.n_columns, '?');
                     __syncwarp();
-                    poa::write_row(w, k, (uint8_t *)&rows[k][0], l, 32);
+                    poa::write_row(w, k, (uint8_t *)&rows[k][0], t, 32);
                 }
             });
         for (auto &t : lanes) t.join();

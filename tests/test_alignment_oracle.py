@@ -123,6 +123,16 @@ def test_warp_row_kernel_under_emulation(tmp_path):
     for n, length, rate in ((5, 200, 0.08), (3, 333, 0.15), (8, 130, 0.05), (4, 257, 0.3)):
         anc = "".join(rnd.choice("ACGT") for _ in range(length))
         blocks.append([("c%d;0;%d;+;999" % (i, length), mutate(anc, rate)) for i in range(n)])
-    f = write_chunk(str(tmp_path / "emu.tmp"), blocks)
-    got = subprocess.run([exe, "--chunk", f], check=True, stdout=subprocess.PIPE, text=True, timeout=600).stdout
-    assert got == poa_oracle_text(f)
+    def emulate(name, bl, cta):
+        f = write_chunk(str(tmp_path / (name + ".tmp")), bl)
+        got = subprocess.run([exe, "--chunk", f, "--cta", str(cta)], check=True, stdout=subprocess.PIPE, text=True, timeout=900).stdout
+        assert got == poa_oracle_text(f), (name, cta)
+
+    # one warp per block (run_block / dp_row): the kernel validated on the GPU
+    emulate("warp", blocks[:5] + [blocks[7]], 0)
+    # one block per CTA for long blocks (run_block_cta / dp_row_cta: the warps of a CTA share every row; two-pass scan, the
+    # pieces' maxima exchanged through shared memory, double-buffered): several warps in one step; one warp over three steps;
+    # two warps over two steps.  Kept small: emulated threads on a few cores spend their time in barriers.
+    emulate("cta4", blocks[:4], 4)
+    emulate("cta1", [blocks[5]], 1)
+    emulate("cta2", [[(h, s2[:300]) for h, s2 in blocks[5]]], 2)
