@@ -218,7 +218,14 @@ __device__ __forceinline__ int kth_bit4(unsigned m, int k)
     return r;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+#if defined(__CUDA_ARCH__) // (nothing to do where the header is compiled for the host: tests/trav_emu.cpp)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 __device__ __forceinline__ unsigned hash_of(int key) { return (unsigned)key * 2654435761u; }
 
@@ -300,6 +307,7 @@ __device__ __forceinline__ void hash_insert(Ctx &c, int key, int val)
         c.err = LCB_ERR_CAPACITY | (1 << 8);
         return;
     }
+    __syncwarp(); // every lane has finished probing the table (hash_find of the same key) before lane 0 changes it
     if (c.lane == 0) {
         unsigned s = (hash_of(key) >> 12) & (unsigned)c.hmask;
         while (c.hash[s].x != 0) s = (s + 1) & (unsigned)c.hmask;
