@@ -694,6 +694,7 @@ __device__ __forceinline__ bool push_parallel(Ctx &c, const bool BACK, int v, in
         }
     }
     if (c.collect) c.ct.scan += (unsigned long long)__reduce_add_sync(kFull, scan_lo <= scan_hi ? (unsigned)(scan_hi - scan_lo + 1) : 0u);
+    __syncwarp(); // every lane has finished reading the instance table (searches, neighbours) before any lane changes it
     // ---- apply.  Candidates of different lanes are different instances (different chromosomes).
     bool newly_good = false;
     if (live && cand >= 0 && scan_lo <= scan_hi) inst_extend_reads(c.inst[cand], scan_lo, scan_hi);
@@ -857,6 +858,7 @@ __device__ __forceinline__ int push_group(Ctx &c, const bool BACK, int v, int di
         }
     }
     if (c.collect) c.ct.scan += (unsigned long long)__reduce_add_sync(kFull, scan_lo <= scan_hi ? (unsigned)(scan_hi - scan_lo + 1) : 0u);
+    __syncwarp(); // every lane has finished reading the instance table (searches, neighbours) before any lane changes it
     // ---- apply.  Candidates of different lanes are different instances (see the group rule above).
     bool newly_good = false;
     if (live && cand >= 0 && scan_lo <= scan_hi) inst_extend_reads(c.inst[cand], scan_lo, scan_hi);

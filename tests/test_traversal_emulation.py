@@ -99,3 +99,11 @@ def trav_emu(tmp_path_factory):
 def test_device_traversal_code_equals_oracle_star(star_small, trav_emu, tmp_path):
     n, nonempty = emulate_and_compare(star_small, lambda S: list(range(0, 24)) + list(range(24, S, max(1, S // 40))), trav_emu, str(tmp_path))
     assert n >= 60 and nonempty >= 40
+
+
+def test_device_traversal_code_equals_oracle_repeat_rich(examples, trav_emu, tmp_path):
+    """examples at k=15: repeat-rich, so the pushes meet vertices that occur several times on a chromosome (push_group), more
+    than 32 instances (bisected order, spill arena) and the general vote.  Evaluations whose result has more than 32
+    instances are left to manual runs (a barrier per collective)."""
+    n, nonempty = emulate_and_compare(examples["k15"], lambda S: list(range(6, S, max(1, S // 45))), trav_emu, str(tmp_path), max_instances=32)
+    assert n >= 30 and nonempty >= 25
