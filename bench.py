@@ -7,8 +7,9 @@
 
 A *step* is one pass of the FindBlocks equivalent (seed enumeration + sort + carving-path traversal +
 ordered commit; blocksfinder.h:453-530) over the workload, J/s = kept junction records / step time.
-Workload = BASELINE configs[1]: synthetic 4 x 10 Mbp star phylogeny (0.05 subs/site, seed 1), k=21,
--b 200 -m 50 -a 150 (inputs: tools/gen_synthetic.py, junction file by the reference twopaco).
+Default workload = the north-star input of BASELINE.json: synthetic 4 x 100 Mbp star phylogeny (0.05 subs/site, seed 1),
+k=25, -b 200 -m 50 -a 150 (14.97 M junction records; inputs: tools/gen_synthetic.py, junction file by the reference
+twopaco).  `--workload star4x10M_k21` is BASELINE configs[1] (the round-1 bench workload).
 
   value      step timed with CUDA events on the library's stream, index already resident in HBM
   e2e        the same through the C ABI from HOST arrays: lcb_create (pinned staging + H2D) + enumerate +
@@ -17,6 +18,12 @@ Workload = BASELINE configs[1]: synthetic 4 x 10 Mbp star phylogeny (0.05 subs/s
              oracle on this workload) / summed CUDA-event time of its launches, vs the
              measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline  oracle/_ref/sibeliaz-lcb-ref (the unmodified reference) on this box's host cores
+  wall_clock    whole-binary seconds (N=1 only): the drop-in CLI sibeliaz_b200/bin/sibeliaz-lcb on the same junction file,
+             default (one process, exits when the CUDA context is released) and --detach, next to the reference binary
+             at -t min(cores, 32); GFF compared byte for byte
+
+The reference arm (--impl reference) times at most REF_MAX_STEPS whole runs of the reference binary (a pass over the
+north-star input takes ~20 s) and says so in its line.
 
 Only the cpu_baseline / --impl reference legs and the one-off parity check touch oracle/.
 """
@@ -41,6 +48,12 @@ WORKLOADS = {
     "star4x100M_k25": ("star", 4, 100_000_000, 0.05, 1, 25),
 }
 B, M, A = 200, 50, 150
+DEFAULT_WORKLOAD = "star4x100M_k25"
+REF_MAX_STEPS = 3
+DESCRIPTIONS = {
+    "star4x100M_k25": "synthetic star 4x100 Mbp, 0.05 subs/site, seed 1, k=25, -b 200 -m 50 -a 150 (BASELINE north-star input)",
+    "star4x10M_k21": "synthetic star 4x10 Mbp, 0.05 subs/site, seed 1, k=21, -b 200 -m 50 -a 150 (BASELINE configs[1])",
+}
 
 
 def prepare_workload(name, rank):
@@ -96,6 +109,25 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if xs else None
+
+
+def time_cli(dbg, fas, k, threads, out, extra=()):
+    """Whole-binary wall clock of the drop-in CLI (fork+exec to exit), same flags as the reference run."""
+    import sibeliaz_b200 as sb
+    os.makedirs(out, exist_ok=True)
+    cmd = [sb.CLI_PATH, "--graph", dbg] + fas + ["-k", str(k), "-b", str(B), "-o", out, "-m", str(M), "-t", str(threads),
+                                                "--abundance", str(A), "--noseq"] + list(extra)
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    t1 = time.perf_counter()
+    if r.returncode:
+        raise RuntimeError("sibeliaz-lcb failed: " + r.stderr.decode(errors="replace")[-300:])
+    return t1 - t0
+
+
 def time_reference(dbg, fas, k, threads):
     """Runs oracle/_ref/sibeliaz-lcb-ref and returns (t_find_s, t_total_s): FindBlocks is the span between the
     reference's own 'Analyzing the graph...' and 'Generating the output...' stdout lines (sibeliaz.cpp:133,142)."""
@@ -130,7 +162,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="star4x10M_k21", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-wall-clock", action="store_true")
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -139,8 +172,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     steps, warmup = max(1, a.steps), max(0, a.warmup)
     host_threads = min(32, os.cpu_count() or 1)  # the sibeliaz wrapper caps sibeliaz-lcb at 32 threads (sibeliaz:139)
-    config = {"workload": "synthetic star 4x10 Mbp, 0.05 subs/site, seed 1, k=21, -b 200 -m 50 -a 150 (BASELINE configs[1])"
-              if a.workload == "star4x10M_k21" else a.workload, "name": a.workload,
+    config = {"workload": DESCRIPTIONS.get(a.workload, a.workload), "name": a.workload,
               "l2_flush": "a 256 MiB device buffer is overwritten before every timed step (outside the timed region)"}
 
     # ------------------------------------------------------------------ reference arm
@@ -150,17 +182,25 @@ def main():
         dbg, fas, k = prepare_workload(a.workload, 0)
         import sibeliaz_b200 as sb
         n_records = sb.JunctionStorage(dbg, fas, k, A).n_records
-        for _ in range(min(warmup, 1)):
+        big = n_records > 5_000_000  # a pass of the reference over the north-star input takes ~20 s: bounded sample
+        ref_steps = min(steps, REF_MAX_STEPS) if big else steps
+        ref_warmup = 0 if big else min(warmup, 1)
+        for _ in range(ref_warmup):
             time_reference(dbg, fas, k, host_threads)
-        t_find = 0.0
-        for _ in range(steps):
-            t_find += time_reference(dbg, fas, k, host_threads)[0]
-        value = steps * n_records / t_find
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": min(warmup, 1),
-                "ms_per_step": 1000.0 * t_find / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/int64",
-                "data": "synthetic", "config": config,
+        t_find, totals = 0.0, []
+        for _ in range(ref_steps):
+            tf, tt = time_reference(dbg, fas, k, host_threads)
+            t_find += tf
+            totals.append(tt)
+        value = ref_steps * n_records / t_find
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": ref_steps, "steps_requested": steps,
+                "warmup": ref_warmup, "ms_per_step": 1000.0 * t_find / ref_steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int32/int64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads, "kind": "reference",
-                                 "sample": "whole workload per step: unmodified reference sibeliaz-lcb -t %d, FindBlocks span" % host_threads},
+                                 "sample": "%d whole passes of the unmodified reference sibeliaz-lcb -t %d over the workload (of %d steps requested: one pass "
+                                           "takes %.1f s); value = records / FindBlocks span (its 'Analyzing the graph...' to 'Generating the output...' lines)"
+                                           % (ref_steps, host_threads, steps, median(totals))},
+                "wall_clock": {"reference_s": median(totals), "threads": host_threads, "runs": len(totals)},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -284,31 +324,56 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
-    try:  # dram__bytes_read+write per launch from the committed ncu --set full captures of this kernel
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))["mean_dram_bytes_per_launch"]
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    for cand in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):
+        # dram__bytes_read+write per launch from the committed ncu --set full captures of this kernel on this workload
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", cand)))
+            t = t.get(a.workload, t if (a.workload == "star4x10M_k21" and "mean_dram_bytes_per_launch" in t) else None)
+            if t:
+                traffic, traffic_src = t["mean_dram_bytes_per_launch"], cand
+                break
+        except Exception:
+            pass
     achieved = (alg_bytes * steps / 1e9) / (trav_ms / 1000.0) if trav_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_traverse", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/ncu_traffic_r1.json)", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, profiles/%s)" % traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes * steps / max(1, trav_launches), "launches_per_step": trav_launches / steps,
                 "kernel_ms_per_step": trav_ms / steps, "kernel_share_of_step": trav_ms / dev_ms if dev_ms else None,
                 "note": "latency-bound dependent random walk: see DESIGN.md section 5"}
-    cpu = None
-    if not a.no_cpu_baseline:
+    cpu, ref_total = None, None
+    if not a.no_cpu_baseline and world == 1:
         try:
-            tf, tt = time_reference(dbg, fas, k, host_threads)
+            tf, ref_total = time_reference(dbg, fas, k, host_threads)
             cpu = {"value": n_records / tf, "unit": UNIT, "cores": host_threads, "kind": "reference",
-                   "sample": "whole workload once: unmodified reference sibeliaz-lcb -t %d; FindBlocks span %.3f s, whole binary %.3f s" % (host_threads, tf, tt)}
+                   "sample": "whole workload once: unmodified reference sibeliaz-lcb -t %d; FindBlocks span %.3f s, whole binary %.3f s" % (host_threads, tf, ref_total)}
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
             cpu = {"value": None, "unit": UNIT, "cores": host_threads, "kind": "reference", "sample": "failed: %s" % e}
+    wall = None
+    if not a.no_wall_clock and world == 1:
+        # whole-binary wall clock (the north-star target is stated on it): same junction file, same flags, same -t
+        try:
+            import filecmp
+            d = os.path.dirname(dbg)
+            sync = [time_cli(dbg, fas, k, host_threads, os.path.join(d, "our_out")) for _ in range(3)]
+            det = [time_cli(dbg, fas, k, host_threads, os.path.join(d, "our_out_detach"), ["--detach"]) for _ in range(3)]
+            time.sleep(1.0)  # the last detached worker is still releasing its context
+            ref_gff = os.path.join(d, "ref_out", "blocks_coords.gff")
+            same = filecmp.cmp(os.path.join(d, "our_out", "blocks_coords.gff"), ref_gff, shallow=False) if os.path.exists(ref_gff) else None
+            wall = {"ours_s": median(sync), "ours_runs_s": [round(x, 3) for x in sync], "ours_detach_s": median(det),
+                    "ours_detach_runs_s": [round(x, 3) for x in det], "reference_s": ref_total, "threads": host_threads,
+                    "ratio": (ref_total / median(sync)) if ref_total else None, "ratio_detach": (ref_total / median(det)) if ref_total else None,
+                    "gff_identical_to_reference": same,
+                    "note": "fork+exec to process exit, CUDA context creation and teardown included; ours_s is the default (one process), "
+                            "ours_detach_s returns when the outputs are complete and a worker releases the GPU afterwards"}
+        except Exception as e:
+            wall = {"error": str(e)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/uint32",
             "data": "synthetic", "config": config, "parity_vs_oracle": parity,
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1000.0 * e2e_t / steps},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "wall_clock": wall,
             "detail": {"records": int(n_records), "seeds": int(stats["n_seeds"]), "block_instances": int(stats["n_block_instances"]),
                        "windows": int(stats["windows"]), "rounds": int(stats["rounds"]), "traversals": int(stats["traversals_first"] + stats["traversals_rerun"]),
                        "wall_ms_per_step": wall_ms / steps, "e2e_last_step_parts": e2e_parts, "ms_enumerate": stats["ms_enumerate"], "oracle_counters": counters}}

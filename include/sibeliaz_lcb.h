@@ -170,6 +170,10 @@ int lcb_write_output(const lcb_index *, const lcb_block_instance *blocks, uint64
                      const char *out_dir, int gen_seq, int chunks, int64_t *blocks_found, double *coverage,
                      char *err, size_t errlen);
 
+/* Upper bound on the host threads the library uses for parsing, packing and output formatting: the `threads`
+ * argument of JunctionStorage / FindBlocks (sibeliaz.cpp:126-141, the CLI's -t).  n <= 0: min(cores, 32). */
+void lcb_set_host_threads(int n);
+
 /* Returns the process-wide cache of device scratch / pinned staging blocks to the driver. */
 void lcb_trim_cache(void);
 

@@ -28,6 +28,7 @@
 #include <cstring>
 
 #include "graph_internal.h"
+#include "lcb_internal.h"
 
 namespace {
 
@@ -518,6 +519,11 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
+        const double need0 = (double)cap * 16.0 + (double)padded * 2.375 + (64 << 20);
+        if (need0 + (double)cap * 4.0 > (double)free_b && lcb_cache_device_bytes(in.device) > 0) {
+            lcb_cache_trim_device(in.device); // scratch parked by the LCB stage (lcb_warmup / lcb_destroy) is reclaimable
+            CU(cudaMemGetInfo(&free_b, &total_b));
+        }
         const double need = (double)cap * (16.0 + (finite_abundance ? 4.0 : 0.0)) + (double)padded * (1.0 + 1.0 + 0.25 + 0.125) + (64 << 20);
         if (need > (double)free_b) {
             err = "the k-mer table (" + std::to_string((unsigned long long)(need / (1 << 20))) + " MiB) does not fit the device (" +

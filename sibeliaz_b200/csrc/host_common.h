@@ -4,6 +4,7 @@
 // namespace: each translation unit gets its own copy.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <cstdint>
 #include <cstdio>
@@ -22,6 +23,8 @@
 #define LCB_ERR_IO 2
 #define LCB_ERR_FORMAT 3
 #endif
+
+extern std::atomic<unsigned> lcb_host_thread_cap; // one per library (defined in lcb_host.cpp); 0 = no cap
 
 namespace {
 
@@ -100,10 +103,15 @@ struct FastaRecords {
     std::vector<std::string> seq;
 };
 
-unsigned WorkerCount()
+// Host threads the library may use for parsing, packing and output formatting: min(cores, 32) (the wrapper's own cap,
+// SibeliaZ-LCB/sibeliaz:139) unless the caller set a lower bound with lcb_set_host_threads (the CLI passes -t).
+inline unsigned WorkerCount()
 {
     unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    return std::min(hw, 32u);
+    unsigned n = std::min(hw, 32u);
+    const unsigned cap = lcb_host_thread_cap.load(std::memory_order_relaxed);
+    if (cap) n = std::min(n, cap);
+    return n;
 }
 
 // runs fn(t, T) on T threads and joins

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +47,8 @@
 #endif
 
 using namespace lcb;
+
+extern std::atomic<unsigned> lcb_host_thread_cap; // lcb_host.cpp
 
 namespace {
 
@@ -758,7 +761,14 @@ cudaError_t cached_alloc(void **p, size_t bytes, int device, bool *want_zeroed)
         }
     }
     if (want_zeroed) *want_zeroed = false;
-    return device < 0 ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes);
+    cudaError_t e = device < 0 ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation && lcb_cache_device_bytes(device) > 0) {
+        // blocks parked by earlier contexts of other sizes are reclaimable memory: give them back and try once more
+        cudaGetLastError();
+        lcb_cache_trim_device(device);
+        e = device < 0 ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes);
+    }
+    return e;
 }
 
 void cached_free(void *p, size_t bytes, int device, bool zeroed = false)
@@ -767,6 +777,41 @@ void cached_free(void *p, size_t bytes, int device, bool zeroed = false)
     std::lock_guard<std::mutex> lk(g_cache_mu);
     g_cache.push_back(CachedBlock{p, bytes, device, zeroed});
 }
+
+} // namespace
+
+size_t lcb_cache_device_bytes(int device)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    size_t n = 0;
+    for (const auto &b : g_cache)
+        if (b.device == device) n += b.bytes;
+    return n;
+}
+
+void lcb_cache_trim_device(int device)
+{
+    std::vector<CachedBlock> mine;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size();)
+            if (g_cache[i].device == device) {
+                mine.push_back(g_cache[i]);
+                g_cache.erase(g_cache.begin() + (long)i);
+            } else {
+                i++;
+            }
+    }
+    int cur = 0;
+    if (device >= 0) cudaGetDevice(&cur), cudaSetDevice(device);
+    for (auto &b : mine) {
+        if (device < 0) cudaFreeHost(b.p);
+        else cudaFree(b.p);
+    }
+    if (device >= 0) cudaSetDevice(cur);
+}
+
+namespace {
 
 constexpr unsigned long long kInstPoolCap = 16ull << 20, kRsPoolCap = 128ull << 20;
 
@@ -1102,6 +1147,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
         for (int i = 0; i <= C; i++) co[(size_t)i] = (uint32_t)v->chr_off[i];
         {
             unsigned T = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+            if (const unsigned cap = lcb_host_thread_cap.load()) T = std::min(T, cap); // lcb_set_host_threads (the CLI's -t)
             std::vector<std::thread> pool;
             std::vector<int> too_many(T, 0);
             for (unsigned t = 0; t < T; t++)

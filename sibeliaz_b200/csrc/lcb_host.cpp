@@ -25,6 +25,10 @@
 #include <unistd.h>
 #include <vector>
 
+std::atomic<unsigned> lcb_host_thread_cap{0};
+
+extern "C" void lcb_set_host_threads(int n) { lcb_host_thread_cap.store(n > 0 ? (unsigned)n : 0u); }
+
 struct lcb_index {
     int k = 0;
     int32_t C = 0;

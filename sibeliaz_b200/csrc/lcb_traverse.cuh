@@ -26,8 +26,15 @@ constexpr int kNotSet = 0x7FFFFFFF;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // ---- capacities -----------------------------------------------------------------------------------
-constexpr int kInstSmem = 32;      // instances kept in shared memory
-constexpr int kHashSmem = 256;     // path hash slots in shared memory (<=128 vertices)
+#ifndef LCB_INST_SMEM
+#define LCB_INST_SMEM 32
+#endif
+#ifndef LCB_HASH_SMEM
+#define LCB_HASH_SMEM 256
+#endif
+constexpr int kInstSmem = LCB_INST_SMEM; // instances kept in shared memory (<= 32: one lane per instance in the searches)
+constexpr int kHashSmem = LCB_HASH_SMEM; // path hash slots in shared memory (half of them usable; a power of two >= 32)
+static_assert(kInstSmem >= 8 && kInstSmem <= 32 && kHashSmem >= 32 && (kHashSmem & (kHashSmem - 1)) == 0, "shared-memory capacities");
 constexpr int kVoteSmem = 128;     // vote table slots in shared memory
 #ifndef LCB_TINY_ARENA
 // per-warp arena; a seed that outgrows any of these is re-run in a big arena slot

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include "host_common.h"
+#include "lcb_internal.h"
 #include "poa_core.cuh"
 #include "sibeliaz_align.h"
 
@@ -242,6 +243,7 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
     d_rows.alloc(rows_cap);
 
     size_t free_b = 0, total_b = 0;
+    lcb_cache_trim_device(prm.device); // scratch parked by an LCB context of this process is invisible to cudaMemGetInfo
     CU(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget = (uint64_t)(free_b * 0.85); // for the arenas of one launch
     int per_sm = 0;

@@ -13,6 +13,7 @@
 #include <unistd.h>
 #include <vector>
 
+#include "cli_common.h"
 #include "sibeliaz_align.h"
 
 int main(int argc, char **argv)
@@ -31,12 +32,19 @@ int main(int argc, char **argv)
             }
             return argv[++i];
         };
+        auto integer = [&](const char *name, int &dst) {
+            const char *v = value(name);
+            if (!cli::ParseInt(v, dst)) {
+                cli::BadValue(v, name);
+                exit(1);
+            }
+        };
         if (a == "--cmd") cmd = value("--cmd");
         else if (a == "-o" || a == "--out") out = value("-o");
-        else if (a == "--gpu") p.device = atoi(value("--gpu"));
-        else if (a == "-m") p.match = atoi(value("-m"));
-        else if (a == "-n") p.mismatch = atoi(value("-n"));
-        else if (a == "-g" || a == "-e") p.gap = atoi(value("-g"));
+        else if (a == "--gpu") integer("--gpu", p.device);
+        else if (a == "-m") integer("-m", p.match);
+        else if (a == "-n") integer("-n", p.mismatch);
+        else if (a == "-g" || a == "-e") integer("-g", p.gap);
         else if (a == "--cleanup") cleanup = true;
         else if (a == "--stats") stats = true;
         else if (a == "-h" || a == "--help") {

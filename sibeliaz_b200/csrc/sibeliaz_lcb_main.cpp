@@ -1,7 +1,11 @@
 // sibeliaz-lcb (B200): drop-in for the reference binary invoked at SibeliaZ-LCB/sibeliaz:146.
 // Same flags, defaults, stdout lines and exit codes as SibeliaZ-LCB/sibeliaz.cpp:37-157; the work is done
-// by libsibeliaz_lcb through its C ABI (include/sibeliaz_lcb.h).  Additive flags: --gpu, --window, --stats, --sync-exit,
-// --construct (fused pipeline: the junctions are found on the GPU from the FASTA files, no --graph file).
+// by libsibeliaz_lcb through its C ABI (include/sibeliaz_lcb.h).  -t bounds the host threads (parsing, packing, output
+// formatting).  Additive flags: --gpu, --window, --stats, --construct (fused pipeline: the junctions are found on the GPU
+// from the FASTA files, no --graph file), --detach (return as soon as the outputs are complete and let a worker process
+// tear the CUDA context down; default is one process that exits when everything is released; --sync-exit, the old name of
+// the default, is still accepted).
+#include "cli_common.h"
 #include "sibeliaz_graph.h"
 #include "sibeliaz_lcb.h"
 
@@ -21,7 +25,7 @@ namespace {
 struct Options {
     unsigned k = 25, b = 200, m = 200, t = 1, a = 150, chunks = 0;
     std::string graph, outdir;
-    bool noseq = false, have_graph = false, stats = false, sync_exit = false, construct = false;
+    bool noseq = false, have_graph = false, stats = false, detach = false, construct = false;
     int gpu = 0, window = 0;
     std::vector<std::string> fasta;
 };
@@ -31,21 +35,13 @@ void Usage(FILE *f)
     fprintf(f,
             "USAGE:\n   sibeliaz-lcb  [--chunks <integer>] [--noseq] [-o <directory name>] --graph <file name>\n"
             "                 [-a <integer>] [-t <integer>] [-m <integer>] [-b <integer>] [-k <oddc>]\n"
-            "                 [--gpu <ordinal>] [--window <seeds>] [--stats] [--sync-exit] [--construct] [--] [--version] [-h]\n"
+            "                 [--gpu <ordinal>] [--window <seeds>] [--stats] [--detach] [--construct] [--] [--version] [-h]\n"
             "                 <fasta files with genomes> ...\n\n"
             "   SibeliaZ-LCB, a program for construction of locally-collinear blocks from complete genomes\n"
             "   (B200-native implementation; flags and outputs follow SibeliaZ-LCB 1.2.7)\n");
 }
 
-bool ParseUnsigned(const char *s, unsigned &out)
-{
-    if (!s || !*s) return false;
-    char *end = nullptr;
-    unsigned long v = strtoul(s, &end, 10);
-    if (*end || s[0] == '-') return false;
-    out = (unsigned)v;
-    return true;
-}
+using cli::ParseUnsigned;
 
 // returns 0 ok, 1 error (message printed), 2 exit quietly with success (help/version)
 int Parse(int argc, char **argv, Options &o)
@@ -120,7 +116,9 @@ int Parse(int argc, char **argv, Options &o)
         } else if (arg == "--stats") {
             o.stats = true;
         } else if (arg == "--sync-exit") {
-            o.sync_exit = true;
+            o.detach = false;
+        } else if (arg == "--detach") {
+            o.detach = true;
         } else if (arg == "--construct") {
             o.construct = true; // no junction file: find the junctions on the GPU too (the twopaco step, fused)
         } else if (arg == "--gpu") {
@@ -162,6 +160,7 @@ int Run(const Options &o, Done done)
     printf("Loading the graph...\n");
     fflush(stdout);
     int device = o.gpu;
+    lcb_set_host_threads((int)o.t); // -t: the caller's thread budget (sibeliaz.cpp:81-87)
     if (!getenv("CUDA_VISIBLE_DEVICES")) {
         // context creation touches every visible GPU of the box: show the driver only the one this job uses
         setenv("CUDA_VISIBLE_DEVICES", std::to_string(o.gpu).c_str(), 1);
@@ -277,11 +276,12 @@ int main(int argc, char **argv)
     int pr = Parse(argc, argv, o);
     if (pr == 2) return 0;
     if (pr) return 1;
-    // The job runs in a worker process.  When its outputs are complete it reports the exit status through a pipe and
-    // this process returns at once; the worker then releases its CUDA context, device and pinned memory (hundreds of
-    // milliseconds on a large GPU) without anybody waiting for it.  --sync-exit keeps everything in one process.
+    // Default: one process; it exits when the outputs are on disk and the CUDA context is released.
+    // --detach: the job runs in a worker process.  When its outputs are complete it reports the exit status through a pipe
+    // and this process returns at once; the worker then releases its CUDA context, device and pinned memory (hundreds of
+    // milliseconds on a large GPU) without anybody waiting for it -- the GPU stays held for that long after the return.
     int report_fd = -1;
-    if (!o.sync_exit) {
+    if (o.detach) {
         int fds[2];
         if (pipe(fds) == 0) {
             fflush(stdout);

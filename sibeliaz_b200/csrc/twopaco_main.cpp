@@ -3,6 +3,7 @@
 // Same flags as TwoPaCo/src/graphconstructor/constructor.cpp:58-143; the Bloom-filter and threading knobs (-f,
 // --filtermemory, -q, -r, -t, --tmpdir) are accepted and ignored: the junctions are found exactly, on the GPU, through
 // libsibeliaz_lcb's C ABI (include/sibeliaz_graph.h).  Additive flags: --gpu <ordinal>, --stats.
+#include "cli_common.h"
 #include "sibeliaz_graph.h"
 
 #include <cstdio>
@@ -29,7 +30,11 @@ int main(int argc, char **argv)
             return argv[++i];
         };
         if (a == "-k" || a == "--kvalue") {
-            k = (unsigned)strtoul(value("-k (--kvalue)"), nullptr, 10);
+            const char *v = value("-k (--kvalue)");
+            if (!cli::ParseUnsigned(v, k)) {
+                cli::BadValue(v, "-k (--kvalue)");
+                return 1;
+            }
             if (k % 2 != 1) {
                 fprintf(stderr, "error: Value '%u' does not meet constraint: value of K must be odd for arg -k (--kvalue)\n", k);
                 return 1;
@@ -40,11 +45,19 @@ int main(int argc, char **argv)
         } else if (a == "-q" || a == "--hashfnumber" || a == "-r" || a == "--rounds" || a == "-t" || a == "--threads" || a == "--tmpdir") {
             value(a.c_str());
         } else if (a == "-a" || a == "--abundance") {
-            abundance = strtoull(value("-a (--abundance)"), nullptr, 10);
+            const char *v = value("-a (--abundance)");
+            if (!cli::ParseU64(v, abundance)) {
+                cli::BadValue(v, "-a (--abundance)");
+                return 1;
+            }
         } else if (a == "-o" || a == "--outfile") {
             out = value("-o (--outfile)");
         } else if (a == "--gpu") {
-            gpu = atoi(value("--gpu"));
+            const char *v = value("--gpu");
+            if (!cli::ParseInt(v, gpu) || gpu < 0) {
+                cli::BadValue(v, "--gpu");
+                return 1;
+            }
         } else if (a == "--stats") {
             stats = true;
         } else if (a == "--test") {

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--dir", default="/tmp/lcb_time")
     ap.add_argument("--dbg", default=None, help="junction file made earlier by the reference twopaco for exactly this synthetic")
+    ap.add_argument("--no-counters", action="store_true", help="timed configuration: the kernel without step counters")
     ap.add_argument("--construct", action="store_true", help="fused pipeline: junctions found on the GPU, no reference twopaco run")
     a = ap.parse_args()
     import numpy as np
@@ -57,7 +58,7 @@ def main():
         st = sb.JunctionStorage(dbg, fas, a.k, 150)
         print("load %.2fs  records %d vertices %d" % (time.time() - t, st.n_records, st.n_vertices), flush=True)
     for rep in range(a.reps):
-        bf = sb.BlocksFinder(st, a.k, window_init=a.window, window_max=a.wmax or a.window, collect_counters=(2 if os.environ.get('LCB_TRACE_ROUNDS') else True))
+        bf = sb.BlocksFinder(st, a.k, window_init=a.window, window_max=a.wmax or a.window, collect_counters=(False if a.no_counters else (2 if os.environ.get('LCB_TRACE_ROUNDS') else True)))
         t = time.time()
         bf.create(50, 200)
         t_create = time.time() - t
