@@ -121,6 +121,7 @@ typedef struct lcb_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t pool_restarts;                /* active sets abandoned because a result pool ran full */
     uint64_t big_arena_runs;               /* evaluations that outgrew the per-warp scratch and were re-run in a big slot */
+    uint64_t lean_runs, lean_bails;        /* evaluations finished by the common-case kernel / handed on to the general kernel */
 } lcb_stats;
 
 void lcb_default_params(lcb_params *p);

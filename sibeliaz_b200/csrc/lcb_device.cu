@@ -38,6 +38,7 @@
 #include <vector>
 
 #include "lcb_traverse.cuh"
+#include "lcb_lean.cuh"
 #include "graph_internal.h"
 #include "lcb_internal.h"
 
@@ -59,8 +60,10 @@ constexpr int kWarpsPerBlock = 4;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
 struct Control { // device-resident round state, mirrored to pinned host memory once per round
-    unsigned head;      // work-queue cursor of the running traversal launch
+    unsigned head;      // work-queue cursor of the running traversal launch (common-case kernel, or the only kernel)
     unsigned max_ns;    // longest single evaluation since the last reset (globaltimer ns, saturating)
+    unsigned head_heavy; // work-queue cursor of the general kernel when it runs behind the common-case kernel
+    unsigned n_heavy;   // items the common-case kernel handed to the general one this round
     unsigned n0, n1;    // length of the work list (bit 31 of an item: commit-time re-run only); n1 unused
     unsigned dirty;     // seeds whose dependencies changed in the last validation
     unsigned first_dirty; // smallest such seed index (0xFFFFFFFF: none): everything before it is final
@@ -71,6 +74,19 @@ struct Control { // device-resident round state, mirrored to pinned host memory 
     unsigned long long runs0, runs1;
     unsigned blocks_done, out_done; // emit: blocks / instances committed so far
     unsigned long long dbg[6];
+    unsigned long long lean_runs, lean_bails; // evaluations finished by the common-case kernel / handed to the general one
+    // ---- device-driven schedule (single GPU): the round loop's decisions are taken by k_round_begin / k_round_end, the host
+    // only keeps launches queued and watches `Mirror` in pinned memory
+    unsigned c0, c1;          // rolling active set [c0, c1): commit frontier, admission frontier
+    unsigned admit_lo, admit, admit_n0; // seeds admitted at the beginning of this round; length of the work list before them
+    unsigned delta, cap;      // admission rate (adapted every round), bound on the active set
+    unsigned drain, hold;     // result pools half full / heavy re-evaluations occupy the warps: no admission
+    unsigned n_seeds;
+    unsigned parity;          // which epoch buffer is current
+    unsigned done, halt;      // all seeds committed / the host must look (error, pool overflow)
+    unsigned rounds, windows;
+    unsigned commit_first, commit_n; // prefix committed by this round's emit kernels
+    unsigned long long t_first, t_last; // %globaltimer bracket of this round's traversal kernels
     unsigned big_runs;            // evaluations that outgrew the per-warp arena and ran in a big slot
     unsigned big_lock[kBigSlots]; // 1 = big arena slot taken (always released by its holder)
 };
@@ -79,8 +95,10 @@ struct Window { // per-seed arrays of the active seeds, ring-indexed by j = seed
     unsigned *res_off[2], *res_cnt[2]; // best instances of slot s in inst_pool
     unsigned *rs_off[2], *rs_cnt[2];   // read-set of slot s in rs_pool
     unsigned char *conf, *has1;
+    unsigned char *heavy; // the seed needs the general kernel (it made the common-case kernel bail once)
     unsigned *blk, *out_off;
     unsigned *list0;
+    unsigned *list_heavy;
     int4 *inst_pool;
     int2 *rs_pool;
     unsigned long long inst_cap, rs_cap;
@@ -169,9 +187,9 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
                                                         const int *__restrict__ seed_vid,
                                                         const unsigned char *__restrict__ seed_ch,
                                                         unsigned phase, int force_slot, const unsigned *__restrict__ list,
-                                                        const unsigned *__restrict__ n_ptr, Window win, Control *ctl,
-                                                        unsigned char *arena_base, size_t arena_stride, unsigned char *big_base,
-                                                        int collect)
+                                                        const unsigned *__restrict__ n_ptr, unsigned *__restrict__ cursor, Window win,
+                                                        Control *ctl, unsigned char *arena_base, size_t arena_stride,
+                                                        unsigned char *big_base, int collect)
 {
     __shared__ WarpSmem smem[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -189,12 +207,13 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
     c.vote_clean = false;
     arena_bind(c, arena_base + warp_global * arena_stride, false);
     int big_slot = -1; // >= 0: this warp holds that big arena slot
-    const unsigned n = *n_ptr;
+    const unsigned n = (ctl->halt | ctl->done) ? 0u : *n_ptr; // (a round queued behind the one that ended the run, or stopped it)
+    if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&ctl->t_first, global_ns());
     unsigned done = 0, done1 = 0;
     unsigned long long longest = 0;
     while (true) {
         unsigned idx = 0;
-        if (lane == 0) idx = atomicAdd(&ctl->head, 1u);
+        if (lane == 0) idx = atomicAdd(cursor, 1u);
         idx = __shfl_sync(kFull, idx, 0);
         if (idx >= n) break;
         const unsigned item = list[idx];
@@ -295,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
         if (longest) atomicMax(&ctl->max_ns, (unsigned)min(longest, 0xFFFFFFFFull));
         if (done) atomicAdd(&ctl->runs0, (unsigned long long)done);
         if (done1) atomicAdd(&ctl->runs1, (unsigned long long)done1);
+        if (done + done1) atomicMax(&ctl->t_last, global_ns());
         if (collect) {
             atomicAdd(&ctl->ct_walk, c.ct.walk);
             atomicAdd(&ctl->ct_occ, c.ct.occ);
@@ -307,6 +327,133 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
             atomicAdd(&ctl->dbg[4], (unsigned long long)c.ct.push_ser);
             atomicAdd(&ctl->dbg[5], (unsigned long long)c.ct.mpv_mid);
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// common-case traversal kernel (lcb_lean.cuh): same work list, same publication; what it cannot evaluate goes to
+// `win.list_heavy` for the general kernel, which runs right behind it in the same round
+// ------------------------------------------------------------------------------------------------
+#ifndef LCB_LEAN_CTAS_PER_SM
+#define LCB_LEAN_CTAS_PER_SM 6
+#endif
+constexpr int kLeanRs = 4096; // read-set intervals per evaluation in the common-case kernel's log (more: general kernel)
+
+__global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lean(Index ix, Params pr, const uint32_t *__restrict__ E,
+                                                        const int *__restrict__ seed_vid,
+                                                        const unsigned char *__restrict__ seed_ch, unsigned phase,
+                                                        const unsigned *__restrict__ list, const unsigned *__restrict__ n_ptr,
+                                                        Window win, Control *ctl, int2 *__restrict__ rs_base)
+{
+    __shared__ lean::LeanSmem smem[kWarpsPerBlock];
+    __shared__ uint32_t chr_off_s[lean::kLChr];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i <= ix.C; i += blockDim.x) chr_off_s[i] = ix.chr_off[i];
+    { // the hash and the vote table start empty and every evaluation leaves them so
+        lean::LeanSmem *sm = &smem[wib];
+        for (int i = lane; i < lean::kLHash; i += 32) sm->hash[i] = make_int2(0, 0);
+        for (int i = lane; i < lean::kLVote; i += 32) sm->vote[i] = make_int2(0, 0), sm->vlast[i] = 0u;
+#ifdef LCB_TMA_WINDOWS
+        if (lane == 0) lean::mbar_init(&sm->mbar);
+#endif
+    }
+    __syncthreads();
+    const size_t warp_global = (size_t)blockIdx.x * kWarpsPerBlock + wib;
+    lean::LCtx c;
+    c.rec = ix.rec, c.occ = ix.occ, c.vtx_off = ix.vtx_off, c.E = E;
+    c.chr_off_s = chr_off_s, c.C = ix.C;
+    c.b = pr.b, c.m = pr.m, c.flank = pr.flank, c.depth = pr.depth;
+    c.lane = lane;
+    c.sm = &smem[wib];
+    c.rs = rs_base + warp_global * (size_t)kLeanRs;
+    c.rs_cap = kLeanRs;
+#ifdef LCB_TMA_WINDOWS
+    c.tma_phase = 0;
+#endif
+    const unsigned n = (ctl->halt | ctl->done) ? 0u : *n_ptr; // (a round queued behind the one that ended the run, or stopped it)
+    if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&ctl->t_first, global_ns());
+    unsigned done = 0, done1 = 0, bails = 0;
+    unsigned long long longest = 0;
+    while (true) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(&ctl->head, 1u);
+        idx = __shfl_sync(kFull, idx, 0);
+        if (idx >= n) break;
+        const unsigned item = list[idx];
+        const unsigned i = item & 0x7FFFFFFFu;
+        const unsigned j = i & win.mask;
+        int slot = (int)(item >> 31); // bit 31: commit-time re-run queued by the validation
+        if (win.heavy[j]) { // known to need the general kernel
+            if (lane == 0) win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = item;
+            continue;
+        }
+        while (true) {
+            c.thresh = slot == 0 ? (i / phase) * phase : i;
+            const unsigned long long t_begin = global_ns();
+            const int r = lean::process_seed(c, seed_vid[i], seed_ch[i]);
+            if (r != lean::kOk) { // the rest of this item (the evaluation that failed and what follows it) is the general kernel's
+                if (lane == 0) {
+                    win.heavy[j] = 1;
+                    win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = i | (slot ? 0x80000000u : 0u);
+                }
+                bails++;
+                break;
+            }
+            longest = max(longest, global_ns() - t_begin);
+            unsigned long long io = 0, ro = 0;
+            if (lane == 0) {
+                io = atomicAdd(&ctl->inst_used, (unsigned long long)c.nbest);
+                ro = atomicAdd(&ctl->rs_used, (unsigned long long)c.nrs);
+            }
+            io = __shfl_sync(kFull, io, 0);
+            ro = __shfl_sync(kFull, ro, 0);
+            if (io + c.nbest > win.inst_cap || ro + c.nrs > win.rs_cap) {
+                if (lane == 0) {
+                    atomicExch(&ctl->pool_overflow, 1u);
+                    win.res_cnt[slot][j] = 0;
+                    win.rs_cnt[slot][j] = 0;
+                }
+                break;
+            }
+            if (lane < c.nbest) win.inst_pool[io + lane] = c.sm->best[lane];
+            for (int t = lane; t < c.nrs; t += 32) win.rs_pool[ro + t] = c.rs[t];
+            if (lane == 0) {
+                win.res_off[slot][j] = (unsigned)io;
+                win.res_cnt[slot][j] = (unsigned)c.nbest;
+                win.rs_off[slot][j] = (unsigned)ro;
+                win.rs_cnt[slot][j] = (unsigned)c.nrs;
+            }
+            if (slot != 0) {
+                done1++;
+                break;
+            }
+            done++;
+            bool conf = false; // commit-time conflict test of the fresh result: any of its edges claimed by a seed < i?
+            if (c.nbest > 1)
+                for (int t = 0; t < c.nbest && !conf; t++) {
+                    int lo, hi;
+                    inst_edges(c.sm->best[t], lo, hi);
+                    for (int base = lo; base <= hi && !conf; base += 32) {
+                        const int f = base + lane;
+                        conf = __any_sync(kFull, f <= hi && __ldg(E + f) < i);
+                    }
+                }
+            if (lane == 0) {
+                win.conf[j] = conf;
+                win.has1[j] = conf;
+            }
+            if (!conf) break;
+            slot = 1;
+        }
+    }
+    if (lane == 0) {
+        if (longest) atomicMax(&ctl->max_ns, (unsigned)min(longest, 0xFFFFFFFFull));
+        if (done) atomicAdd(&ctl->runs0, (unsigned long long)done);
+        if (done1) atomicAdd(&ctl->runs1, (unsigned long long)done1);
+        if (done + done1) atomicAdd(&ctl->lean_runs, (unsigned long long)(done + done1));
+        if (done + done1 + bails) atomicMax(&ctl->t_last, global_ns());
+        if (bails) atomicAdd(&ctl->lean_bails, (unsigned long long)bails);
     }
 }
 
@@ -336,8 +483,15 @@ __device__ __forceinline__ void final_result(const Window &win, unsigned j, unsi
 }
 
 // start of a round's new epochs: the committed claims only (claims of seeds < c0 are final and minimal)
-__global__ void k_rebase(uint32_t *dst, const uint32_t *src, size_t n, uint32_t c0) // dst may alias src
+// `sched` (device-driven schedule): the frontier comes from the control block, and thread 0 resets the validation counters
+// (this kernel runs between the traversal, which reads n0, and the validation, which rebuilds it)
+__global__ void k_rebase(uint32_t *dst, const uint32_t *src, size_t n, uint32_t c0, Control *sched) // dst may alias src
 {
+    if (sched) {
+        if (sched->done | sched->halt) return;
+        c0 = sched->c0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) sched->n0 = 0, sched->n1 = 0, sched->dirty = 0, sched->first_dirty = 0xFFFFFFFFu;
+    }
     for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (size_t)gridDim.x * blockDim.x) {
         const uint32_t e = src[f];
         dst[f] = e < c0 ? e : kFree;
@@ -345,8 +499,12 @@ __global__ void k_rebase(uint32_t *dst, const uint32_t *src, size_t n, uint32_t 
 }
 
 // epoch'[e] = min(seed index) over the final results of the active seeds [lo, hi)
-__global__ void k_claim(uint32_t *__restrict__ Enew, unsigned lo_seed, unsigned hi_seed, Window win)
+__global__ void k_claim(uint32_t *__restrict__ Enew, unsigned lo_seed, unsigned hi_seed, Window win, const Control *sched)
 {
+    if (sched) {
+        if (sched->done | sched->halt) return;
+        lo_seed = sched->c0, hi_seed = sched->c1;
+    }
     const int lane = threadIdx.x & 31;
     for (unsigned i = lo_seed + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < hi_seed; i += gridDim.x * (blockDim.x >> 5)) {
         unsigned off, cnt;
@@ -377,8 +535,12 @@ __device__ __forceinline__ bool readset_changed(const int2 *rs, unsigned cnt, co
 
 // re-validate every seed of the window against the new epochs; build next round's work lists
 __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned lo_seed,
-                           unsigned hi_seed, unsigned phase, Window win, Control *ctl)
+                           unsigned hi_seed, unsigned phase, Window win, Control *ctl, int sched)
 {
+    if (sched) {
+        if (ctl->done | ctl->halt) return;
+        lo_seed = ctl->c0, hi_seed = ctl->c1;
+    }
     const int lane = threadIdx.x & 31;
     for (unsigned i = lo_seed + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < hi_seed; i += gridDim.x * (blockDim.x >> 5)) {
         const unsigned j = i & win.mask;
@@ -418,37 +580,119 @@ __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__
 }
 
 // admission of the seeds [lo, lo + n): fresh per-seed state; this rank's share (i % R == me) joins work list 0
-__global__ void k_admit(unsigned lo, unsigned n, unsigned R, unsigned me, unsigned n0_before, Window win, Control *ctl)
+__global__ void k_admit(unsigned lo, unsigned n, unsigned R, unsigned me, unsigned n0_before, Window win, Control *ctl, int sched)
 {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sched) { // k_round_begin has decided what to admit and has already set the new length of the work list
+        if (ctl->done | ctl->halt) return;
+        lo = ctl->admit_lo, n = ctl->admit, n0_before = ctl->admit_n0;
+    }
     const unsigned first_own = lo + (me + R - lo % R) % R; // smallest i >= lo with i % R == me
-    if (t == 0) ctl->n0 = n0_before + (lo + n > first_own ? (lo + n - first_own + R - 1) / R : 0u);
-    if (t >= n) return;
-    const unsigned i = lo + t, j = i & win.mask;
-    win.res_cnt[0][j] = win.res_cnt[1][j] = 0;
-    win.rs_cnt[0][j] = win.rs_cnt[1][j] = 0;
-    win.conf[j] = 0;
-    win.has1[j] = 0;
-    if (i % R == me) win.list0[n0_before + (i - first_own) / R] = i;
+    if (!sched && blockIdx.x == 0 && threadIdx.x == 0) ctl->n0 = n0_before + (lo + n > first_own ? (lo + n - first_own + R - 1) / R : 0u);
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const unsigned i = lo + t, j = i & win.mask;
+        win.res_cnt[0][j] = win.res_cnt[1][j] = 0;
+        win.rs_cnt[0][j] = win.rs_cnt[1][j] = 0;
+        win.conf[j] = 0;
+        win.has1[j] = 0;
+        win.heavy[j] = 0;
+        if (i % R == me) win.list0[n0_before + (i - first_own) / R] = i;
+    }
+}
+
+struct SchedParams { // admission thresholds of the round loop (developer knobs, see lcb_find_blocks)
+    float grow_below, min_round_ms, shrink_above, heavy_ms;
+    unsigned phase, window_max, warps;
+    unsigned long long inst_cap, rs_cap;
+};
+
+// start of a round: admission decision (what the host loop of lcb_find_blocks decides between two rounds)
+__global__ void k_round_begin(Control *ctl)
+{
+    if (ctl->done | ctl->halt) return;
+    if (ctl->c0 == ctl->c1) { // nothing active: no pool entry is referenced any more
+        ctl->inst_used = 0, ctl->rs_used = 0;
+        ctl->drain = 0;
+        ctl->n0 = 0;
+        ctl->windows++;
+    }
+    const unsigned c0 = ctl->c0, c1 = ctl->c1, S = ctl->n_seeds, cap = ctl->cap;
+    unsigned admit = 0;
+    if (!ctl->drain && !(ctl->hold && c1 > c0) && c1 < S && c1 - c0 < cap) admit = min(min(ctl->delta, S - c1), cap - (c1 - c0));
+    ctl->admit_lo = c1, ctl->admit = admit, ctl->admit_n0 = ctl->n0;
+    ctl->n0 += admit;
+    ctl->c1 = c1 + admit;
+    ctl->rounds++;
+    ctl->head = 0, ctl->max_ns = 0, ctl->head_heavy = 0, ctl->n_heavy = 0;
+    ctl->t_first = ~0ull, ctl->t_last = 0;
+}
+
+struct Mirror { // pinned host memory the device writes at the end of every round
+    volatile unsigned rounds_done, done, halt, c0;
+};
+
+// end of a round: admission rate for the next one, commit frontier, epoch buffer swap
+__global__ void k_round_end(Control *ctl, SchedParams sp, Mirror *mirror)
+{
+    if (ctl->done | ctl->halt) { // a round queued behind the last one: nothing to commit (the emit kernels follow unconditionally)
+        ctl->commit_n = 0;
+        return;
+    }
+    if (ctl->inst_used * 2 > sp.inst_cap || ctl->rs_used * 2 > sp.rs_cap) ctl->drain = 1;
+    // Admission rate: a launch lasts max(longest evaluation, work / resident warps).  While it is latency-bound more fresh
+    // seeds are free; when the fresh work dominates, far-ahead speculation only adds re-evaluations.
+    const float ms = ctl->t_last > ctl->t_first ? (float)(ctl->t_last - ctl->t_first) * 1e-6f : 0.f;
+    const float longest_ms = (float)ctl->max_ns * 1e-6f;
+    const unsigned delta = ctl->delta;
+    unsigned next_delta = delta, hold = 0;
+    if (ms < sp.grow_below * longest_ms || ms < sp.min_round_ms) next_delta = (unsigned)min((unsigned long long)sp.window_max, 2ull * delta);
+    else if (ms > sp.shrink_above * longest_ms && ms > 2 * sp.min_round_ms) next_delta = max(sp.phase, delta / 2 / sp.phase * sp.phase);
+    if (longest_ms > sp.heavy_ms) { // heavy evaluations: fresh seeds are free only while warps are left over
+        if (ctl->n0 + sp.phase > sp.warps) hold = 1;
+        else next_delta = min(next_delta, max(sp.phase, (sp.warps - ctl->n0) / sp.phase * sp.phase));
+    }
+    ctl->hold = hold;
+    if (ctl->err | ctl->pool_overflow) { // the host handles both (error report / restart with half the active set)
+        ctl->halt = 1;
+        ctl->commit_n = 0;
+    } else {
+        const unsigned fd = min(ctl->first_dirty, ctl->c1);
+        ctl->commit_first = ctl->c0;
+        ctl->commit_n = fd > ctl->c0 ? fd - ctl->c0 : 0u;
+        if (fd > ctl->c0) ctl->c0 = fd;
+        ctl->parity ^= 1u;
+        ctl->delta = min(next_delta, ctl->cap);
+        if (ctl->c0 >= ctl->n_seeds) ctl->done = 1;
+    }
+    mirror->c0 = ctl->c0;
+    mirror->done = ctl->done;
+    mirror->halt = ctl->halt;
+    __threadfence_system();
+    mirror->rounds_done = ctl->rounds;
+    __threadfence_system();
 }
 
 
 // Finalize (blocksfinder.h:312-332) for a converged window: block ids and output offsets are prefix
 // sums in seed order (one block, W <= 65536)
 // per-seed size of the final result (0 for seeds this rank does not own); summed across ranks before the scan
-__global__ void k_final_counts(unsigned lo, unsigned n, Window win, unsigned *cnt_out)
+__global__ void k_final_counts(unsigned lo, unsigned n, Window win, unsigned *cnt_out, const Control *sched)
 {
-    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    unsigned off, cnt;
-    final_result(win, (lo + t) & win.mask, off, cnt);
-    cnt_out[t] = cnt;
+    if (sched) lo = sched->commit_first, n = (sched->halt ? 0u : sched->commit_n); // (commit_n of the round that set `done` still counts)
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        unsigned off, cnt;
+        final_result(win, (lo + t) & win.mask, off, cnt);
+        cnt_out[t] = cnt;
+    }
 }
 
 __global__ void __launch_bounds__(1024) k_emit_scan(unsigned first, unsigned n, Window win, Control *ctl,
-                                                     const unsigned *__restrict__ counts)
+                                                     const unsigned *__restrict__ counts, int sched)
 {
     __shared__ unsigned sb[1024], so[1024];
+    if (sched) {
+        first = ctl->commit_first, n = (ctl->halt ? 0u : ctl->commit_n);
+        if (n == 0) return;
+    }
     const unsigned blocks_before = ctl->blocks_done, out_before = ctl->out_done; // updated after the scan's barriers
     const unsigned per = (n + 1023) / 1024;
     const unsigned lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
@@ -479,10 +723,10 @@ __global__ void __launch_bounds__(1024) k_emit_scan(unsigned first, unsigned n, 
     }
 }
 
-__global__ void k_emit_write(Index ix, int k, unsigned first, unsigned n, Window win, lcb_block_instance *out)
+__global__ void k_emit_write(Index ix, int k, unsigned first, unsigned n, Window win, lcb_block_instance *out, Control *sched)
 {
-    unsigned t_ = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t_ >= n) return;
+    if (sched) first = sched->commit_first, n = (sched->halt ? 0u : sched->commit_n);
+    for (unsigned t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < n; t_ += gridDim.x * blockDim.x) {
     const unsigned j = (first + t_) & win.mask;
     unsigned off, cnt;
     final_result(win, j, off, cnt);
@@ -508,6 +752,7 @@ __global__ void k_emit_write(Index ix, int k, unsigned first, unsigned n, Window
             r.end = (uint32_t)b.z + (uint32_t)k;
         }
         out[win.out_off[j] + t] = r;
+    }
     }
 }
 
@@ -702,6 +947,8 @@ struct lcb_ctx {
     size_t arena_stride = 0;
     size_t d_big = 0;
     int grid_traverse = 0;
+    int grid_lean = 0;         // 0: the common-case kernel is not used (see use_lean in create_end)
+    int2 *d_lean_rs = nullptr; // its per-warp read-set logs
     lcb_block_instance *d_out = nullptr;
     lcb_stats st{};
     int rank = 0, n_ranks = 1;
@@ -715,6 +962,10 @@ struct lcb_ctx {
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
     bool step_timed = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device-driven round loop (single GPU)
+    Mirror *h_mirror = nullptr;                         // pinned; written by k_round_end
+    cudaGraphExec_t tail_graph[2] = {nullptr, nullptr}; // the non-traversal part of a round + the next round's admission, per epoch-buffer parity
+    std::vector<cudaEvent_t> ev_ring;                   // event pairs around the traversal launches of the rounds in flight
 };
 
 namespace {
@@ -916,10 +1167,13 @@ extern "C" int lcb_warmup(int device)
         // CUDA loads kernels lazily, on first use: touch all of them here, off the critical path
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_traverse<false>);
+        cudaFuncGetAttributes(&fa, k_traverse_lean);
         cudaFuncGetAttributes(&fa, k_rebase);
         cudaFuncGetAttributes(&fa, k_claim);
         cudaFuncGetAttributes(&fa, k_validate);
         cudaFuncGetAttributes(&fa, k_admit);
+        cudaFuncGetAttributes(&fa, k_round_begin);
+        cudaFuncGetAttributes(&fa, k_round_end);
         cudaFuncGetAttributes(&fa, k_final_counts);
         cudaFuncGetAttributes(&fa, k_emit_scan);
         cudaFuncGetAttributes(&fa, k_emit_write);
@@ -963,6 +1217,10 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     if (ctx->ev_step0) cudaEventDestroy(ctx->ev_step0);
     if (ctx->ev_step1) cudaEventDestroy(ctx->ev_step1);
     if (ctx->h_ctl) cached_free(ctx->h_ctl, sizeof(Control), -1);
+    if (ctx->h_mirror) cached_free(ctx->h_mirror, sizeof(Mirror), -1);
+    for (auto &g : ctx->tail_graph)
+        if (g) cudaGraphExecDestroy(g);
+    for (auto &e : ctx->ev_ring) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1050,6 +1308,8 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
     if ((rc = dev_alloc(ctx, &ctx->win.blk, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.out_off, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.list0, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.list_heavy, W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->win.heavy, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_wnext, 8))) return rc;
     ctx->win.inst_cap = kInstPoolCap;
@@ -1069,6 +1329,15 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
     ctx->grid_traverse = per_sm * ctx->sms;
+    // The common-case kernel (lcb_lean.cuh) takes every work item first when its preconditions hold for the whole run;
+    // LCB_NO_LEAN=1 keeps the general kernel alone (A/B runs, and the step counters live only there).
+    ctx->grid_lean = 0;
+    if (ctx->ix.C + 1 <= lean::kLChr && p.max_flank <= 32767 && !p.collect_counters && !getenv("LCB_NO_LEAN")) {
+        int lean_per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lean_per_sm, k_traverse_lean, kThreads, 0));
+        ctx->grid_lean = std::max(lean_per_sm, 1) * ctx->sms;
+        if ((rc = dev_alloc(ctx, &ctx->d_lean_rs, (size_t)ctx->grid_lean * kWarpsPerBlock * kLeanRs))) return rc;
+    }
     lap("occupancy query");
     ctx->arena_stride = arena_stride_bytes();
     const size_t arena_bytes = arena_total_bytes((size_t)ctx->grid_traverse * kWarpsPerBlock);
@@ -1530,15 +1799,25 @@ namespace {
 int launch_traverse(lcb_ctx *ctx, const uint32_t *E, int slot, const unsigned *list, const unsigned *n_ptr, bool reset_longest)
 {
     Params pr{ctx->prm.k, ctx->prm.max_branch, ctx->prm.min_block, ctx->prm.max_flank, ctx->prm.looking_depth};
-    CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, (reset_longest ? 2 : 1) * sizeof(unsigned), ctx->stream)); // head (+ max_ns)
+    if (reset_longest) // (the device-driven loop resets them in k_round_begin)
+        CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, 4 * sizeof(unsigned), ctx->stream)); // head, max_ns, head_heavy, n_heavy
+    unsigned *cursor = &ctx->d_ctl->head;
+    if (ctx->grid_lean > 0 && slot < 0) {
+        // the common case first; what it hands back is evaluated by the general kernel right behind it
+        k_traverse_lean<<<ctx->grid_lean, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
+                                                                      (unsigned)ctx->prm.phase_size, list, n_ptr, ctx->win, ctx->d_ctl,
+                                                                      ctx->d_lean_rs);
+        ctx->st.kernel_launches++;
+        list = ctx->win.list_heavy, n_ptr = &ctx->d_ctl->n_heavy, cursor = &ctx->d_ctl->head_heavy;
+    }
     if (ctx->prm.collect_counters)
         k_traverse<true><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
-                                                                           (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
+                                                                           (unsigned)ctx->prm.phase_size, slot, list, n_ptr, cursor, ctx->win,
                                                                            ctx->d_ctl, ctx->d_arena, ctx->arena_stride, ctx->d_arena + ctx->d_big,
                                                                            ctx->prm.collect_counters);
     else
         k_traverse<false><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
-                                                                            (unsigned)ctx->prm.phase_size, slot, list, n_ptr, ctx->win,
+                                                                            (unsigned)ctx->prm.phase_size, slot, list, n_ptr, cursor, ctx->win,
                                                                             ctx->d_ctl, ctx->d_arena, ctx->arena_stride, ctx->d_arena + ctx->d_big, 0);
     ctx->st.kernel_launches++;
     ctx->st.traverse_launches++;
@@ -1550,6 +1829,171 @@ int fetch_control(lcb_ctx *ctx)
     CUDA_TRY(cudaMemcpyAsync(ctx->h_ctl, ctx->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaGetLastError());
+    return LCB_OK;
+}
+
+} // namespace
+
+
+namespace {
+
+constexpr int kRoundsInFlight = 4; // rounds the host keeps queued ahead of the device
+constexpr int kEvRing = 16;        // event pairs (> kRoundsInFlight)
+
+// the non-traversal part of round r (epochs, validation, schedule, commit) followed by the admission of round r + 1
+int enqueue_tail(lcb_ctx *ctx, int parity, const SchedParams &sp)
+{
+    const size_t N = (size_t)ctx->ix.N;
+    uint32_t *Ecur = ctx->d_E[parity], *Enew = ctx->d_E[parity ^ 1];
+    const unsigned vgrid = (unsigned)ctx->sms * 8;
+    const unsigned egrid = (unsigned)std::min<size_t>((N + 1023) / 1024 + 1, (size_t)ctx->sms * 16);
+    const unsigned sgrid = (unsigned)ctx->sms * 4; // grid-stride kernels over admitted / committed seeds
+    cudaStream_t st = ctx->stream;
+    k_rebase<<<egrid, 256, 0, st>>>(Enew, Ecur, N, 0u, ctx->d_ctl);
+    k_claim<<<vgrid, 256, 0, st>>>(Enew, 0u, 0u, ctx->win, ctx->d_ctl);
+    k_validate<<<vgrid, 256, 0, st>>>(Ecur, Enew, 0u, 0u, (unsigned)ctx->prm.phase_size, ctx->win, ctx->d_ctl, 1);
+    k_round_end<<<1, 1, 0, st>>>(ctx->d_ctl, sp, ctx->h_mirror);
+    k_final_counts<<<sgrid, 256, 0, st>>>(0u, 0u, ctx->win, ctx->d_counts, ctx->d_ctl);
+    k_emit_scan<<<1, 1024, 0, st>>>(0u, 0u, ctx->win, ctx->d_ctl, ctx->d_counts, 1);
+    k_emit_write<<<sgrid, 256, 0, st>>>(ctx->ix, ctx->prm.k, 0u, 0u, ctx->win, ctx->d_out, ctx->d_ctl);
+    k_round_begin<<<1, 1, 0, st>>>(ctx->d_ctl);
+    k_admit<<<sgrid, 256, 0, st>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
+    CUDA_TRY(cudaGetLastError());
+    return LCB_OK;
+}
+constexpr unsigned kTailKernels = 9;
+
+// Single-GPU round loop driven from the device: every decision of a round (admission, commit frontier, buffer swap) is taken
+// by k_round_begin / k_round_end from the control block, so the host never waits for a round: it keeps kRoundsInFlight rounds
+// queued (two traversal launches + one graph launch each) and watches a few words the device writes to pinned memory.
+int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
+{
+    const unsigned S = (unsigned)ctx->n_seeds;
+    const unsigned phase = (unsigned)ctx->prm.phase_size;
+    const size_t N = (size_t)ctx->ix.N;
+    const bool trace_rounds = getenv("LCB_TRACE_ROUNDS") != nullptr;
+    const bool use_graph = !getenv("LCB_NO_GRAPH");
+    SchedParams sp;
+    sp.grow_below = getenv("LCB_GROW_BELOW") ? (float)atof(getenv("LCB_GROW_BELOW")) : 1.2f;
+    sp.min_round_ms = getenv("LCB_MIN_ROUND_MS") ? (float)atof(getenv("LCB_MIN_ROUND_MS")) : 0.6f;
+    sp.shrink_above = getenv("LCB_SHRINK_ABOVE") ? (float)atof(getenv("LCB_SHRINK_ABOVE")) : 2.0f;
+    sp.heavy_ms = getenv("LCB_HEAVY_MS") ? (float)atof(getenv("LCB_HEAVY_MS")) : 20.0f;
+    sp.phase = phase;
+    sp.window_max = (unsigned)ctx->prm.window_max;
+    sp.warps = (unsigned)(ctx->grid_traverse * kWarpsPerBlock);
+    sp.inst_cap = ctx->win.inst_cap, sp.rs_cap = ctx->win.rs_cap;
+    if (!ctx->h_mirror) CUDA_TRY(cached_alloc((void **)&ctx->h_mirror, sizeof(Mirror), -1, nullptr));
+    if (ctx->ev_ring.empty()) {
+        ctx->ev_ring.resize(2 * kEvRing);
+        for (auto &e : ctx->ev_ring) CUDA_TRY(cudaEventCreate(&e));
+    }
+    Mirror *mir = ctx->h_mirror;
+    mir->rounds_done = 0, mir->done = 0, mir->halt = 0, mir->c0 = 0;
+    // ---- initial control block
+    Control &h = *ctx->h_ctl;
+    memset(&h, 0, sizeof(Control));
+    h.first_dirty = 0xFFFFFFFFu;
+    h.n_seeds = S;
+    h.cap = (unsigned)ctx->prm.window_max;
+    h.delta = (unsigned)ctx->prm.window_init;
+    if (ctx->max_seed_count >= 32) // see lcb_find_blocks: repeat-rich inputs start with one wave of warps
+        h.delta = std::min(h.delta, std::max(phase, sp.warps / phase * phase));
+    if (S == 0) h.done = 1;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_ctl, &h, sizeof(Control), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // ---- the tail of a round as a graph (one per parity); captured once per context
+    if (use_graph && !ctx->tail_graph[0]) {
+        for (int par = 0; par < 2; par++) {
+            cudaGraph_t g = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_tail(ctx, par, sp);
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            if (rc) return rc;
+            CUDA_TRY(e);
+            CUDA_TRY(cudaGraphInstantiate(&ctx->tail_graph[par], g, 0));
+            cudaGraphDestroy(g);
+        }
+    }
+    const unsigned sgrid = (unsigned)ctx->sms * 4;
+    k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
+    k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
+    ctx->st.kernel_launches += 2;
+    unsigned launched = 0, timed = 0;
+    int parity = 0, rc;
+    auto collect_times = [&](unsigned upto) { // rounds < upto are complete: read their event pairs
+        for (; timed < upto; timed++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev_ring[2 * (timed % kEvRing)], ctx->ev_ring[2 * (timed % kEvRing) + 1]) == cudaSuccess) trav_ms += ms;
+        }
+    };
+    while (true) {
+        // keep the queue full
+        while (!mir->done && !mir->halt && launched - mir->rounds_done < (unsigned)(trace_rounds ? 1 : kRoundsInFlight)) {
+            collect_times(std::min((unsigned)mir->rounds_done, launched));
+            CUDA_TRY(cudaEventRecord(ctx->ev_ring[2 * (launched % kEvRing)], ctx->stream));
+            if ((rc = launch_traverse(ctx, ctx->d_E[parity], -1, ctx->win.list0, &ctx->d_ctl->n0, false))) return rc;
+            CUDA_TRY(cudaEventRecord(ctx->ev_ring[2 * (launched % kEvRing) + 1], ctx->stream));
+            if (use_graph) CUDA_TRY(cudaGraphLaunch(ctx->tail_graph[parity], ctx->stream));
+            else if ((rc = enqueue_tail(ctx, parity, sp))) return rc;
+            ctx->st.kernel_launches += kTailKernels;
+            launched++;
+            parity ^= 1;
+            if (trace_rounds) {
+                if ((rc = fetch_control(ctx))) return rc;
+                const Control &t = *ctx->h_ctl;
+                fprintf(stderr, "[round] %u active [%u,%u) next admit %u traverse=%.3f ms longest=%.3f ms n0=%u dirty=%u first=%u delta=%u heavy=%u pools %.1f%% %.1f%%\n",
+                        launched, t.c0, t.c1, t.admit, (t.t_last > t.t_first ? (double)(t.t_last - t.t_first) * 1e-6 : 0.0), t.max_ns * 1e-6, t.n0, t.dirty,
+                        t.first_dirty, t.delta, t.n_heavy, 100.0 * t.inst_used / ctx->win.inst_cap, 100.0 * t.rs_used / ctx->win.rs_cap);
+            }
+        }
+        if (mir->done || mir->halt) {
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream)); // the rounds queued behind the last one are no-ops
+            collect_times(launched);
+            if ((rc = fetch_control(ctx))) return rc;
+            Control &c = *ctx->h_ctl;
+            if (c.err) {
+                ctx->arena_dirty = true;
+                static const char *const what[] = {"a per-seed buffer", "path vertices (cap 524288)", "read-set intervals (cap 1048576)",
+                                                   "path instances (cap 32768)", "look-ahead vote table (cap 262144 vertices)"};
+                ctx->error = std::string("a per-seed device buffer overflowed its hard cap: ") + what[std::min(c.err >> 8, 4u)];
+                return (int)(c.err & 0xFF);
+            }
+            if (c.done) break;
+            // halt without error: a result pool ran full.  Forget the active set (committed seeds are final), halve it, go on.
+            if (c.c1 - c.c0 <= phase) {
+                ctx->error = "result pools overflowed at the minimum active set (one phase)";
+                return LCB_ERR_CAPACITY;
+            }
+            c.cap = std::max(phase, (c.c1 - c.c0) / 2 / phase * phase);
+            c.delta = std::min(c.delta, c.cap);
+            c.c1 = c.c0;
+            c.n0 = c.n1 = c.dirty = 0;
+            c.pool_overflow = 0, c.halt = 0;
+            c.first_dirty = 0xFFFFFFFFu;
+            // the round that overflowed did not swap the buffers: its `current` epochs are those of c.parity
+            parity = (int)c.parity;
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_ctl, &c, sizeof(Control), cudaMemcpyHostToDevice, ctx->stream));
+            k_rebase<<<(unsigned)std::min<size_t>((N + 1023) / 1024 + 1, (size_t)ctx->sms * 16), 256, 0, ctx->stream>>>(ctx->d_E[parity], ctx->d_E[parity], N, c.c0, nullptr); // drop the abandoned seeds' claims
+            k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
+            k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
+            ctx->st.kernel_launches += 3;
+            ctx->st.pool_restarts++;
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            mir->halt = 0;
+            mir->rounds_done = launched = timed = 0; // round counters restart with the control block's (rounds keeps counting on the device)
+            {
+                // keep the device's round counter and the host's in step: the mirror reports ctl->rounds
+                launched = timed = c.rounds;
+                mir->rounds_done = c.rounds;
+            }
+            continue;
+        }
+        // queue full: wait for the device to finish a round (pinned-memory poll, no stream synchronisation)
+        const unsigned seen = mir->rounds_done;
+        while (mir->rounds_done == seen && !mir->done && !mir->halt) std::this_thread::yield();
+    }
+    ctx->st.rounds = ctx->h_ctl->rounds;
+    ctx->st.windows = ctx->h_ctl->windows;
     return LCB_OK;
 }
 
@@ -1599,6 +2043,13 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     bool drain = false;                                  // result pools half full: stop admitting until the set is empty
     bool hold = false;                                   // heavy re-evaluations keep every warp busy: admit nothing this round
     const double heavy_ms = getenv("LCB_HEAVY_MS") ? atof(getenv("LCB_HEAVY_MS")) : 20.0;
+    // One GPU: the round loop runs from the device (find_blocks_device_loop).  Several ranks (and LCB_HOST_LOOP=1, the A/B
+    // switch): the loop below, where the host takes every round's decisions after a stream synchronisation.
+    const bool device_loop = R == 1 && !getenv("LCB_HOST_LOOP");
+    if (device_loop) {
+        if ((rc = find_blocks_device_loop(ctx, trav_ms))) return rc;
+        c0 = S;
+    }
     while (c0 < S) {
         // ---- admission
         if (c0 == c1) { // nothing active: no pool entry is referenced any more
@@ -1610,7 +2061,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         unsigned admit = 0;
         if (!drain && !(hold && c1 > c0) && c1 < S && c1 - c0 < cap) admit = std::min(std::min(delta, S - c1), cap - (c1 - c0));
         if (admit) {
-            k_admit<<<(admit + 255) / 256, 256, 0, ctx->stream>>>(c1, admit, R, me, n0, ctx->win, ctx->d_ctl);
+            k_admit<<<(admit + 255) / 256, 256, 0, ctx->stream>>>(c1, admit, R, me, n0, ctx->win, ctx->d_ctl, 0);
             ctx->st.kernel_launches++;
             c1 += admit;
         }
@@ -1621,8 +2072,8 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         if ((rc = launch_traverse(ctx, Ecur, -1, ctx->win.list0, &ctx->d_ctl->n0, true))) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
         // D. new epochs: committed claims + the active seeds' current final results
-        k_rebase<<<egrid, 256, 0, ctx->stream>>>(Enew, Ecur, N, c0);
-        k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, c0, c1, ctx->win);
+        k_rebase<<<egrid, 256, 0, ctx->stream>>>(Enew, Ecur, N, c0, nullptr);
+        k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, c0, c1, ctx->win, nullptr);
 #ifdef LCB_WITH_NCCL
         // the one real exchange of the path: every rank's claims meet in a min-reduction over NVLink
         if (R > 1) NCCL_TRY(ncclAllReduce(Enew, Enew, N, ncclUint32, ncclMin, ctx->comm, ctx->stream));
@@ -1630,7 +2081,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         // E. validation + next work lists
         CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream));        // n0, n1, dirty
         CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->first_dirty, 0xFF, sizeof(unsigned), ctx->stream));
-        k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, c0, c1, phase, ctx->win, ctx->d_ctl);
+        k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, c0, c1, phase, ctx->win, ctx->d_ctl, 0);
         ctx->st.kernel_launches += 3;
         if ((rc = fetch_control(ctx))) return rc;
         float ms = 0;
@@ -1694,7 +2145,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             c1 = c0;
             CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream));
             CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->pool_overflow, 0, sizeof(unsigned), ctx->stream));
-            k_rebase<<<egrid, 256, 0, ctx->stream>>>(Ecur, Ecur, N, c0); // drop the abandoned seeds' claims
+            k_rebase<<<egrid, 256, 0, ctx->stream>>>(Ecur, Ecur, N, c0, nullptr); // drop the abandoned seeds' claims
             ctx->st.kernel_launches++;
             ctx->st.pool_restarts++;
             continue;
@@ -1703,12 +2154,12 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         const unsigned fd = std::min(first_dirty, c1);
         if (fd > c0) {
             const unsigned n = fd - c0;
-            k_final_counts<<<(n + 255) / 256, 256, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_counts);
+            k_final_counts<<<(n + 255) / 256, 256, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_counts, nullptr);
 #ifdef LCB_WITH_NCCL
             if (R > 1) NCCL_TRY(ncclAllReduce(ctx->d_counts, ctx->d_counts, n, ncclUint32, ncclSum, ctx->comm, ctx->stream));
 #endif
-            k_emit_scan<<<1, 1024, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_ctl, ctx->d_counts);
-            k_emit_write<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ix, ctx->prm.k, c0, n, ctx->win, ctx->d_out);
+            k_emit_scan<<<1, 1024, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_ctl, ctx->d_counts, 0);
+            k_emit_write<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ix, ctx->prm.k, c0, n, ctx->win, ctx->d_out, nullptr);
             ctx->st.kernel_launches += 3;
             c0 = fd;
         }
@@ -1748,6 +2199,8 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     ctx->st.n_blocks = blocks_done;
     ctx->st.traversals_first = ctx->h_ctl->runs0;
     ctx->st.big_arena_runs = ctx->h_ctl->big_runs;
+    ctx->st.lean_runs = ctx->h_ctl->lean_runs;
+    ctx->st.lean_bails = ctx->h_ctl->lean_bails;
     ctx->st.traversals_rerun = ctx->h_ctl->runs1;
     ctx->st.t_walk = ctx->h_ctl->ct_walk;
     ctx->st.t_occ = ctx->h_ctl->ct_occ;

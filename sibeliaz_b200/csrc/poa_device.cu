@@ -262,9 +262,13 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
     float ms_kernels = 0;
 
     // Blocks whose longest copy has at least this many characters are given a whole CTA (run_block_cta) instead of a warp.
-    // OFF unless LCA_CTA_ROWS is set (to the threshold, e.g. 2048): the CTA variant is validated under the lockstep emulator
-    // (tests/poa_warp_emu.cpp --cta) but has not yet run on a GPU.
-    const uint64_t cta_from = getenv("LCA_CTA_ROWS") ? std::max<uint64_t>(strtoull(getenv("LCA_CTA_ROWS"), nullptr, 10), 256) : ~0ull;
+    // Default threshold 2048 (LCA_CTA_ROWS=<n> overrides, LCA_CTA_ROWS=0 keeps every block on a warp): with it all 1350 blocks of
+    // the examples take 8.4 s on one B200 instead of 108 s, byte-identical (profiles/align_examples_full_r2.log).
+    uint64_t cta_from = 2048;
+    if (const char *e = getenv("LCA_CTA_ROWS")) {
+        const uint64_t v = strtoull(e, nullptr, 10);
+        cta_from = v ? std::max<uint64_t>(v, 256) : ~0ull;
+    }
     auto launch_cta = [&](const std::vector<uint32_t> &list, int level, uint64_t stride) {
         const unsigned ctas = (unsigned)std::min<uint64_t>(std::min<uint64_t>(list.size(), (uint64_t)sms), std::max<uint64_t>(budget / stride, 1));
         DevBuf<uint8_t> arena;

@@ -70,11 +70,10 @@ def _filtered_chunks(src_dir, dst_dir, longest):
 
 def test_examples_alignment_maf_contains_the_golden(example_chunks, tmp_path):
     """The 256 chunk files of the examples: every paragraph of the reference's shipped alignment.maf must come out byte for
-    byte, in the golden's order.  Blocks with a copy of 6 kbp or more are left out by default: one warp works on a block,
-    so the 18 longest blocks (8 x 10 - 27.6 kbp) alone take 108 s (profiles/align_examples_full_r1.log); LCA_TEST_FULL=1
-    runs everything (1350 blocks, all 1332 golden paragraphs)."""
+    byte, in the golden's order: all 1350 blocks, all 1332 golden paragraphs (the 18 longest blocks, 8 x 10 - 27.6 kbp, are
+    the ones the golden lacks; they run one block per CTA).  LCA_TEST_FULL=0 leaves out blocks with a copy of 6 kbp or more."""
     import sibeliaz_b200 as sb
-    full = os.environ.get("LCA_TEST_FULL") == "1"
+    full = os.environ.get("LCA_TEST_FULL", "1") == "1"
     files, kept = _filtered_chunks(example_chunks, str(tmp_path / "chunks"), 10 ** 9 if full else 6000)
     out = str(tmp_path / "alignment.maf")
     st = sb.global_alignment(files, "genome1.fa genome2.fa", out)

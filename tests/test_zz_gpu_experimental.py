@@ -1,6 +1,5 @@
-"""GPU paths that were validated under the CPU lockstep emulator only (tests/poa_warp_emu.cpp) and have not run on a GPU
-yet.  Each runs in its own process with a time limit and is an expected failure until proven otherwise (non-strict: an
-XPASS in the log is the proof), so that it can neither break nor wedge the rest of the suite.  The file name sorts last."""
+"""Variants of GPU paths that are not the default configuration, each in its own process with a time limit so that it can
+neither break nor wedge the rest of the suite.  The file name sorts last."""
 import os
 import subprocess
 import sys
@@ -23,8 +22,9 @@ print(st)
 """
 
 
-@pytest.mark.xfail(strict=False, reason="one-block-per-CTA rows (LCA_CTA_ROWS): emulator-validated, first GPU run")
-def test_cta_rows_variant_equals_restatement(examples, tmp_path):
+@pytest.mark.parametrize("threshold", ["256", "0"])
+def test_cta_rows_threshold_does_not_change_the_alignment(examples, tmp_path, threshold):
+    """One block per CTA for every block whose longest copy has >= 256 characters (default: 2048), and never (0)."""
     case = examples["k25"]
     orc = Oracle(case.graph, case.fastas, case.k, case.a)
     orc.find_blocks(case.m, case.b)
@@ -33,7 +33,7 @@ def test_cta_rows_variant_equals_restatement(examples, tmp_path):
     names = ["%d.tmp" % i for i in (3, 7, 11)]
     files = [os.path.join(out, n) for n in names]
     maf = str(tmp_path / "cta.maf")
-    r = subprocess.run([sys.executable, "-c", CHILD % ROOT, maf] + files, env=dict(os.environ, LCA_CTA_ROWS="256"),
+    r = subprocess.run([sys.executable, "-c", CHILD % ROOT, maf] + files, env=dict(os.environ, LCA_CTA_ROWS=threshold),
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     want = HEAD % "x" + "".join(poa_oracle_text(os.path.join(out, n)) for n in sorted(names))

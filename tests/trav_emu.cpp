@@ -2,19 +2,24 @@
 // (sibeliaz_b200/csrc/lcb_traverse.cuh: process_seed with mpv_fast / mpv_mid / the general vote, push_parallel / push_group,
 // path_score, the shadow state, ...) executed on the CPU by 32 host threads in lockstep (tests/cuda_emu.h), one evaluation
 // after the other against a given epoch array, so that the device code is checked against the oracle without a GPU.
-//   trav_emu <input.bin> <output.txt>
+//   trav_emu <input.bin> <output.txt> [--lean]
+// --lean: the common-case body (lcb_lean.cuh) first, the general code only for the evaluations it hands back (as the two
+// traversal kernels do on the device); prints how many were handed back.
 // input.bin (little endian): int64 N, V, C, S; int32 k, b, m, flank, depth; int4 rec[N]; int2 occ[N]; uint32 vtx_off[V+2];
 //   uint32 chr_off[C+1]; uint32 E[N+32]; then S x {int32 vid; uint32 ch; uint32 thresh}
 // output.txt: per evaluation one line "n  fg|pos<<62 bg  ..." in bestInstance order (the format of lcbo_epoch_process)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include "cuda_emu.h"
 #define LCB_ERR_CAPACITY 5
 #include "../sibeliaz_b200/csrc/lcb_traverse.cuh"
+#include "../sibeliaz_b200/csrc/lcb_lean.cuh"
 
 template <class T>
 static void rd(FILE *f, T *p, size_t n)
@@ -28,6 +33,7 @@ static void rd(FILE *f, T *p, size_t n)
 int main(int argc, char **argv)
 {
     if (argc < 3) return 1;
+    const bool use_lean = argc > 3 && std::string(argv[3]) == "--lean";
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 1;
     int64_t hdr[4];
@@ -52,6 +58,10 @@ int main(int argc, char **argv)
     ix.C = (int)C, ix.N = (int)N, ix.V = (int)V;
     lcb::Params pr{prm[0], prm[1], prm[2], prm[3], prm[4]};
     auto sm = std::make_unique<lcb::WarpSmem>(); // the warp's shared memory
+    auto lsm = std::make_unique<lcb::lean::LeanSmem>();
+    memset(lsm.get(), 0, sizeof(lcb::lean::LeanSmem)); // k_traverse_lean zeroes the hash and the vote table once per warp
+    std::vector<int2> lean_rs((size_t)lcb::kReadSetMax);
+    long long bails = 0;
     std::vector<unsigned char> arena(lcb::arena_stride_of(false) + 256, 0); // spill arena: the hash part must start all-empty
     unsigned char *abase = (unsigned char *)(((uintptr_t)arena.data() + 255) & ~(uintptr_t)255);
     std::barrier<> wb(32);
@@ -69,9 +79,31 @@ int main(int argc, char **argv)
             c.ct.pushes = c.ct.mpv_fast = c.ct.mpv_mid = c.ct.mpv_slow = c.ct.push_par = c.ct.push_ser = 0;
             c.vote_clean = false;
             lcb::arena_bind(c, abase, false);
+            lcb::lean::LCtx lc;
+            lc.rec = ix.rec, lc.occ = ix.occ, lc.vtx_off = ix.vtx_off, lc.E = E.data(), lc.chr_off_s = ix.chr_off, lc.C = ix.C;
+            lc.b = pr.b, lc.m = pr.m, lc.flank = pr.flank, lc.depth = pr.depth;
+            lc.lane = l, lc.sm = lsm.get(), lc.rs = lean_rs.data(), lc.rs_cap = (int)lean_rs.size();
             for (int64_t s = 0; s < S; s++) {
                 c.thresh = jobs[(size_t)s].thresh;
                 c.err = 0;
+                if (use_lean) {
+                    lc.thresh = jobs[(size_t)s].thresh;
+                    const int r = lcb::lean::process_seed(lc, jobs[(size_t)s].vid, (unsigned char)jobs[(size_t)s].ch);
+                    __syncwarp();
+                    if (r == lcb::lean::kOk) {
+                        if (l == 0) {
+                            errs[(size_t)s] = 0;
+                            for (int t = 0; t < lc.nbest; t++) {
+                                const int4 b = lsm->best[t];
+                                results[(size_t)s].push_back((long long)(b.x & 0x7FFFFFFF) | (b.x < 0 ? 1ll << 62 : 0));
+                                results[(size_t)s].push_back(b.y);
+                            }
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                    if (l == 0) bails++;
+                }
                 lcb::process_seed(c, jobs[(size_t)s].vid, (unsigned char)jobs[(size_t)s].ch);
                 __syncwarp();
                 if (l == 0) {
@@ -91,6 +123,7 @@ int main(int argc, char **argv)
             }
         });
     for (auto &t : lanes) t.join();
+    if (use_lean) fprintf(stderr, "lean: %lld of %lld evaluations handed back to the general code\n", bails, (long long)S);
     FILE *o = fopen(argv[2], "w");
     for (int64_t s = 0; s < S; s++) {
         if (errs[(size_t)s]) {
