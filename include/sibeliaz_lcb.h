@@ -122,6 +122,9 @@ typedef struct lcb_stats {
     uint64_t pool_restarts;                /* active sets abandoned because a result pool ran full */
     uint64_t big_arena_runs;               /* evaluations that outgrew the per-warp scratch and were re-run in a big slot */
     uint64_t lean_runs, lean_bails;        /* evaluations finished by the common-case kernel / handed on to the general kernel */
+    uint64_t lean_bail_why[8];             /* ... by reason: > 32 occurrences of a vertex, > 128 path vertices, two occurrences on one
+                                              chromosome, > 32 instances, read-set log full, look-ahead walk > 24 junctions, vote table
+                                              full, |path distance| >= 2^30 */
 } lcb_stats;
 
 void lcb_default_params(lcb_params *p);

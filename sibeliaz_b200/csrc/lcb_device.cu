@@ -75,6 +75,7 @@ struct Control { // device-resident round state, mirrored to pinned host memory 
     unsigned blocks_done, out_done; // emit: blocks / instances committed so far
     unsigned long long dbg[6];
     unsigned long long lean_runs, lean_bails; // evaluations finished by the common-case kernel / handed to the general one
+    unsigned lean_why[lean::kWhyCount];       // ... by reason
     // ---- device-driven schedule (single GPU): the round loop's decisions are taken by k_round_begin / k_round_end, the host
     // only keeps launches queued and watches `Mirror` in pinned memory
     unsigned c0, c1;          // rolling active set [c0, c1): commit frontier, admission frontier
@@ -368,6 +369,8 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
     c.sm = &smem[wib];
     c.rs = rs_base + warp_global * (size_t)kLeanRs;
     c.rs_cap = kLeanRs;
+    c.last_clo = 0, c.last_chi = 0;
+    c.why = 0;
 #ifdef LCB_TMA_WINDOWS
     c.tma_phase = 0;
 #endif
@@ -396,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
                 if (lane == 0) {
                     win.heavy[j] = 1;
                     win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = i | (slot ? 0x80000000u : 0u);
+                    atomicAdd(&ctl->lean_why[c.why], 1u);
                 }
                 bails++;
                 break;
@@ -606,7 +610,10 @@ struct SchedParams { // admission thresholds of the round loop (developer knobs,
 };
 
 // start of a round: admission decision (what the host loop of lcb_find_blocks decides between two rounds)
-__global__ void k_round_begin(Control *ctl)
+// `wave` > 0 (experiment, LCB_WAVE_QUANT=1): while a round's work is between one and four waves of resident warps it is rounded
+// down to whole waves (a launch lasts as long as its last wave, and evaluations of one region of the seed list last about
+// equally long), and a round with less than one wave is filled up to one.
+__global__ void k_round_begin(Control *ctl, unsigned wave)
 {
     if (ctl->done | ctl->halt) return;
     if (ctl->c0 == ctl->c1) { // nothing active: no pool entry is referenced any more
@@ -618,6 +625,15 @@ __global__ void k_round_begin(Control *ctl)
     const unsigned c0 = ctl->c0, c1 = ctl->c1, S = ctl->n_seeds, cap = ctl->cap;
     unsigned admit = 0;
     if (!ctl->drain && !(ctl->hold && c1 > c0) && c1 < S && c1 - c0 < cap) admit = min(min(ctl->delta, S - c1), cap - (c1 - c0));
+    if (wave && admit) {
+        const unsigned room = min(S - c1, cap - (c1 - c0));
+        const unsigned items = ctl->n0 + admit;
+        if (items < wave) admit = min(room, wave - ctl->n0);
+        else if (items < 4 * wave) {
+            const unsigned target = items / wave * wave;
+            if (target > ctl->n0) admit = min(admit, target - ctl->n0);
+        }
+    }
     ctl->admit_lo = c1, ctl->admit = admit, ctl->admit_n0 = ctl->n0;
     ctl->n0 += admit;
     ctl->c1 = c1 + admit;
@@ -1841,8 +1857,15 @@ constexpr int kRoundsInFlight = 4; // rounds the host keeps queued ahead of the 
 constexpr int kEvRing = 16;        // event pairs (> kRoundsInFlight)
 
 // the non-traversal part of round r (epochs, validation, schedule, commit) followed by the admission of round r + 1
+unsigned wave_of(const lcb_ctx *ctx)
+{
+    if (!getenv("LCB_WAVE_QUANT")) return 0u;
+    return (unsigned)((ctx->grid_lean > 0 ? ctx->grid_lean : ctx->grid_traverse) * kWarpsPerBlock);
+}
+
 int enqueue_tail(lcb_ctx *ctx, int parity, const SchedParams &sp)
 {
+    const unsigned wave = wave_of(ctx);
     const size_t N = (size_t)ctx->ix.N;
     uint32_t *Ecur = ctx->d_E[parity], *Enew = ctx->d_E[parity ^ 1];
     const unsigned vgrid = (unsigned)ctx->sms * 8;
@@ -1856,7 +1879,7 @@ int enqueue_tail(lcb_ctx *ctx, int parity, const SchedParams &sp)
     k_final_counts<<<sgrid, 256, 0, st>>>(0u, 0u, ctx->win, ctx->d_counts, ctx->d_ctl);
     k_emit_scan<<<1, 1024, 0, st>>>(0u, 0u, ctx->win, ctx->d_ctl, ctx->d_counts, 1);
     k_emit_write<<<sgrid, 256, 0, st>>>(ctx->ix, ctx->prm.k, 0u, 0u, ctx->win, ctx->d_out, ctx->d_ctl);
-    k_round_begin<<<1, 1, 0, st>>>(ctx->d_ctl);
+    k_round_begin<<<1, 1, 0, st>>>(ctx->d_ctl, wave);
     k_admit<<<sgrid, 256, 0, st>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
     CUDA_TRY(cudaGetLastError());
     return LCB_OK;
@@ -1915,7 +1938,8 @@ int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
         }
     }
     const unsigned sgrid = (unsigned)ctx->sms * 4;
-    k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
+    const unsigned wave = wave_of(ctx);
+    k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, wave);
     k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
     ctx->st.kernel_launches += 2;
     unsigned launched = 0, timed = 0;
@@ -1974,7 +1998,7 @@ int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
             parity = (int)c.parity;
             CUDA_TRY(cudaMemcpyAsync(ctx->d_ctl, &c, sizeof(Control), cudaMemcpyHostToDevice, ctx->stream));
             k_rebase<<<(unsigned)std::min<size_t>((N + 1023) / 1024 + 1, (size_t)ctx->sms * 16), 256, 0, ctx->stream>>>(ctx->d_E[parity], ctx->d_E[parity], N, c.c0, nullptr); // drop the abandoned seeds' claims
-            k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
+            k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, wave);
             k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
             ctx->st.kernel_launches += 3;
             ctx->st.pool_restarts++;
@@ -2201,6 +2225,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     ctx->st.big_arena_runs = ctx->h_ctl->big_runs;
     ctx->st.lean_runs = ctx->h_ctl->lean_runs;
     ctx->st.lean_bails = ctx->h_ctl->lean_bails;
+    for (int w = 0; w < 8; w++) ctx->st.lean_bail_why[w] = ctx->h_ctl->lean_why[w];
     ctx->st.traversals_rerun = ctx->h_ctl->runs1;
     ctx->st.t_walk = ctx->h_ctl->ct_walk;
     ctx->st.t_occ = ctx->h_ctl->ct_occ;

@@ -36,6 +36,9 @@ constexpr int kLVote = 128;  // vote table slots
 constexpr int kLTiers = 3;   // look-ahead depth = 8 * kLTiers junctions per walk
 constexpr int kLChr = 64;    // chr_off entries cached per CTA (C + 1 <= kLChr)
 constexpr int kOk = 0, kBail = 1;
+// reasons for handing an evaluation back (diagnostics: lcb_stats.lean_bail_why)
+constexpr int kWhyOccurrences = 0, kWhyPathLength = 1, kWhySameChromosome = 2, kWhyInstances = 3, kWhyReadSet = 4, kWhyWalkDepth = 5,
+              kWhyVote = 6, kWhyDistance = 7, kWhyCount = 8;
 
 struct LInst { // Path::Instance (path.h:53-181); compareIdx_ = (flags & kPos) ? bg : fg is derived, not stored
     int fg, bg;        // front_/back_ : global record index
@@ -80,6 +83,7 @@ struct LCtx { // warp-uniform unless noted
     LeanSmem *sm;
     int2 *rs;   // read-set log of this warp (HBM)
     int rs_cap; // its capacity in intervals
+    int why;    // why the last evaluation was handed back (kWhy*)
 #ifdef LCB_TMA_WINDOWS
     unsigned tma_phase; // parity of the mbarrier's current phase
 #endif
@@ -88,6 +92,7 @@ struct LCtx { // warp-uniform unless noted
     int nright, nleft;
     int ninst, ngood, nbest, hcount, nrs;
     int ordreg, keyreg; // PER LANE: id and key of the lane-th instance in multiset order (lane >= ninst: key = INT_MAX)
+    int last_clo, last_chi; // PER LANE: bounds of the chromosome this lane looked up last (collinear genomes: the same one next time)
     // state at the best forward point
     int snap_ninst, snap_ngood, snap_hcount, snap_right_flank, snap_right_vertex, snap_nright, snap_ordreg, snap_keyreg;
 };
@@ -228,17 +233,19 @@ struct LOcc { // per-lane occurrence
     bool pos, used;
 };
 
-__device__ __forceinline__ LOcc load_occurrence(const LCtx &c, unsigned o, int vertex)
+__device__ __forceinline__ LOcc load_occurrence(LCtx &c, unsigned o, int vertex)
 {
     LOcc r;
     const int2 oc = __ldg(c.occ + o);
     r.g = oc.x & 0x7FFFFFFF;
     r.bp = (unsigned)oc.y;
     r.pos = (oc.x < 0) == (vertex < 0); // JunctionIterator::IsPositiveStrand (junctionstorage.h:408-411)
-    chr_bounds_s(c, r.g, r.clo, r.chi);
+    if (r.g >= c.last_clo && r.g < c.last_chi) r.clo = c.last_clo, r.chi = c.last_chi;
+    else chr_bounds_s(c, r.g, r.clo, r.chi);
     const bool has = r.pos || r.g > r.clo; // IsUsed on the - strand at idx 0 is false (junctionstorage.h:277-282)
     r.flag = has ? (r.pos ? r.g : r.g - 1) : -1;
     r.used = has ? (__ldg(c.E + r.flag) < c.thresh) : false;
+    c.last_clo = r.clo, c.last_chi = r.chi;
     return r;
 }
 
@@ -264,7 +271,7 @@ __device__ __forceinline__ int path_init(LCtx &c, int vid, unsigned char ch)
     hash_insert(c, vid, 0);
     const int av = vid < 0 ? -vid : vid;
     const unsigned o0 = __ldg(c.vtx_off + av), o1 = __ldg(c.vtx_off + av + 1);
-    if (o1 - o0 > 32u) return kBail;
+    if (o1 - o0 > 32u) return c.why = kWhyOccurrences, kBail;
     const bool live = (unsigned)c.lane < o1 - o0;
     LOcc q;
     q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = 0, q.chi = 0;
@@ -277,7 +284,7 @@ __device__ __forceinline__ int path_init(LCtx &c, int vid, unsigned char ch)
     const unsigned lt = lanemask_lt(c.lane);
     const unsigned um = __ballot_sync(kFull, match && q.used); // outcome depends on these epochs although no instance is born
     if (um) {
-        if (c.nrs + __popc(um) > c.rs_cap) return kBail;
+        if (c.nrs + __popc(um) > c.rs_cap) return c.why = kWhyReadSet, kBail;
         if (match && q.used) c.rs[c.nrs + __popc(um & lt)] = make_int2(q.flag, q.flag);
         c.nrs += __popc(um);
     }
@@ -298,8 +305,9 @@ __device__ __forceinline__ int path_push(LCtx &c, const bool back, int v, int le
 {
     if (hash_find(c, v) != kNotSet) return 1;
     const int dist = back ? c.right_flank + len : c.left_flank - len;
-    if (cnt > 32u || dist >= (1 << 30) || dist <= -(1 << 30)) return 2;
-    if (!hash_insert(c, v, dist)) return 2;
+    if (cnt > 32u) return c.why = kWhyOccurrences, 2;
+    if (dist >= (1 << 30) || dist <= -(1 << 30)) return c.why = kWhyDistance, 2;
+    if (!hash_insert(c, v, dist)) return c.why = kWhyPathLength, 2;
     const bool live = (unsigned)c.lane < cnt;
     LOcc q;
     q.g = 0, q.bp = 0, q.pos = false, q.used = false, q.flag = -1, q.clo = -1 - c.lane, q.chi = 0;
@@ -308,18 +316,18 @@ __device__ __forceinline__ int path_push(LCtx &c, const bool back, int v, int le
         const int prev_clo = __shfl_up_sync(kFull, q.clo, 1);
         if (__any_sync(kFull, live && c.lane > 0 && prev_clo == q.clo)) {
             hash_truncate(c, c.hcount - 1);
-            return 2;
+            return c.why = kWhySameChromosome, 2;
         }
     }
     // multiset neighbours: position of the first key > g, by one ballot per occurrence over the sorted key registers
     const int n = c.ninst;
-    int ub = n;
+    unsigned my_gt = 0;
     for (unsigned o = 0; o < cnt; o++) {
         const int go = __shfl_sync(kFull, q.g, (int)o);
         const unsigned gt = __ballot_sync(kFull, c.keyreg > go); // lanes >= n hold INT_MAX: first of them = n
-        if ((unsigned)c.lane == o) ub = gt ? ffs_lane(gt) : 32;
+        if ((unsigned)c.lane == o) my_gt = gt;
     }
-    ub = min(ub, n);
+    const int ub = min(my_gt ? ffs_lane(my_gt) : 32, n);
     const int hs = min(ub, 31), ls = max(ub - 1, 0);
     const int hi_cand = __shfl_sync(kFull, c.ordreg, hs), hi_key = __shfl_sync(kFull, c.keyreg, hs);
     const int lo_cand = __shfl_sync(kFull, c.ordreg, ls), lo_key = __shfl_sync(kFull, c.keyreg, ls);
@@ -375,12 +383,12 @@ __device__ __forceinline__ int path_push(LCtx &c, const bool back, int v, int le
     const unsigned nm = __ballot_sync(kFull, outcome == 2);
     if (c.ninst + __popc(nm) > kLInst) { // more instances than lanes: the general code's business
         hash_truncate(c, c.hcount - 1);
-        return 2;
+        return c.why = kWhyInstances, 2;
     }
     const unsigned om = __ballot_sync(kFull, outcome == 3);
     if (c.nrs + __popc(om) > c.rs_cap) {
         hash_truncate(c, c.hcount - 1);
-        return 2;
+        return c.why = kWhyReadSet, 2;
     }
     __syncwarp(); // every lane has finished reading the instance table before any lane changes it
     // ---- apply.  Candidates of different lanes are different instances (different chromosomes).
@@ -634,6 +642,7 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
         }
         if (__any_sync(kFull, lane_on && nok == 8 * kLTiers)) { // a walk needs more depth than its lanes offer
             fail = true;
+            c.why = kWhyWalkDepth;
             break;
         }
         int mylo = 0x7FFFFFFF, myhi = -1;
@@ -675,7 +684,7 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
         // the next group inserts up to 4 * 8 * kLTiers keys: go on only while its probing is certain to find empty slots
         if (gb + 4 < E) {
             const int total_distinct = (int)__reduce_add_sync(kFull, (unsigned)distinct);
-            if (total_distinct + 4 * 8 * kLTiers > kLVote - 1) fail = true;
+            if (total_distinct + 4 * 8 * kLTiers > kLVote - 1) fail = true, c.why = kWhyVote;
         }
         __syncwarp();
     }
@@ -787,6 +796,7 @@ __device__ __forceinline__ int process_seed(LCtx &c, int vid, unsigned char ch)
             // bestRightSize - 1 right pushes
             if (!restore_state(c)) {
                 abandon(c);
+                c.why = kWhyReadSet;
                 return kBail;
             }
         }
@@ -809,6 +819,7 @@ __device__ __forceinline__ int process_seed(LCtx &c, int vid, unsigned char ch)
     const int nb = c.nbest;
     if (!path_clear(c)) {
         abandon(c);
+        c.why = kWhyReadSet;
         return kBail;
     }
     c.nbest = nb;
