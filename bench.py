@@ -219,10 +219,16 @@ def main():
     n_records = storage.n_records
     win = dict(window_init=a.window, window_max=a.window) if a.window else {}
 
+    comm_id = [None]
+
     def make_finder(collect=False):
-        bf = sb.BlocksFinder(storage, k, device=local_rank, collect_counters=collect, **win)
-        bf.create(M, B)
-        if world > 1:
+        """One context per call.  N > 1: lcb_create_shared -- rank 0 uploads the index (one PCIe copy), the other ranks
+        receive it over NVLink; the communicator and the peer mailboxes are made once per process and reused."""
+        if world == 1:
+            bf = sb.BlocksFinder(storage, k, device=local_rank, collect_counters=collect, **win)
+            bf.create(M, B)
+            return bf
+        if comm_id[0] is None:
             idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
                 import ctypes
@@ -230,7 +236,9 @@ def main():
                 sb.load_library().lcb_comm_unique_id(buf)
                 idb = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
             dist.broadcast(idb, 0)
-            bf.comm_init(rank, world, bytes(idb.cpu().tolist()))
+            comm_id[0] = bytes(idb.cpu().tolist())
+        bf = sb.BlocksFinder(storage, k, device=local_rank, collect_counters=collect, shared=(rank, world, comm_id[0]), **win)
+        bf.create(M, B)
         return bf
 
     def sync():

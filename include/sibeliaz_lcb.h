@@ -148,6 +148,12 @@ int lcb_create_from_graph(const struct lcg_graph *graph, lcb_index *index, int a
 int lcb_comm_unique_id(void *id_bytes);
 int lcb_comm_init(lcb_ctx *, int rank, int n_ranks, const void *id_bytes);
 
+/* Multi-GPU creation in one call: rank 0 uploads the index once and the other ranks receive it over NVLink (NCCL
+ * broadcast) instead of pushing the same arrays over PCIe n_ranks times; `index` is read on rank 0 only (may be NULL
+ * elsewhere).  Includes lcb_comm_init.  Collective: every rank calls it. */
+int lcb_create_shared(const lcb_index_view *index, const lcb_params *params, int rank, int n_ranks, const void *id_bytes,
+                      lcb_ctx **out);
+
 /* Bundle enumeration + sort (blocksfinder.h:461-503,517). */
 int lcb_enumerate_seeds(lcb_ctx *, uint64_t *n_seeds);
 /* Parity hook: copies the sorted seed list (Bundle fields, blocksfinder.h:182-192); any pointer may be NULL. */

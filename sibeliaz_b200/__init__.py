@@ -107,6 +107,7 @@ def load_library(path=None):
     lib.lcb_create.argtypes = [C.POINTER(IndexView), C.POINTER(Params), C.POINTER(C.c_void_p)]
     lib.lcb_comm_unique_id.argtypes = [C.c_void_p]
     lib.lcb_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.lcb_create_shared.argtypes = [C.POINTER(IndexView), C.POINTER(Params), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.lcb_enumerate_seeds.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.lcb_get_seeds.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     lib.lcb_reset_seeds.argtypes = [C.c_void_p]
@@ -233,8 +234,11 @@ class ArrayStorage:
 class BlocksFinder:
     """Device context (reference: Sibelia::BlocksFinder, blocksfinder.h:178-929)."""
 
-    def __init__(self, storage, k=None, device=0, window_init=0, window_max=0, collect_counters=False):
+    def __init__(self, storage, k=None, device=0, window_init=0, window_max=0, collect_counters=False, shared=None):
+        """`shared` = (rank, n_ranks, id_bytes): multi-GPU creation through lcb_create_shared -- rank 0 uploads the index once,
+        the other ranks receive it over NVLink (their `storage` is only consulted for k and may be rank 0's)."""
         self._lib = load_library()
+        self._shared = shared
         self.storage = storage
         self.k = int(k if k is not None else storage.k)
         self.device = device
@@ -257,6 +261,10 @@ class BlocksFinder:
         p.collect_counters = int(self._collect) if not isinstance(self._collect, bool) else (1 if self._collect else 0)
         if isinstance(self.storage, FusedStorage):
             rc = self._lib.lcb_create_from_graph(self.storage._graph, self.storage._h, self.storage.abundance, C.byref(p), C.byref(self._ctx))
+        elif self._shared is not None:
+            rank, n_ranks, id_bytes = self._shared
+            view = C.byref(self.storage.view) if (rank == 0 or self.storage is not None) else None
+            rc = self._lib.lcb_create_shared(view, C.byref(p), rank, n_ranks, id_bytes, C.byref(self._ctx))
         else:
             rc = self._lib.lcb_create(C.byref(self.storage.view), C.byref(p), C.byref(self._ctx))
         if rc:

@@ -62,8 +62,12 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 struct Control { // device-resident round state, mirrored to pinned host memory once per round
     unsigned head;      // work-queue cursor of the running traversal launch (common-case kernel, or the only kernel)
     unsigned max_ns;    // longest single evaluation since the last reset (globaltimer ns, saturating)
-    unsigned head_heavy; // work-queue cursor of the general kernel when it runs behind the common-case kernel
-    unsigned n_heavy;   // items the common-case kernel handed to the general one this round
+    unsigned head_heavy; // work-queue cursor of the general kernel over win.list_heavy
+    unsigned n_heavy;   // entries of win.list_heavy: seeds known to need the general kernel (queued by the validation) + what
+                        // the common-case kernel hands over while it runs
+    unsigned heavy_done;  // entries of the list the general kernel processed in the last round
+    unsigned lean_exited; // CTAs of the common-case kernel that have finished this round (the general kernel beside it stops
+                          // waiting for hand-overs when all have)
     unsigned n0, n1;    // length of the work list (bit 31 of an item: commit-time re-run only); n1 unused
     unsigned dirty;     // seeds whose dependencies changed in the last validation
     unsigned first_dirty; // smallest such seed index (0xFFFFFFFF: none): everything before it is final
@@ -88,6 +92,8 @@ struct Control { // device-resident round state, mirrored to pinned host memory 
     unsigned rounds, windows;
     unsigned commit_first, commit_n; // prefix committed by this round's emit kernels
     unsigned long long t_first, t_last; // %globaltimer bracket of this round's traversal kernels
+    unsigned x_entries, x_inst;         // results / instances this rank has stored into its peers' mailboxes this round
+    unsigned x_tag_base;                // run number << 22: tags of different runs never compare equal
     unsigned big_runs;            // evaluations that outgrew the per-warp arena and ran in a big slot
     unsigned big_lock[kBigSlots]; // 1 = big arena slot taken (always released by its holder)
 };
@@ -129,6 +135,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -150,8 +157,9 @@ NcclApi *nccl_api()
         a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
         a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
         a.Broadcast = (decltype(a.Broadcast))dlsym(h, "ncclBroadcast");
+        a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
         a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
-        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.GetErrorString;
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.AllGather && a.GetErrorString;
         return a;
     }();
     return &api;
@@ -161,6 +169,7 @@ NcclApi *nccl_api()
 #define ncclCommDestroy nccl_api()->CommDestroy
 #define ncclAllReduce nccl_api()->AllReduce
 #define ncclBroadcast nccl_api()->Broadcast
+#define ncclAllGather nccl_api()->AllGather
 #define ncclGetErrorString nccl_api()->GetErrorString
 #define NCCL_TRY(x)                                                                                       \
     do {                                                                                                  \
@@ -180,17 +189,168 @@ __device__ __forceinline__ void inst_edges(const int4 &b, int &lo, int &hi)
     hi = max(fg, bg) - 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: peer exchange over NVLink (one process per GPU, CUDA IPC).  The index and the epochs are replicated, the
+// seeds of the active set are dealt round-robin (i % R); every rank needs every seed's RESULT (for the claims and the
+// ordered commit) but only the owner needs its read-set.  So a traversal warp that publishes a result also stores it into
+// every peer's MAILBOX (plain stores to peer memory, overlapped with the traversal of the other seeds); after the traversal
+// a one-warp kernel stores the counts and a round tag, the peers wait for the tags and file the results into their own
+// pools.  A second, 16-word exchange per round carries the owners' validation outcome (first dirty seed, overflow, timing)
+// so that all ranks take the same decisions.  No collective library call and no host in the loop.
+// Mailbox of a rank: R x 2 regions (source rank, round parity), each {XHdr, entries[ent_cap], instances[inst_cap]}.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+struct XHdr {
+    unsigned tag, n_entries, n_inst, ctl_tag; // tags: (run << 22) | round, written last
+    unsigned ctl[12];                         // first_dirty, err, overflow, drain, ms bits, longest ns, n0, n_heavy
+};
+static_assert(sizeof(XHdr) == 64, "mailbox header");
+struct XchDev { // by value to the kernels; R <= 1: no exchange
+    int R, me;
+    unsigned ent_cap, inst_cap;
+    unsigned char *box[kMaxRanks]; // box[r]: rank r's mailbox in this process' address space (box[me]: the local one)
+};
+__host__ __device__ __forceinline__ size_t xch_region_bytes(unsigned ent_cap, unsigned inst_cap)
+{
+    return sizeof(XHdr) + (size_t)ent_cap * 16 + (size_t)inst_cap * 16;
+}
+__device__ __forceinline__ unsigned char *xch_region(const XchDev &x, int owner, int src, unsigned parity)
+{
+    return x.box[owner] + ((size_t)src * 2 + parity) * xch_region_bytes(x.ent_cap, x.inst_cap);
+}
+
+// a freshly published result goes to every peer: entry {item, conflict flag, instances, offset} + the instances
+__device__ __forceinline__ void x_send(const XchDev &x, Control *ctl, unsigned i, int slot, bool conf, int nbest, const int4 *best, int lane)
+{
+    if (x.R <= 1) return;
+    unsigned e = 0, io = 0;
+    if (lane == 0) {
+        e = atomicAdd(&ctl->x_entries, 1u);
+        io = atomicAdd(&ctl->x_inst, (unsigned)nbest);
+    }
+    e = __shfl_sync(kFull, e, 0);
+    io = __shfl_sync(kFull, io, 0);
+    if (e >= x.ent_cap || io + (unsigned)nbest > x.inst_cap) { // handled like a full result pool: all ranks restart the active set
+        if (lane == 0) atomicExch(&ctl->pool_overflow, 1u);
+        return;
+    }
+    const unsigned parity = ctl->rounds & 1u;
+    for (int r = 0; r < x.R; r++) {
+        if (r == x.me) continue;
+        unsigned char *reg = xch_region(x, r, x.me, parity);
+        if (lane == 0) ((uint4 *)(reg + sizeof(XHdr)))[e] = make_uint4(i | (slot ? 0x80000000u : 0u), conf ? 1u : 0u, (unsigned)nbest, io);
+        int4 *dst = (int4 *)(reg + sizeof(XHdr) + (size_t)x.ent_cap * 16) + io;
+        for (int t = lane; t < nbest; t += 32) dst[t] = best[t];
+    }
+}
+
+// after the traversal kernels of a round: counts, then the tag, into every peer's mailbox
+__global__ void k_xflag(XchDev x, Control *ctl)
+{
+    if (ctl->done | ctl->halt) return;
+    const int r = threadIdx.x;
+    if (r >= x.R || r == x.me) return;
+    XHdr *h = (XHdr *)xch_region(x, r, x.me, ctl->rounds & 1u);
+    h->n_entries = min(ctl->x_entries, x.ent_cap);
+    h->n_inst = ctl->x_inst;
+    __threadfence_system();
+    *(volatile unsigned *)&h->tag = ctl->x_tag_base | ctl->rounds;
+    __threadfence_system();
+}
+
+// wait until every peer's results of this round are in the local mailbox (lane r watches peer r)
+__global__ void k_xwait(XchDev x, Control *ctl)
+{
+    if (ctl->done | ctl->halt) return;
+    const int r = threadIdx.x;
+    if (r >= x.R || r == x.me) return;
+    const volatile XHdr *h = (const volatile XHdr *)xch_region(x, x.me, r, ctl->rounds & 1u);
+    const unsigned want = ctl->x_tag_base | ctl->rounds;
+    const unsigned long long t0 = global_ns();
+    while (h->tag != want) {
+        __nanosleep(200);
+        if (global_ns() - t0 > 60000000000ull) { // a peer that has not shown up for a minute is gone
+            atomicCAS(&ctl->err, 0u, (unsigned)LCB_ERR_CUDA);
+            break;
+        }
+    }
+}
+
+// file the peers' results of this round into the local pools and per-seed state (one warp per entry)
+__global__ void k_xapply(XchDev x, Window win, Control *ctl)
+{
+    if (ctl->done | ctl->halt) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned warps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned parity = ctl->rounds & 1u;
+    for (int src = 0; src < x.R; src++) {
+        if (src == x.me) continue;
+        const unsigned char *reg = xch_region(x, x.me, src, parity);
+        const XHdr *h = (const XHdr *)reg;
+        const uint4 *ent = (const uint4 *)(reg + sizeof(XHdr));
+        const int4 *inst = (const int4 *)(reg + sizeof(XHdr) + (size_t)x.ent_cap * 16);
+        const unsigned n = h->n_entries;
+        for (unsigned e = warp; e < n; e += warps) {
+            const uint4 en = ent[e];
+            const unsigned i = en.x & 0x7FFFFFFFu, j = i & win.mask, cnt = en.z;
+            const int slot = (int)(en.x >> 31);
+            unsigned long long io = 0;
+            if (lane == 0) io = atomicAdd(&ctl->inst_used, (unsigned long long)cnt);
+            io = __shfl_sync(kFull, io, 0);
+            if (io + cnt > win.inst_cap) {
+                if (lane == 0) {
+                    atomicExch(&ctl->pool_overflow, 1u);
+                    win.res_cnt[slot][j] = 0;
+                }
+                continue;
+            }
+            for (unsigned t = lane; t < cnt; t += 32) win.inst_pool[io + t] = inst[en.w + t];
+            if (lane == 0) {
+                win.res_off[slot][j] = (unsigned)io;
+                win.res_cnt[slot][j] = cnt;
+                if (slot == 0) win.conf[j] = (unsigned char)en.y;
+            }
+        }
+    }
+}
+
+// after the validation: this rank's outcome of the round to every peer
+__global__ void k_csend(XchDev x, Control *ctl, unsigned long long inst_cap, unsigned long long rs_cap)
+{
+    if (ctl->done | ctl->halt) return;
+    const int r = threadIdx.x;
+    if (r >= x.R || r == x.me) return;
+    XHdr *h = (XHdr *)xch_region(x, r, x.me, ctl->rounds & 1u);
+    const float ms = ctl->t_last > ctl->t_first ? (float)(ctl->t_last - ctl->t_first) * 1e-6f : 0.f;
+    h->ctl[0] = ctl->first_dirty;
+    h->ctl[1] = ctl->err;
+    h->ctl[2] = ctl->pool_overflow;
+    h->ctl[3] = (ctl->inst_used * 2 > inst_cap || ctl->rs_used * 2 > rs_cap) ? 1u : 0u;
+    h->ctl[4] = __float_as_uint(ms);
+    h->ctl[5] = ctl->max_ns;
+    h->ctl[6] = ctl->n0;
+    h->ctl[7] = ctl->n_heavy;
+    __threadfence_system();
+    *(volatile unsigned *)&h->ctl_tag = ctl->x_tag_base | ctl->rounds;
+    __threadfence_system();
+}
+
 // ------------------------------------------------------------------------------------------------
 // traversal kernel: persistent warps pull (seed, slot) items from a list
 // ------------------------------------------------------------------------------------------------
-template <bool COLLECT>
-__global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
+// `heavy_mode` 0: `list` holds plain work items.  1: the work is win.list_heavy (entries are item + 1, 0 = not written yet;
+// consumed entries are zeroed), complete when the kernel starts.  2: the same list while the common-case kernel is still
+// appending to it from the other stream: a warp that finds the list exhausted waits until all `lean_total` CTAs of that
+// kernel have exited (MINB = 5: 96 registers, so that a CTA of this kernel fits beside five of the other).
+template <bool COLLECT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_traverse(Index ix, Params pr, const uint32_t *__restrict__ E,
                                                         const int *__restrict__ seed_vid,
                                                         const unsigned char *__restrict__ seed_ch,
                                                         unsigned phase, int force_slot, const unsigned *__restrict__ list,
                                                         const unsigned *__restrict__ n_ptr, unsigned *__restrict__ cursor, Window win,
                                                         Control *ctl, unsigned char *arena_base, size_t arena_stride,
-                                                        unsigned char *big_base, int collect)
+                                                        unsigned char *big_base, int collect, int heavy_mode, unsigned lean_total, XchDev xch)
 {
     __shared__ WarpSmem smem[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -208,16 +368,43 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
     c.vote_clean = false;
     arena_bind(c, arena_base + warp_global * arena_stride, false);
     int big_slot = -1; // >= 0: this warp holds that big arena slot
-    const unsigned n = (ctl->halt | ctl->done) ? 0u : *n_ptr; // (a round queued behind the one that ended the run, or stopped it)
+    const bool off = (ctl->halt | ctl->done) != 0; // (a round queued behind the one that ended the run, or stopped it)
+    const unsigned n = off ? 0u : *n_ptr;
     if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&ctl->t_first, global_ns());
     unsigned done = 0, done1 = 0;
     unsigned long long longest = 0;
-    while (true) {
+    while (!off) {
         unsigned idx = 0;
         if (lane == 0) idx = atomicAdd(cursor, 1u);
         idx = __shfl_sync(kFull, idx, 0);
-        if (idx >= n) break;
-        const unsigned item = list[idx];
+        unsigned item = 0;
+        if (heavy_mode == 0) {
+            if (idx >= n) break;
+            item = list[idx];
+        } else {
+            if (lane == 0) {
+                volatile unsigned *vl = win.list_heavy;
+                const volatile unsigned *vn = &ctl->n_heavy, *vx = &ctl->lean_exited;
+                while (true) {
+                    if (idx < *vn) { // the entry exists; its writer may still be between the counter and the store
+                        unsigned v;
+                        while ((v = vl[idx]) == 0u) __nanosleep(100);
+                        vl[idx] = 0u;
+                        item = v;
+                        break;
+                    }
+                    if (heavy_mode == 1 || *vx >= lean_total) {
+                        __threadfence();
+                        if (idx < *vn) continue; // appended just before the last producer left
+                        break;
+                    }
+                    __nanosleep(1000);
+                }
+            }
+            item = __shfl_sync(kFull, item, 0);
+            if (item == 0u) break;
+            item -= 1u;
+        }
         const unsigned i = item & 0x7FFFFFFFu;
         const unsigned j = i & win.mask;
         int slot = force_slot >= 0 ? force_slot : (int)(item >> 31); // bit 31: commit-time re-run queued by the validation
@@ -275,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
                 win.rs_cnt[slot][j] = (unsigned)c.nrs;
             }
             if (slot != 0) {
+                x_send(xch, ctl, i, 1, false, c.nbest, c.best, lane);
                 done1++;
                 break;
             }
@@ -293,6 +481,7 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
                 win.conf[j] = conf;
                 win.has1[j] = conf;
             }
+            x_send(xch, ctl, i, 0, conf, c.nbest, c.best, lane);
             if (!conf) break;
             slot = 1;
         }
@@ -311,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, LCB_TRAVERSE_CTAS_PER_SM) k_traverse
             break;
         }
     }
+    if (xch.R > 1) __threadfence_system(); // this warp's stores to the peers' mailboxes
     if (lane == 0) {
         if (longest) atomicMax(&ctl->max_ns, (unsigned)min(longest, 0xFFFFFFFFull));
         if (done) atomicAdd(&ctl->runs0, (unsigned long long)done);
@@ -345,7 +535,8 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
                                                         const int *__restrict__ seed_vid,
                                                         const unsigned char *__restrict__ seed_ch, unsigned phase,
                                                         const unsigned *__restrict__ list, const unsigned *__restrict__ n_ptr,
-                                                        Window win, Control *ctl, int2 *__restrict__ rs_base)
+                                                        Window win, Control *ctl, int2 *__restrict__ rs_base, lean::LInst *__restrict__ shadow_base,
+                                                        XchDev xch)
 {
     __shared__ lean::LeanSmem smem[kWarpsPerBlock];
     __shared__ uint32_t chr_off_s[lean::kLChr];
@@ -369,6 +560,7 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
     c.sm = &smem[wib];
     c.rs = rs_base + warp_global * (size_t)kLeanRs;
     c.rs_cap = kLeanRs;
+    c.shadow = shadow_base + warp_global * (size_t)lean::kLInst;
     c.last_clo = 0, c.last_chi = 0;
     c.why = 0;
 #ifdef LCB_TMA_WINDOWS
@@ -388,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
         const unsigned j = i & win.mask;
         int slot = (int)(item >> 31); // bit 31: commit-time re-run queued by the validation
         if (win.heavy[j]) { // known to need the general kernel
-            if (lane == 0) win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = item;
+            if (lane == 0) win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = item + 1u;
             continue;
         }
         while (true) {
@@ -398,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
             if (r != lean::kOk) { // the rest of this item (the evaluation that failed and what follows it) is the general kernel's
                 if (lane == 0) {
                     win.heavy[j] = 1;
-                    win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = i | (slot ? 0x80000000u : 0u);
+                    win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = (i | (slot ? 0x80000000u : 0u)) + 1u;
                     atomicAdd(&ctl->lean_why[c.why], 1u);
                 }
                 bails++;
@@ -429,6 +621,7 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
                 win.rs_cnt[slot][j] = (unsigned)c.nrs;
             }
             if (slot != 0) {
+                x_send(xch, ctl, i, 1, false, c.nbest, c.sm->best, lane);
                 done1++;
                 break;
             }
@@ -447,10 +640,12 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
                 win.conf[j] = conf;
                 win.has1[j] = conf;
             }
+            x_send(xch, ctl, i, 0, conf, c.nbest, c.sm->best, lane);
             if (!conf) break;
             slot = 1;
         }
     }
+    if (xch.R > 1) __threadfence_system(); // this warp's stores to the peers' mailboxes
     if (lane == 0) {
         if (longest) atomicMax(&ctl->max_ns, (unsigned)min(longest, 0xFFFFFFFFull));
         if (done) atomicAdd(&ctl->runs0, (unsigned long long)done);
@@ -459,13 +654,40 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
         if (done + done1 + bails) atomicMax(&ctl->t_last, global_ns());
         if (bails) atomicAdd(&ctl->lean_bails, (unsigned long long)bails);
     }
+    __syncthreads(); // every hand-over of this CTA is in the list before the CTA counts as gone
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&ctl->lean_exited, 1u);
+    }
 }
 
-// does any edge of result `slot 0` of seed j carry an epoch < limit?   (warp-wide)
+// One byte per 64 epoch entries: did any of them change between the current and the new epochs of this round (k_diff)?
+// A seed's validation can only come out differently where something changed, so the validation reads its intervals'
+// bytes (a few hundred KB in all, cache-resident) instead of both epoch arrays.
+constexpr int kDiffShift = 6;
+__device__ __forceinline__ bool range_dirty(const unsigned char *__restrict__ diff, int lo, int hi)
+{
+    if (!diff) return true;
+    for (int b = lo >> kDiffShift; b <= (hi >> kDiffShift); b++)
+        if (diff[b]) return true;
+    return false;
+}
+
+// does any edge of result `slot 0` of seed j carry an epoch < limit?   (warp-wide); `was`: the answer against the current epochs
 __device__ __forceinline__ bool result_conflicts(const Window &win, unsigned j, const uint32_t *E, uint32_t limit,
-                                                 int lane)
+                                                 int lane, const unsigned char *__restrict__ diff, bool was)
 {
     const unsigned cnt = win.res_cnt[0][j], off = win.res_off[0][j];
+    if (diff) { // unchanged epochs under every edge of the result: unchanged answer
+        bool any = false;
+        for (unsigned t = 0; t < cnt && !any; t++) {
+            int lo, hi;
+            inst_edges(win.inst_pool[off + t], lo, hi);
+            for (int base = (lo >> kDiffShift) + lane; base <= (hi >> kDiffShift) && !any; base += 32) any = diff[base] != 0;
+            any = __any_sync(kFull, any);
+        }
+        if (!any) return was;
+    }
     bool hit = false;
     for (unsigned t = 0; t < cnt && !hit; t++) {
         int lo, hi;
@@ -494,7 +716,11 @@ __global__ void k_rebase(uint32_t *dst, const uint32_t *src, size_t n, uint32_t 
     if (sched) {
         if (sched->done | sched->halt) return;
         c0 = sched->c0;
-        if (blockIdx.x == 0 && threadIdx.x == 0) sched->n0 = 0, sched->n1 = 0, sched->dirty = 0, sched->first_dirty = 0xFFFFFFFFu;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            sched->n0 = 0, sched->n1 = 0, sched->dirty = 0, sched->first_dirty = 0xFFFFFFFFu;
+            sched->heavy_done = sched->n_heavy;        // what the general kernel had to do in this round
+            sched->head_heavy = 0, sched->n_heavy = 0; // the validation queues the known-heavy seeds of the next round
+        }
     }
     for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (size_t)gridDim.x * blockDim.x) {
         const uint32_t e = src[f];
@@ -523,62 +749,137 @@ __global__ void k_claim(uint32_t *__restrict__ Enew, unsigned lo_seed, unsigned 
 
 // did any epoch in the read-set change its meaning (< limit) between Ecur and Enew?
 __device__ __forceinline__ bool readset_changed(const int2 *rs, unsigned cnt, const uint32_t *Ecur,
-                                                const uint32_t *Enew, uint32_t limit, int lane)
+                                                const uint32_t *Enew, uint32_t limit, int lane, const unsigned char *__restrict__ diff)
 {
     bool changed = false;
     for (unsigned base = 0; base < cnt && !changed; base += 32) {
         bool ch = false;
         if (base + lane < cnt) {
             int2 iv = rs[base + lane];
-            for (int f = iv.x; f <= iv.y && !ch; f++) ch = (Ecur[f] < limit) != (Enew[f] < limit);
+            if (range_dirty(diff, iv.x, iv.y))
+                for (int f = iv.x; f <= iv.y && !ch; f++) ch = (Ecur[f] < limit) != (Enew[f] < limit);
         }
         changed = __any_sync(kFull, ch);
     }
     return changed;
 }
 
-// re-validate every seed of the window against the new epochs; build next round's work lists
+// diff[b] = do the current and the new epochs differ anywhere in entries [64 b, 64 b + 64)?  (n is padded to a multiple of 128)
+__global__ void k_diff(const uint4 *__restrict__ Ecur, const uint4 *__restrict__ Enew, size_t n4, unsigned char *__restrict__ diff,
+                       const Control *sched)
+{
+    if (sched && (sched->done | sched->halt)) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) { // n4 is a multiple of 32: whole warps
+        const uint4 a = Ecur[t], b = Enew[t];
+        const unsigned m = __ballot_sync(kFull, a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w);
+        if ((threadIdx.x & 31) == 0) *(unsigned short *)(diff + (t >> 4)) = (unsigned short)(((m & 0xFFFFu) ? 1u : 0u) | ((m >> 16) ? 0x100u : 0u));
+    }
+}
+
+// one seed against the new epochs, by a whole warp: is its result still what an evaluation against them would give?
+// The conflict status of the speculative result depends on replicated data only (results + epochs) and is recomputed by
+// every rank for every seed; the read-sets live with the seed's owner (i % R == me), who alone decides about re-evaluations.
+__device__ __forceinline__ void validate_seed(unsigned i, const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned phase,
+                                              const Window &win, Control *ctl, const unsigned char *__restrict__ diff, int lane, bool own)
+{
+    const unsigned j = i & win.mask;
+    const uint32_t T = (i / phase) * phase;
+    const bool rs0 = own && readset_changed(win.rs_pool + win.rs_off[0][j], win.rs_cnt[0][j], Ecur, Enew, T, lane, diff);
+    const bool was = win.conf[j] != 0;
+    bool conf = false;
+    if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, Enew, i, lane, diff, was);
+    if (lane == 0) win.conf[j] = conf;
+    if (!own) return;
+    unsigned dirty = 0;
+    if (rs0) { // the speculative result itself is stale: evaluate again (and with it, if need be, the commit-time re-run)
+        if (lane == 0) {
+            if (win.heavy[j]) win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = i + 1u;
+            else win.list0[atomicAdd(&ctl->n0, 1u)] = i;
+            win.has1[j] = 0;
+        }
+        dirty = 1;
+    } else {
+        if (conf != was) dirty = 1;
+        bool rerun = false;
+        if (conf) {
+            if (!win.has1[j]) rerun = true;
+            else rerun = readset_changed(win.rs_pool + win.rs_off[1][j], win.rs_cnt[1][j], Ecur, Enew, i, lane, diff);
+        }
+        if (lane == 0) {
+            if (rerun) {
+                win.has1[j] = 1;
+                // evaluated together with the speculative work
+                if (win.heavy[j]) win.list_heavy[atomicAdd(&ctl->n_heavy, 1u)] = (i | 0x80000000u) + 1u;
+                else win.list0[atomicAdd(&ctl->n0, 1u)] = i | 0x80000000u;
+            }
+            if (!conf) win.has1[j] = 0;
+        }
+        if (rerun) dirty = 1;
+    }
+    if (lane == 0 && dirty) {
+        atomicAdd(&ctl->dirty, 1u);
+        atomicMin(&ctl->first_dirty, i);
+    }
+}
+
+// Re-validate every seed of the active set against the new epochs; build next round's work lists.  With the change map
+// (`diff`) one LANE per seed first looks whether any epoch the seed depends on changed at all -- its read-set intervals, the
+// edges of its result (conflict status), the read-set of its commit-time re-run; almost always nothing did, and the seed costs
+// a few cached byte loads.  The others get the full check by the whole warp.
 __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned lo_seed,
-                           unsigned hi_seed, unsigned phase, Window win, Control *ctl, int sched)
+                           unsigned hi_seed, unsigned phase, Window win, Control *ctl, int sched, const unsigned char *__restrict__ diff,
+                           unsigned R, unsigned me)
 {
     if (sched) {
         if (ctl->done | ctl->halt) return;
         lo_seed = ctl->c0, hi_seed = ctl->c1;
     }
     const int lane = threadIdx.x & 31;
-    for (unsigned i = lo_seed + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < hi_seed; i += gridDim.x * (blockDim.x >> 5)) {
-        const unsigned j = i & win.mask;
-        const uint32_t T = (i / phase) * phase;
-        unsigned dirty = 0;
-        if (readset_changed(win.rs_pool + win.rs_off[0][j], win.rs_cnt[0][j], Ecur, Enew, T, lane)) {
-            if (lane == 0) {
-                win.list0[atomicAdd(&ctl->n0, 1u)] = i;
-                win.has1[j] = 0;
-            }
-            dirty = 1;
-        } else {
-            bool conf = false;
-            if (win.res_cnt[0][j] > 1) conf = result_conflicts(win, j, Enew, i, lane);
-            const bool was = win.conf[j] != 0;
-            if (conf != was) dirty = 1;
-            bool rerun = false;
-            if (conf) {
-                if (!win.has1[j]) rerun = true;
-                else rerun = readset_changed(win.rs_pool + win.rs_off[1][j], win.rs_cnt[1][j], Ecur, Enew, i, lane);
-            }
-            if (lane == 0) {
-                win.conf[j] = conf;
-                if (rerun) {
-                    win.has1[j] = 1;
-                    win.list0[atomicAdd(&ctl->n0, 1u)] = i | 0x80000000u; // evaluated together with the speculative work
+    const unsigned warps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (!diff) { // no change map (LCB_NO_DIFF=1): every seed gets the full check
+        for (unsigned i = lo_seed + warp; i < hi_seed; i += warps) validate_seed(i, Ecur, Enew, phase, win, ctl, diff, lane, i % R == me);
+        return;
+    }
+    for (unsigned base = lo_seed + warp * 32u; base < hi_seed; base += warps * 32u) {
+        const unsigned i = base + (unsigned)lane;
+        bool need = false;
+        if (i < hi_seed) {
+            const unsigned j = i & win.mask;
+            {
+                const int2 *rs = win.rs_pool + win.rs_off[0][j];
+                const unsigned cnt = win.rs_cnt[0][j];
+                for (unsigned t = 0; t < cnt && !need; t++) {
+                    const int2 iv = rs[t];
+                    need = range_dirty(diff, iv.x, iv.y);
                 }
-                if (!conf) win.has1[j] = 0;
             }
-            if (rerun) dirty = 1;
+            const unsigned rc = win.res_cnt[0][j];
+            if (!need && rc > 1) {
+                const unsigned ro = win.res_off[0][j];
+                for (unsigned t = 0; t < rc && !need; t++) {
+                    int lo, hi;
+                    inst_edges(win.inst_pool[ro + t], lo, hi);
+                    need = range_dirty(diff, lo, hi);
+                }
+            }
+            if (!need && win.conf[j] && i % R == me) {
+                if (!win.has1[j]) need = true;
+                else {
+                    const int2 *rs = win.rs_pool + win.rs_off[1][j];
+                    const unsigned cnt = win.rs_cnt[1][j];
+                    for (unsigned t = 0; t < cnt && !need; t++) {
+                        const int2 iv = rs[t];
+                        need = range_dirty(diff, iv.x, iv.y);
+                    }
+                }
+            }
         }
-        if (lane == 0 && dirty) {
-            atomicAdd(&ctl->dirty, 1u);
-            atomicMin(&ctl->first_dirty, i);
+        unsigned m = __ballot_sync(kFull, need);
+        while (m) {
+            const int src = ffs_lane(m);
+            m &= m - 1;
+            validate_seed(base + (unsigned)src, Ecur, Enew, phase, win, ctl, diff, lane, (base + (unsigned)src) % R == me);
         }
     }
 }
@@ -610,10 +911,7 @@ struct SchedParams { // admission thresholds of the round loop (developer knobs,
 };
 
 // start of a round: admission decision (what the host loop of lcb_find_blocks decides between two rounds)
-// `wave` > 0 (experiment, LCB_WAVE_QUANT=1): while a round's work is between one and four waves of resident warps it is rounded
-// down to whole waves (a launch lasts as long as its last wave, and evaluations of one region of the seed list last about
-// equally long), and a round with less than one wave is filled up to one.
-__global__ void k_round_begin(Control *ctl, unsigned wave)
+__global__ void k_round_begin(Control *ctl, unsigned R, unsigned me)
 {
     if (ctl->done | ctl->halt) return;
     if (ctl->c0 == ctl->c1) { // nothing active: no pool entry is referenced any more
@@ -625,46 +923,66 @@ __global__ void k_round_begin(Control *ctl, unsigned wave)
     const unsigned c0 = ctl->c0, c1 = ctl->c1, S = ctl->n_seeds, cap = ctl->cap;
     unsigned admit = 0;
     if (!ctl->drain && !(ctl->hold && c1 > c0) && c1 < S && c1 - c0 < cap) admit = min(min(ctl->delta, S - c1), cap - (c1 - c0));
-    if (wave && admit) {
-        const unsigned room = min(S - c1, cap - (c1 - c0));
-        const unsigned items = ctl->n0 + admit;
-        if (items < wave) admit = min(room, wave - ctl->n0);
-        else if (items < 4 * wave) {
-            const unsigned target = items / wave * wave;
-            if (target > ctl->n0) admit = min(admit, target - ctl->n0);
-        }
-    }
     ctl->admit_lo = c1, ctl->admit = admit, ctl->admit_n0 = ctl->n0;
-    ctl->n0 += admit;
+    {
+        const unsigned first_own = c1 + (me + R - c1 % R) % R; // smallest i >= c1 with i % R == me
+        ctl->n0 += c1 + admit > first_own ? (c1 + admit - first_own + R - 1) / R : 0u;
+    }
     ctl->c1 = c1 + admit;
     ctl->rounds++;
-    ctl->head = 0, ctl->max_ns = 0, ctl->head_heavy = 0, ctl->n_heavy = 0;
+    ctl->head = 0, ctl->max_ns = 0, ctl->lean_exited = 0;
     ctl->t_first = ~0ull, ctl->t_last = 0;
+    ctl->x_entries = 0, ctl->x_inst = 0;
 }
 
 struct Mirror { // pinned host memory the device writes at the end of every round
     volatile unsigned rounds_done, done, halt, c0;
+    volatile unsigned n_heavy; // seeds already known to need the general kernel in the next round
+    volatile unsigned heavy_last; // what the general kernel had to do in the last round (known + handed over)
 };
 
 // end of a round: admission rate for the next one, commit frontier, epoch buffer swap
-__global__ void k_round_end(Control *ctl, SchedParams sp, Mirror *mirror)
+__global__ void k_round_end(Control *ctl, SchedParams sp, Mirror *mirror, XchDev x)
 {
     if (ctl->done | ctl->halt) { // a round queued behind the last one: nothing to commit (the emit kernels follow unconditionally)
         ctl->commit_n = 0;
         return;
     }
     if (ctl->inst_used * 2 > sp.inst_cap || ctl->rs_used * 2 > sp.rs_cap) ctl->drain = 1;
+    float ms = ctl->t_last > ctl->t_first ? (float)(ctl->t_last - ctl->t_first) * 1e-6f : 0.f;
+    unsigned n0_all = ctl->n0;
+    if (x.R > 1) { // every rank combines the same R outcomes: same decisions everywhere
+        const unsigned want = ctl->x_tag_base | ctl->rounds;
+        for (int r = 0; r < x.R; r++) {
+            if (r == x.me) continue;
+            const volatile XHdr *h = (const volatile XHdr *)xch_region(x, x.me, r, ctl->rounds & 1u);
+            const unsigned long long t0 = global_ns();
+            while (h->ctl_tag != want) {
+                __nanosleep(200);
+                if (global_ns() - t0 > 60000000000ull) {
+                    ctl->err = ctl->err ? ctl->err : (unsigned)LCB_ERR_CUDA;
+                    break;
+                }
+            }
+            ctl->first_dirty = min(ctl->first_dirty, h->ctl[0]);
+            if (h->ctl[1] && !ctl->err) ctl->err = h->ctl[1];
+            ctl->pool_overflow |= h->ctl[2];
+            ctl->drain |= h->ctl[3];
+            ms = fmaxf(ms, __uint_as_float(h->ctl[4]));
+            ctl->max_ns = max(ctl->max_ns, h->ctl[5]);
+            n0_all = max(n0_all, h->ctl[6]);
+        }
+    }
     // Admission rate: a launch lasts max(longest evaluation, work / resident warps).  While it is latency-bound more fresh
     // seeds are free; when the fresh work dominates, far-ahead speculation only adds re-evaluations.
-    const float ms = ctl->t_last > ctl->t_first ? (float)(ctl->t_last - ctl->t_first) * 1e-6f : 0.f;
     const float longest_ms = (float)ctl->max_ns * 1e-6f;
     const unsigned delta = ctl->delta;
     unsigned next_delta = delta, hold = 0;
     if (ms < sp.grow_below * longest_ms || ms < sp.min_round_ms) next_delta = (unsigned)min((unsigned long long)sp.window_max, 2ull * delta);
     else if (ms > sp.shrink_above * longest_ms && ms > 2 * sp.min_round_ms) next_delta = max(sp.phase, delta / 2 / sp.phase * sp.phase);
     if (longest_ms > sp.heavy_ms) { // heavy evaluations: fresh seeds are free only while warps are left over
-        if (ctl->n0 + sp.phase > sp.warps) hold = 1;
-        else next_delta = min(next_delta, max(sp.phase, (sp.warps - ctl->n0) / sp.phase * sp.phase));
+        if (n0_all + sp.phase / (unsigned)max(x.R, 1) > sp.warps) hold = 1;
+        else next_delta = min(next_delta, max(sp.phase, (sp.warps - n0_all) * (unsigned)max(x.R, 1) / sp.phase * sp.phase));
     }
     ctl->hold = hold;
     if (ctl->err | ctl->pool_overflow) { // the host handles both (error report / restart with half the active set)
@@ -680,6 +998,8 @@ __global__ void k_round_end(Control *ctl, SchedParams sp, Mirror *mirror)
         if (ctl->c0 >= ctl->n_seeds) ctl->done = 1;
     }
     mirror->c0 = ctl->c0;
+    mirror->n_heavy = ctl->n_heavy;
+    mirror->heavy_last = ctl->heavy_done;
     mirror->done = ctl->done;
     mirror->halt = ctl->halt;
     __threadfence_system();
@@ -965,9 +1285,12 @@ struct lcb_ctx {
     int grid_traverse = 0;
     int grid_lean = 0;         // 0: the common-case kernel is not used (see use_lean in create_end)
     int2 *d_lean_rs = nullptr; // its per-warp read-set logs
+    lean::LInst *d_lean_shadow = nullptr; // ... and shadow copies of the instance table
+    unsigned char *d_diff = nullptr; // one byte per 64 epoch entries: changed in this round? (k_diff; null: LCB_NO_DIFF=1)
     lcb_block_instance *d_out = nullptr;
     lcb_stats st{};
     int rank = 0, n_ranks = 1;
+    XchDev xch{}; // R <= 1: no peers
 #ifdef LCB_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
@@ -979,6 +1302,8 @@ struct lcb_ctx {
     bool step_timed = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // device-driven round loop (single GPU)
+    cudaStream_t stream2 = nullptr;                     // side stream: the general kernel beside the common-case kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Mirror *h_mirror = nullptr;                         // pinned; written by k_round_end
     cudaGraphExec_t tail_graph[2] = {nullptr, nullptr}; // the non-traversal part of a round + the next round's admission, per epoch-buffer parity
     std::vector<cudaEvent_t> ev_ring;                   // event pairs around the traversal launches of the rounds in flight
@@ -1001,6 +1326,15 @@ std::vector<CachedBlock> g_cache;
 ncclComm_t g_comm = nullptr; // reused by every context of this process (lcb_comm_init), freed by lcb_trim_cache
 int g_comm_dev = -1, g_comm_rank = -1, g_comm_size = 0;
 #endif
+// peer mailboxes of this process (set up once per communicator by lcb_comm_init, shared by its contexts)
+struct XchHost {
+    bool ready = false;
+    XchDev dev{};
+    void *local = nullptr;
+    unsigned run_seq = 0; // runs (lcb_find_blocks calls) so far: every rank counts the same
+};
+XchHost g_xch;
+constexpr unsigned kXchEntries = 1u << 18, kXchInst = 1u << 20; // per (source rank, parity): 4 MB of entries, 16 MB of instances
 
 // `want_zeroed`: the caller needs the arena invariant (null: any block will do).  A block tagged zeroed is handed
 // only to such callers while an untagged one of the right size exists; *want_zeroed tells whether the invariant
@@ -1083,6 +1417,8 @@ namespace {
 constexpr unsigned long long kInstPoolCap = 16ull << 20, kRsPoolCap = 128ull << 20;
 
 size_t arena_stride_bytes() { return arena_stride_of(false); }
+// entries of an epoch array: N + 32 (the traversal reads a little past the end), padded to whole warps of uint4 for k_diff
+size_t epoch_len(size_t N) { return (N + 32 + 127) / 128 * 128; }
 // one allocation: a per-warp arena for every resident warp, then the big slots
 size_t arena_total_bytes(size_t warps) { return arena_stride_of(false) * warps + arena_stride_of(true) * (size_t)kBigSlots; }
 
@@ -1168,7 +1504,7 @@ extern "C" int lcb_warmup(int device)
     lap("context");
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false, LCB_TRAVERSE_CTAS_PER_SM>, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     const size_t arena_bytes = arena_total_bytes((size_t)per_sm * (size_t)sms * kWarpsPerBlock);
     void *arena = nullptr, *ip = nullptr, *rp = nullptr;
     bool cached = false;
@@ -1182,11 +1518,13 @@ extern "C" int lcb_warmup(int device)
     {
         // CUDA loads kernels lazily, on first use: touch all of them here, off the critical path
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, k_traverse<false>);
+        cudaFuncGetAttributes(&fa, k_traverse<false, LCB_TRAVERSE_CTAS_PER_SM>);
+        cudaFuncGetAttributes(&fa, k_traverse<false, 5>);
         cudaFuncGetAttributes(&fa, k_traverse_lean);
         cudaFuncGetAttributes(&fa, k_rebase);
         cudaFuncGetAttributes(&fa, k_claim);
         cudaFuncGetAttributes(&fa, k_validate);
+        cudaFuncGetAttributes(&fa, k_diff);
         cudaFuncGetAttributes(&fa, k_admit);
         cudaFuncGetAttributes(&fa, k_round_begin);
         cudaFuncGetAttributes(&fa, k_round_end);
@@ -1239,6 +1577,9 @@ extern "C" void lcb_destroy(lcb_ctx *ctx)
     for (auto &e : ctx->ev_ring) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2), cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1294,6 +1635,13 @@ int create_begin(lcb_ctx *ctx, const lcb_params *params, const CreateTrace &lap)
     }
     lap("device");
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        int lo_prio = 0, hi_prio = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi_prio));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaEventCreate(&ctx->ev0));
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(cudaEventCreate(&ctx->ev_step0));
@@ -1342,7 +1690,7 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
     lap("pools + control");
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false>, kThreads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse<false, LCB_TRAVERSE_CTAS_PER_SM>, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
     ctx->grid_traverse = per_sm * ctx->sms;
     // The common-case kernel (lcb_lean.cuh) takes every work item first when its preconditions hold for the whole run;
@@ -1353,6 +1701,7 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lean_per_sm, k_traverse_lean, kThreads, 0));
         ctx->grid_lean = std::max(lean_per_sm, 1) * ctx->sms;
         if ((rc = dev_alloc(ctx, &ctx->d_lean_rs, (size_t)ctx->grid_lean * kWarpsPerBlock * kLeanRs))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_lean_shadow, (size_t)ctx->grid_lean * kWarpsPerBlock * lean::kLInst))) return rc;
     }
     lap("occupancy query");
     ctx->arena_stride = arena_stride_bytes();
@@ -1362,6 +1711,7 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
     if ((rc = dev_alloc(ctx, &ctx->d_arena, arena_bytes, &arena_cached))) return rc;
     if (!arena_cached) CUDA_TRY(cudaMemsetAsync(ctx->d_arena, 0, arena_bytes, ctx->stream)); // the spill hash must start all-empty
     if ((rc = dev_alloc(ctx, &ctx->d_out, (size_t)N + 1))) return rc;
+    if (!getenv("LCB_NO_DIFF") && (rc = dev_alloc(ctx, &ctx->d_diff, epoch_len((size_t)N) / 64 + 2))) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     lap("window state + arena");
     return LCB_OK;
@@ -1369,22 +1719,15 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
 
 } // namespace
 
-extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb_ctx **out)
+namespace {
+
+// pack + upload the index from host arrays (the H2D part of lcb_create)
+int create_upload(lcb_ctx *ctx, const lcb_index_view *v, const CreateTrace &lap)
 {
-    if (!v || !params || !out) return LCB_ERR_ARG;
-    lcb_ctx *ctx = new lcb_ctx;
-    *out = ctx; // returned even on failure so that lcb_last_error works; caller destroys it
     if (v->n_records < 0 || v->n_records >= (int64_t)0x7FFFFFF0 || v->n_vertices >= (int64_t)0x3FFFFFF0 || v->n_chr < 0) {
         ctx->error = "index too large for 32-bit device indices";
         return LCB_ERR_ARG;
     }
-    CreateTrace lap;
-    {
-        const int rc0 = create_begin(ctx, params, lap);
-        if (rc0) return rc0;
-    }
-    lcb_params &p = ctx->prm;
-    (void)p;
     const int64_t N = v->n_records, V = v->n_vertices;
     const int C = v->n_chr;
     auto t0 = std::chrono::steady_clock::now();
@@ -1402,7 +1745,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
         if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
         for (int e = 0; e < 2; e++)
-            if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
+            if ((rc = dev_alloc(ctx, &ctx->d_E[e], epoch_len((size_t)N)))) return rc;
         lap("index alloc");
         CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, v->packed_rec, b_rec, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, v->packed_occ, b_occ, cudaMemcpyHostToDevice, ctx->stream));
@@ -1462,7 +1805,7 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
         if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, (size_t)V + 2))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
         for (int e = 0; e < 2; e++)
-            if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
+            if ((rc = dev_alloc(ctx, &ctx->d_E[e], epoch_len((size_t)N)))) return rc;
         CUDA_TRY(cudaMemcpyAsync(ctx->d_rec, rec, b_rec, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_occ, oc, b_occ, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_vtx_off, vo, b_vo, cudaMemcpyHostToDevice, ctx->stream));
@@ -1481,7 +1824,79 @@ extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb
     ctx->ix.V = (int)V;
     ctx->st.n_records = (uint64_t)N;
     ctx->st.n_vertices = (uint64_t)V;
+    return LCB_OK;
+}
+
+} // namespace
+
+extern "C" int lcb_create(const lcb_index_view *v, const lcb_params *params, lcb_ctx **out)
+{
+    if (!v || !params || !out) return LCB_ERR_ARG;
+    lcb_ctx *ctx = new lcb_ctx;
+    *out = ctx; // returned even on failure so that lcb_last_error works; caller destroys it
+    CreateTrace lap;
+    int rc;
+    if ((rc = create_begin(ctx, params, lap))) return rc;
+    if ((rc = create_upload(ctx, v, lap))) return rc;
     return create_end(ctx, lap);
+}
+
+extern "C" int lcb_create_shared(const lcb_index_view *v, const lcb_params *params, int rank, int n_ranks, const void *id_bytes, lcb_ctx **out)
+{
+    if (!params || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks || (rank == 0 && !v)) return LCB_ERR_ARG;
+    if (n_ranks == 1) return lcb_create(v, params, out);
+    lcb_ctx *ctx = new lcb_ctx;
+    *out = ctx;
+#ifdef LCB_WITH_NCCL
+    CreateTrace lap;
+    int rc;
+    if ((rc = create_begin(ctx, params, lap))) return rc;
+    if ((rc = lcb_comm_init(ctx, rank, n_ranks, id_bytes))) return rc;
+    lap("communicator");
+    // rank 0 uploads (one PCIe copy), everybody else receives over NVLink; a header first so that the receivers can allocate
+    long long hdr[4] = {0, 0, 0, 0}; // N, V, C, rank 0's status
+    if (rank == 0) {
+        hdr[3] = create_upload(ctx, v, lap);
+        hdr[0] = ctx->ix.N, hdr[1] = ctx->ix.V, hdr[2] = ctx->ix.C;
+    }
+    long long *d_hdr = nullptr;
+    if ((rc = dev_alloc(ctx, &d_hdr, 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_hdr, hdr, sizeof hdr, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(ncclBroadcast(d_hdr, d_hdr, sizeof hdr, ncclUint8, 0, ctx->comm, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hdr, d_hdr, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (hdr[3]) {
+        if (rank) ctx->error = "rank 0 could not upload the index";
+        return (int)hdr[3];
+    }
+    const size_t N = (size_t)hdr[0], V = (size_t)hdr[1];
+    const int C = (int)hdr[2];
+    if (rank) {
+        auto t0 = std::chrono::steady_clock::now();
+        if ((rc = dev_alloc(ctx, &ctx->d_rec, N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_occ, N))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_vtx_off, V + 2))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_chr_off, (size_t)C + 1))) return rc;
+        for (int e = 0; e < 2; e++)
+            if ((rc = dev_alloc(ctx, &ctx->d_E[e], epoch_len(N)))) return rc;
+        ctx->ix.rec = ctx->d_rec, ctx->ix.occ = ctx->d_occ, ctx->ix.vtx_off = ctx->d_vtx_off, ctx->ix.chr_off = ctx->d_chr_off;
+        ctx->ix.C = C, ctx->ix.N = (int)N, ctx->ix.V = (int)V;
+        ctx->st.n_records = N, ctx->st.n_vertices = V;
+        ctx->st.h2d_bytes = 0;
+        ctx->st.ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    NCCL_TRY(ncclBroadcast(ctx->d_rec, ctx->d_rec, sizeof(int4) * N, ncclUint8, 0, ctx->comm, ctx->stream));
+    NCCL_TRY(ncclBroadcast(ctx->d_occ, ctx->d_occ, sizeof(int2) * N, ncclUint8, 0, ctx->comm, ctx->stream));
+    NCCL_TRY(ncclBroadcast(ctx->d_vtx_off, ctx->d_vtx_off, sizeof(uint32_t) * (V + 2), ncclUint8, 0, ctx->comm, ctx->stream));
+    NCCL_TRY(ncclBroadcast(ctx->d_chr_off, ctx->d_chr_off, sizeof(uint32_t) * ((size_t)C + 1), ncclUint8, 0, ctx->comm, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    lap("index broadcast");
+    return create_end(ctx, lap);
+#else
+    (void)id_bytes;
+    ctx->error = "multi-GPU support is not compiled in (NCCL not found at build time)";
+    return LCB_ERR_STATE;
+#endif
 }
 
 extern "C" int lcb_create_from_graph(const lcg_graph *graph, lcb_index *index, int abundance, const lcb_params *params, lcb_ctx **out)
@@ -1571,7 +1986,7 @@ extern "C" int lcb_create_from_graph(const lcg_graph *graph, lcb_index *index, i
     if ((rc = dev_alloc(ctx, &ctx->d_rec, (size_t)N))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_occ, (size_t)N))) return rc;
     for (int e = 0; e < 2; e++)
-        if ((rc = dev_alloc(ctx, &ctx->d_E[e], (size_t)N + 32))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_E[e], epoch_len((size_t)N)))) return rc;
     k_fill_u32<<<(unsigned)((C + 1 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_chr_off, (size_t)C + 1, N);
     if (N) {
         const unsigned nbk = (N + 255) / 256;
@@ -1641,11 +2056,16 @@ extern "C" int lcb_comm_init(lcb_ctx *ctx, int rank, int n_ranks, const void *id
     {
         // communicators are expensive (seconds) and independent of the index: keep one per (device, rank, size)
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        if (g_comm && g_comm_dev == ctx->device && g_comm_rank == rank && g_comm_size == n_ranks) {
+        if (g_comm && g_comm_dev == ctx->device && g_comm_rank == rank && g_comm_size == n_ranks && g_xch.ready) {
             ctx->comm = g_comm;
             ctx->rank = rank, ctx->n_ranks = n_ranks;
+            ctx->xch = g_xch.dev;
             return LCB_OK;
         }
+    }
+    if (n_ranks > kMaxRanks) {
+        ctx->error = "at most 8 ranks (one node)";
+        return LCB_ERR_ARG;
     }
     ncclUniqueId id;
     memcpy(&id, id_bytes, sizeof id);
@@ -1662,6 +2082,41 @@ extern "C" int lcb_comm_init(lcb_ctx *ctx, int rank, int n_ranks, const void *id
     }
     ctx->comm = comm;
     ctx->rank = rank, ctx->n_ranks = n_ranks;
+    // ---- peer mailboxes: one allocation per rank, opened by every peer through CUDA IPC (handles travel once over NCCL)
+    {
+        if (g_xch.local) cudaFree(g_xch.local); // (a communicator of another shape was replaced)
+        g_xch = XchHost{};
+        const size_t bytes = xch_region_bytes(kXchEntries, kXchInst) * 2 * (size_t)n_ranks;
+        CUDA_TRY(cudaMalloc(&g_xch.local, bytes));
+        CUDA_TRY(cudaMemset(g_xch.local, 0, bytes));
+        cudaIpcMemHandle_t mine;
+        CUDA_TRY(cudaIpcGetMemHandle(&mine, g_xch.local));
+        cudaIpcMemHandle_t *d_all = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&d_all, sizeof(cudaIpcMemHandle_t) * (size_t)n_ranks));
+        CUDA_TRY(cudaMemcpy(d_all + rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+        NCCL_TRY(ncclAllGather(d_all + rank, d_all, sizeof mine, ncclUint8, comm, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        std::vector<cudaIpcMemHandle_t> all((size_t)n_ranks);
+        CUDA_TRY(cudaMemcpy(all.data(), d_all, sizeof mine * (size_t)n_ranks, cudaMemcpyDeviceToHost));
+        cudaFree(d_all);
+        g_xch.dev.R = n_ranks, g_xch.dev.me = rank;
+        g_xch.dev.ent_cap = kXchEntries, g_xch.dev.inst_cap = kXchInst;
+        for (int r = 0; r < n_ranks; r++) {
+            if (r == rank) {
+                g_xch.dev.box[r] = (unsigned char *)g_xch.local;
+                continue;
+            }
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                ctx->error = std::string("cudaIpcOpenMemHandle (peer mailbox of rank ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+                return LCB_ERR_CUDA;
+            }
+            g_xch.dev.box[r] = (unsigned char *)p;
+        }
+        g_xch.ready = true;
+        ctx->xch = g_xch.dev;
+    }
     return LCB_OK;
 #else
     ctx->error = "multi-GPU support is not compiled in (NCCL not found at build time)";
@@ -1812,29 +2267,51 @@ extern "C" int lcb_get_seeds(lcb_ctx *ctx, int64_t *vid, uint8_t *ch, uint64_t *
 
 namespace {
 
-int launch_traverse(lcb_ctx *ctx, const uint32_t *E, int slot, const unsigned *list, const unsigned *n_ptr, bool reset_longest)
+constexpr int kSideCtas = 32; // CTAs of the general kernel that run beside the common-case kernel (one per SM on 32 SMs)
+
+// One round's traversal.  `host_reset`: the host-driven loop resets the cursors here (the device-driven one does it in
+// k_round_begin / k_rebase).  `beside`: the general kernel runs BESIDE the common-case kernel on the side stream (few CTAs
+// at 96 registers, polling the hand-over list) instead of behind it: a heavy seed's evaluation lasts about as long as a
+// whole round of light ones, and behind the common-case kernel it would add that to every round that has one.
+int launch_traverse(lcb_ctx *ctx, const uint32_t *E, int slot, const unsigned *list, const unsigned *n_ptr, bool host_reset, bool beside)
 {
     Params pr{ctx->prm.k, ctx->prm.max_branch, ctx->prm.min_block, ctx->prm.max_flank, ctx->prm.looking_depth};
-    if (reset_longest) // (the device-driven loop resets them in k_round_begin)
-        CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, 4 * sizeof(unsigned), ctx->stream)); // head, max_ns, head_heavy, n_heavy
-    unsigned *cursor = &ctx->d_ctl->head;
+    const unsigned phase = (unsigned)ctx->prm.phase_size;
+    if (host_reset) {
+        CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->head, 0, 3 * sizeof(unsigned), ctx->stream)); // head, max_ns, head_heavy
+        CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->lean_exited, 0, sizeof(unsigned), ctx->stream));
+    }
     if (ctx->grid_lean > 0 && slot < 0) {
-        // the common case first; what it hands back is evaluated by the general kernel right behind it
-        k_traverse_lean<<<ctx->grid_lean, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
-                                                                      (unsigned)ctx->prm.phase_size, list, n_ptr, ctx->win, ctx->d_ctl,
-                                                                      ctx->d_lean_rs);
-        ctx->st.kernel_launches++;
-        list = ctx->win.list_heavy, n_ptr = &ctx->d_ctl->n_heavy, cursor = &ctx->d_ctl->head_heavy;
+        const int side = beside ? std::min(kSideCtas, ctx->grid_lean / 2) : 0;
+        const unsigned lean_grid = (unsigned)(ctx->grid_lean - side);
+        if (side) { // fork: the side stream's kernel is queued first so that its CTAs are placed first
+            CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+            k_traverse<false, 5><<<side, kThreads, 0, ctx->stream2>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, phase, slot,
+                                                                       ctx->win.list_heavy, &ctx->d_ctl->n_heavy, &ctx->d_ctl->head_heavy,
+                                                                       ctx->win, ctx->d_ctl, ctx->d_arena, ctx->arena_stride,
+                                                                       ctx->d_arena + ctx->d_big, 0, 2, lean_grid, ctx->xch);
+            CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        }
+        k_traverse_lean<<<lean_grid, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, phase, list, n_ptr,
+                                                                 ctx->win, ctx->d_ctl, ctx->d_lean_rs, ctx->d_lean_shadow, ctx->xch);
+        if (side) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        else // behind it: the list is complete
+            k_traverse<false, LCB_TRAVERSE_CTAS_PER_SM><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(
+                ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, phase, slot, ctx->win.list_heavy, &ctx->d_ctl->n_heavy,
+                &ctx->d_ctl->head_heavy, ctx->win, ctx->d_ctl, ctx->d_arena, ctx->arena_stride, ctx->d_arena + ctx->d_big, 0, 1, 0u, ctx->xch);
+        ctx->st.kernel_launches += 2;
+        ctx->st.traverse_launches++;
+        return LCB_OK;
     }
     if (ctx->prm.collect_counters)
-        k_traverse<true><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
-                                                                           (unsigned)ctx->prm.phase_size, slot, list, n_ptr, cursor, ctx->win,
-                                                                           ctx->d_ctl, ctx->d_arena, ctx->arena_stride, ctx->d_arena + ctx->d_big,
-                                                                           ctx->prm.collect_counters);
+        k_traverse<true, LCB_TRAVERSE_CTAS_PER_SM><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(
+            ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, phase, slot, list, n_ptr, &ctx->d_ctl->head, ctx->win, ctx->d_ctl, ctx->d_arena,
+            ctx->arena_stride, ctx->d_arena + ctx->d_big, ctx->prm.collect_counters, 0, 0u, ctx->xch);
     else
-        k_traverse<false><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch,
-                                                                            (unsigned)ctx->prm.phase_size, slot, list, n_ptr, cursor, ctx->win,
-                                                                            ctx->d_ctl, ctx->d_arena, ctx->arena_stride, ctx->d_arena + ctx->d_big, 0);
+        k_traverse<false, LCB_TRAVERSE_CTAS_PER_SM><<<ctx->grid_traverse, kThreads, 0, ctx->stream>>>(
+            ctx->ix, pr, E, ctx->d_seed_vid, ctx->d_seed_ch, phase, slot, list, n_ptr, &ctx->d_ctl->head, ctx->win, ctx->d_ctl, ctx->d_arena,
+            ctx->arena_stride, ctx->d_arena + ctx->d_big, 0, 0, 0u, ctx->xch);
     ctx->st.kernel_launches++;
     ctx->st.traverse_launches++;
     return LCB_OK;
@@ -1857,34 +2334,35 @@ constexpr int kRoundsInFlight = 4; // rounds the host keeps queued ahead of the 
 constexpr int kEvRing = 16;        // event pairs (> kRoundsInFlight)
 
 // the non-traversal part of round r (epochs, validation, schedule, commit) followed by the admission of round r + 1
-unsigned wave_of(const lcb_ctx *ctx)
-{
-    if (!getenv("LCB_WAVE_QUANT")) return 0u;
-    return (unsigned)((ctx->grid_lean > 0 ? ctx->grid_lean : ctx->grid_traverse) * kWarpsPerBlock);
-}
-
 int enqueue_tail(lcb_ctx *ctx, int parity, const SchedParams &sp)
 {
-    const unsigned wave = wave_of(ctx);
     const size_t N = (size_t)ctx->ix.N;
     uint32_t *Ecur = ctx->d_E[parity], *Enew = ctx->d_E[parity ^ 1];
     const unsigned vgrid = (unsigned)ctx->sms * 8;
     const unsigned egrid = (unsigned)std::min<size_t>((N + 1023) / 1024 + 1, (size_t)ctx->sms * 16);
     const unsigned sgrid = (unsigned)ctx->sms * 4; // grid-stride kernels over admitted / committed seeds
     cudaStream_t st = ctx->stream;
+    const unsigned R = (unsigned)ctx->n_ranks, me = (unsigned)ctx->rank;
+    if (R > 1) { // the peers' results of this round: tags out, tags in, results filed
+        k_xflag<<<1, 32, 0, st>>>(ctx->xch, ctx->d_ctl);
+        k_xwait<<<1, 32, 0, st>>>(ctx->xch, ctx->d_ctl);
+        k_xapply<<<vgrid, 256, 0, st>>>(ctx->xch, ctx->win, ctx->d_ctl);
+    }
     k_rebase<<<egrid, 256, 0, st>>>(Enew, Ecur, N, 0u, ctx->d_ctl);
     k_claim<<<vgrid, 256, 0, st>>>(Enew, 0u, 0u, ctx->win, ctx->d_ctl);
-    k_validate<<<vgrid, 256, 0, st>>>(Ecur, Enew, 0u, 0u, (unsigned)ctx->prm.phase_size, ctx->win, ctx->d_ctl, 1);
-    k_round_end<<<1, 1, 0, st>>>(ctx->d_ctl, sp, ctx->h_mirror);
+    if (ctx->d_diff) k_diff<<<egrid, 256, 0, st>>>((const uint4 *)Ecur, (const uint4 *)Enew, epoch_len(N) / 4, ctx->d_diff, ctx->d_ctl);
+    k_validate<<<vgrid, 256, 0, st>>>(Ecur, Enew, 0u, 0u, (unsigned)ctx->prm.phase_size, ctx->win, ctx->d_ctl, 1, ctx->d_diff, R, me);
+    if (R > 1) k_csend<<<1, 32, 0, st>>>(ctx->xch, ctx->d_ctl, ctx->win.inst_cap, ctx->win.rs_cap);
+    k_round_end<<<1, 1, 0, st>>>(ctx->d_ctl, sp, ctx->h_mirror, ctx->xch);
     k_final_counts<<<sgrid, 256, 0, st>>>(0u, 0u, ctx->win, ctx->d_counts, ctx->d_ctl);
     k_emit_scan<<<1, 1024, 0, st>>>(0u, 0u, ctx->win, ctx->d_ctl, ctx->d_counts, 1);
     k_emit_write<<<sgrid, 256, 0, st>>>(ctx->ix, ctx->prm.k, 0u, 0u, ctx->win, ctx->d_out, ctx->d_ctl);
-    k_round_begin<<<1, 1, 0, st>>>(ctx->d_ctl, wave);
-    k_admit<<<sgrid, 256, 0, st>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
+    k_round_begin<<<1, 1, 0, st>>>(ctx->d_ctl, R, me);
+    k_admit<<<sgrid, 256, 0, st>>>(0u, 0u, R, me, 0u, ctx->win, ctx->d_ctl, 1);
     CUDA_TRY(cudaGetLastError());
     return LCB_OK;
 }
-constexpr unsigned kTailKernels = 9;
+constexpr unsigned kTailKernels = 10;
 
 // Single-GPU round loop driven from the device: every decision of a round (admission, commit frontier, buffer swap) is taken
 // by k_round_begin / k_round_end from the control block, so the host never waits for a round: it keeps kRoundsInFlight rounds
@@ -1911,12 +2389,15 @@ int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
         for (auto &e : ctx->ev_ring) CUDA_TRY(cudaEventCreate(&e));
     }
     Mirror *mir = ctx->h_mirror;
-    mir->rounds_done = 0, mir->done = 0, mir->halt = 0, mir->c0 = 0;
+    mir->rounds_done = 0, mir->done = 0, mir->halt = 0, mir->c0 = 0, mir->n_heavy = 0;
+    mir->heavy_last = 0xFFFFFFFFu; // nothing known yet: the general kernel behind the common-case kernel
+    const bool allow_beside = !getenv("LCB_HEAVY_BEHIND"); // A/B switch: the general kernel always behind the common-case kernel
     // ---- initial control block
     Control &h = *ctx->h_ctl;
     memset(&h, 0, sizeof(Control));
     h.first_dirty = 0xFFFFFFFFu;
     h.n_seeds = S;
+    h.x_tag_base = (++g_xch.run_seq & 0x3FFu) << 22; // (every rank runs lcb_find_blocks the same number of times)
     h.cap = (unsigned)ctx->prm.window_max;
     h.delta = (unsigned)ctx->prm.window_init;
     if (ctx->max_seed_count >= 32) // see lcb_find_blocks: repeat-rich inputs start with one wave of warps
@@ -1938,9 +2419,8 @@ int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
         }
     }
     const unsigned sgrid = (unsigned)ctx->sms * 4;
-    const unsigned wave = wave_of(ctx);
-    k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, wave);
-    k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
+    k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, (unsigned)ctx->n_ranks, (unsigned)ctx->rank);
+    k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, (unsigned)ctx->n_ranks, (unsigned)ctx->rank, 0u, ctx->win, ctx->d_ctl, 1);
     ctx->st.kernel_launches += 2;
     unsigned launched = 0, timed = 0;
     int parity = 0, rc;
@@ -1955,7 +2435,9 @@ int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
         while (!mir->done && !mir->halt && launched - mir->rounds_done < (unsigned)(trace_rounds ? 1 : kRoundsInFlight)) {
             collect_times(std::min((unsigned)mir->rounds_done, launched));
             CUDA_TRY(cudaEventRecord(ctx->ev_ring[2 * (launched % kEvRing)], ctx->stream));
-            if ((rc = launch_traverse(ctx, ctx->d_E[parity], -1, ctx->win.list0, &ctx->d_ctl->n0, false))) return rc;
+            // beside while the known-heavy seeds fit the side CTAs' warps; otherwise the general kernel gets the whole GPU behind
+            const bool beside = allow_beside && std::max((unsigned)mir->n_heavy, (unsigned)mir->heavy_last) <= (unsigned)(kSideCtas * kWarpsPerBlock) / 2;
+            if ((rc = launch_traverse(ctx, ctx->d_E[parity], -1, ctx->win.list0, &ctx->d_ctl->n0, false, beside))) return rc;
             CUDA_TRY(cudaEventRecord(ctx->ev_ring[2 * (launched % kEvRing) + 1], ctx->stream));
             if (use_graph) CUDA_TRY(cudaGraphLaunch(ctx->tail_graph[parity], ctx->stream));
             else if ((rc = enqueue_tail(ctx, parity, sp))) return rc;
@@ -1992,14 +2474,16 @@ int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
             c.delta = std::min(c.delta, c.cap);
             c.c1 = c.c0;
             c.n0 = c.n1 = c.dirty = 0;
+            c.n_heavy = c.head_heavy = 0;
+            CUDA_TRY(cudaMemsetAsync(ctx->win.list_heavy, 0, sizeof(unsigned) * ctx->wmax, ctx->stream));
             c.pool_overflow = 0, c.halt = 0;
             c.first_dirty = 0xFFFFFFFFu;
             // the round that overflowed did not swap the buffers: its `current` epochs are those of c.parity
             parity = (int)c.parity;
             CUDA_TRY(cudaMemcpyAsync(ctx->d_ctl, &c, sizeof(Control), cudaMemcpyHostToDevice, ctx->stream));
             k_rebase<<<(unsigned)std::min<size_t>((N + 1023) / 1024 + 1, (size_t)ctx->sms * 16), 256, 0, ctx->stream>>>(ctx->d_E[parity], ctx->d_E[parity], N, c.c0, nullptr); // drop the abandoned seeds' claims
-            k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, wave);
-            k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, 1u, 0u, 0u, ctx->win, ctx->d_ctl, 1);
+            k_round_begin<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, (unsigned)ctx->n_ranks, (unsigned)ctx->rank);
+            k_admit<<<sgrid, 256, 0, ctx->stream>>>(0u, 0u, (unsigned)ctx->n_ranks, (unsigned)ctx->rank, 0u, ctx->win, ctx->d_ctl, 1);
             ctx->st.kernel_launches += 3;
             ctx->st.pool_restarts++;
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -2039,11 +2523,11 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     const unsigned phase = (unsigned)ctx->prm.phase_size;
     const size_t N = (size_t)ctx->ix.N;
     uint32_t *Ecur = ctx->d_E[0], *Enew = ctx->d_E[1];
-    CUDA_TRY(cudaMemsetAsync(Ecur, 0xFF, (N + 32) * sizeof(uint32_t), ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(Enew, 0xFF, (N + 32) * sizeof(uint32_t), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(Ecur, 0xFF, epoch_len(N) * sizeof(uint32_t), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(Enew, 0xFF, epoch_len(N) * sizeof(uint32_t), ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(Control), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->win.list_heavy, 0, sizeof(unsigned) * ctx->wmax, ctx->stream)); // 0 = entry not written
     memset(ctx->h_ctl, 0, sizeof(Control));
-    if (ctx->n_ranks > 1) CUDA_TRY(cudaMemsetAsync(ctx->d_out, 0, (N + 1) * sizeof(lcb_block_instance), ctx->stream));
     const unsigned vgrid = (unsigned)ctx->sms * 8;
     const unsigned egrid = (unsigned)std::min<size_t>((N + 1023) / 1024 + 1, (size_t)ctx->sms * 16);
     float trav_ms = 0;
@@ -2067,9 +2551,14 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     bool drain = false;                                  // result pools half full: stop admitting until the set is empty
     bool hold = false;                                   // heavy re-evaluations keep every warp busy: admit nothing this round
     const double heavy_ms = getenv("LCB_HEAVY_MS") ? atof(getenv("LCB_HEAVY_MS")) : 20.0;
-    // One GPU: the round loop runs from the device (find_blocks_device_loop).  Several ranks (and LCB_HOST_LOOP=1, the A/B
-    // switch): the loop below, where the host takes every round's decisions after a stream synchronisation.
-    const bool device_loop = R == 1 && !getenv("LCB_HOST_LOOP");
+    // The round loop runs from the device (find_blocks_device_loop); with several ranks the results travel through the peers'
+    // mailboxes inside it.  LCB_HOST_LOOP=1 (one rank only, the A/B switch): the loop below, where the host takes every
+    // round's decisions after a stream synchronisation.
+    if (R > 1 && !ctx->xch.R) {
+        ctx->error = "lcb_comm_init must run on every rank before lcb_find_blocks";
+        return LCB_ERR_STATE;
+    }
+    const bool device_loop = R > 1 || !getenv("LCB_HOST_LOOP");
     if (device_loop) {
         if ((rc = find_blocks_device_loop(ctx, trav_ms))) return rc;
         c0 = S;
@@ -2093,20 +2582,18 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         // A. speculative evaluations (new + invalidated seeds), each followed at once by its commit-time re-run when the
         //    fresh result conflicts; plus the commit-time re-runs the last validation queued (tagged items)
         CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-        if ((rc = launch_traverse(ctx, Ecur, -1, ctx->win.list0, &ctx->d_ctl->n0, true))) return rc;
+        if ((rc = launch_traverse(ctx, Ecur, -1, ctx->win.list0, &ctx->d_ctl->n0, true, false))) return rc;
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
         // D. new epochs: committed claims + the active seeds' current final results
         k_rebase<<<egrid, 256, 0, ctx->stream>>>(Enew, Ecur, N, c0, nullptr);
         k_claim<<<vgrid, 256, 0, ctx->stream>>>(Enew, c0, c1, ctx->win, nullptr);
-#ifdef LCB_WITH_NCCL
-        // the one real exchange of the path: every rank's claims meet in a min-reduction over NVLink
-        if (R > 1) NCCL_TRY(ncclAllReduce(Enew, Enew, N, ncclUint32, ncclMin, ctx->comm, ctx->stream));
-#endif
         // E. validation + next work lists
         CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream));        // n0, n1, dirty
+        CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n_heavy, 0, sizeof(unsigned), ctx->stream));       // (the validation queues the known-heavy seeds)
         CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->first_dirty, 0xFF, sizeof(unsigned), ctx->stream));
-        k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, c0, c1, phase, ctx->win, ctx->d_ctl, 0);
-        ctx->st.kernel_launches += 3;
+        if (ctx->d_diff) k_diff<<<egrid, 256, 0, ctx->stream>>>((const uint4 *)Ecur, (const uint4 *)Enew, epoch_len(N) / 4, ctx->d_diff, nullptr);
+        k_validate<<<vgrid, 256, 0, ctx->stream>>>(Ecur, Enew, c0, c1, phase, ctx->win, ctx->d_ctl, 0, ctx->d_diff, R, me);
+        ctx->st.kernel_launches += 4;
         if ((rc = fetch_control(ctx))) return rc;
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
@@ -2129,20 +2616,6 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             }
         }
         unsigned first_dirty = h.first_dirty;
-#ifdef LCB_WITH_NCCL
-        if (R > 1) { // every rank must take the same decisions: one max-reduction carries them all
-            unsigned local[6] = {~first_dirty, h.err, h.pool_overflow, drain ? 1u : 0u, me == 0 ? next_delta : 0u, 0u};
-            CUDA_TRY(cudaMemcpyAsync(ctx->d_wnext, local, sizeof local, cudaMemcpyHostToDevice, ctx->stream));
-            NCCL_TRY(ncclAllReduce(ctx->d_wnext, ctx->d_wnext, 6, ncclUint32, ncclMax, ctx->comm, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(local, ctx->d_wnext, sizeof local, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            first_dirty = ~local[0];
-            if (local[1] && !h.err) h.err = local[1];
-            h.pool_overflow = local[2];
-            drain = local[3] != 0;
-            next_delta = local[4];
-        }
-#endif
         hold = (next_delta >> 31) != 0;
         next_delta &= 0x7FFFFFFFu;
         if (trace_rounds)
@@ -2168,6 +2641,8 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
             delta = std::min(delta, cap);
             c1 = c0;
             CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n0, 0, 3 * sizeof(unsigned), ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->n_heavy, 0, sizeof(unsigned), ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(ctx->win.list_heavy, 0, sizeof(unsigned) * ctx->wmax, ctx->stream));
             CUDA_TRY(cudaMemsetAsync(&ctx->d_ctl->pool_overflow, 0, sizeof(unsigned), ctx->stream));
             k_rebase<<<egrid, 256, 0, ctx->stream>>>(Ecur, Ecur, N, c0, nullptr); // drop the abandoned seeds' claims
             ctx->st.kernel_launches++;
@@ -2179,9 +2654,6 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         if (fd > c0) {
             const unsigned n = fd - c0;
             k_final_counts<<<(n + 255) / 256, 256, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_counts, nullptr);
-#ifdef LCB_WITH_NCCL
-            if (R > 1) NCCL_TRY(ncclAllReduce(ctx->d_counts, ctx->d_counts, n, ncclUint32, ncclSum, ctx->comm, ctx->stream));
-#endif
             k_emit_scan<<<1, 1024, 0, ctx->stream>>>(c0, n, ctx->win, ctx->d_ctl, ctx->d_counts, 0);
             k_emit_write<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ix, ctx->prm.k, c0, n, ctx->win, ctx->d_out, nullptr);
             ctx->st.kernel_launches += 3;
@@ -2200,11 +2672,6 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
         ctx->error = "out of host memory";
         return LCB_ERR_ARG;
     }
-#ifdef LCB_WITH_NCCL
-    // every rank wrote only its own seeds' records (the rest is zero): one sum yields the full commit-ordered list everywhere
-    if (ctx->n_ranks > 1 && out_done)
-        NCCL_TRY(ncclAllReduce(ctx->d_out, ctx->d_out, (size_t)out_done * 4, ncclUint32, ncclSum, ctx->comm, ctx->stream));
-#endif
     CUDA_TRY(cudaEventRecord(ctx->ev_step1, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(host, ctx->d_out, sizeof(lcb_block_instance) * out_done, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -2254,6 +2721,12 @@ extern "C" void lcb_trim_cache(void)
     if (g_comm) ncclCommDestroy(g_comm);
     g_comm = nullptr;
 #endif
+    if (g_xch.ready) {
+        for (int r = 0; r < g_xch.dev.R; r++)
+            if (r != g_xch.dev.me && g_xch.dev.box[r]) cudaIpcCloseMemHandle(g_xch.dev.box[r]);
+        if (g_xch.local) cudaFree(g_xch.local);
+        g_xch = XchHost{};
+    }
 }
 
 extern "C" int lcb_reset_seeds(lcb_ctx *ctx)

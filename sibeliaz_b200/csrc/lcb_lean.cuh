@@ -12,8 +12,8 @@
 //     the best forward state undo insertions instead of copying or zeroing the table);
 //   * every pushed vertex occurs at most 32 times, at most once per chromosome (the lanes evaluate all occurrences at
 //     once against the pre-push state, as push_parallel does);
-//   * look-ahead walks of at most 24 junctions, any number of walks (four at a time), at most 31 distinct vertices
-//     in the vote before every further group of four walks;
+//   * look-ahead votes over at most ~160 distinct vertices (any number of walks, four at a time, 24 junctions of each
+//     per pass);
 //   * |path distances| < 2^30 (so 32-bit arithmetic is exact), at most 63 chromosomes (offsets cached in shared memory).
 // A seed that needs more makes process_seed return kBail after leaving the shared state clean; the caller evaluates it
 // with the general code (lcb_traverse.cuh), which is the specification of everything here: same results, same
@@ -32,7 +32,11 @@ constexpr int kLInst = 32;   // instances (one lane each in the searches)
 #define LCB_LEAN_HASH 256
 #endif
 constexpr int kLHash = LCB_LEAN_HASH; // path hash slots (half of them usable)
-constexpr int kLVote = 128;  // vote table slots
+#ifdef LCB_LEAN_MPV_V1
+constexpr int kLVote = 128;
+#else
+constexpr int kLVote = 256;  // vote table slots
+#endif
 constexpr int kLTiers = 3;   // look-ahead depth = 8 * kLTiers junctions per walk
 constexpr int kLChr = 64;    // chr_off entries cached per CTA (C + 1 <= kLChr)
 constexpr int kOk = 0, kBail = 1;
@@ -53,7 +57,6 @@ static_assert(sizeof(LInst) == 52, "13-word records");
 
 struct LeanSmem {
     LInst inst[kLInst];
-    LInst s_inst[kLInst]; // instances at the best forward point (restored instead of Clear + Init + re-push, blocksfinder.h:271-284)
     int2 hash[kLHash];    // vertex -> path distance (DistanceKeeper, distancekeeper.h:9-41); key 0 = empty
     int2 vote[kLVote];    // vertex -> weight sum
     unsigned vlast[kLVote]; // vertex -> last (list position << 20 | depth) that voted for it
@@ -61,6 +64,8 @@ struct LeanSmem {
     unsigned short hslot[kLHash / 2]; // slot of the i-th inserted vertex (undo log)
     unsigned char good[kLInst], s_good[kLInst];
     unsigned char elist[kLInst]; // list positions of the instances that sit on the path end (one look-ahead walk each)
+    unsigned char used[kLVote];  // slots of the vote table that hold a key (so that resolving and emptying it costs what the
+                                 // vote had, not what the table could hold)
 #ifdef LCB_TMA_WINDOWS
     // A/B variant (profiles/ab_tma_graph_r2.md): the look-ahead windows of a group of four walks are staged by bulk
     // copies (cp.async.bulk + mbarrier) instead of being read by one load per lane
@@ -82,6 +87,8 @@ struct LCtx { // warp-uniform unless noted
     int lane;
     LeanSmem *sm;
     int2 *rs;   // read-set log of this warp (HBM)
+    LInst *shadow; // instances at the best forward point (HBM, written at every improvement and read once: restored
+                   // instead of Clear + Init + re-push, blocksfinder.h:271-284)
     int rs_cap; // its capacity in intervals
     int why;    // why the last evaluation was handed back (kWhy*)
 #ifdef LCB_TMA_WINDOWS
@@ -187,7 +194,7 @@ __device__ __forceinline__ void snapshot_state(LCtx &c)
 {
     LeanSmem *sm = c.sm;
     const int *src = (const int *)sm->inst;
-    int *dst = (int *)sm->s_inst;
+    int *dst = (int *)c.shadow;
     const int words = c.ninst * (int)(sizeof(LInst) / sizeof(int));
     for (int i = c.lane; i < words; i += 32) dst[i] = src[i];
     if (c.lane < c.ngood) sm->s_good[c.lane] = sm->good[c.lane];
@@ -213,7 +220,7 @@ __device__ __forceinline__ bool restore_state(LCtx &c)
         c.nrs += n;
     }
     __syncwarp();
-    const int *src = (const int *)sm->s_inst;
+    const int *src = (const int *)c.shadow;
     int *dst = (int *)sm->inst;
     const int words = c.snap_ninst * (int)(sizeof(LInst) / sizeof(int));
     for (int i = c.lane; i < words; i += 32) dst[i] = src[i];
@@ -527,9 +534,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 #endif
 
 // BlocksFinder::MostPopularVertex (blocksfinder.h:708-768): four look-ahead walks at a time (8 lanes each, kLTiers depths
-// per lane, all loads of a group in flight at once), votes in the shared-memory table, closed-form resolution by a scan
-// of the table (see most_popular_vertex in lcb_traverse.cuh for why the running arg-max has a closed form).
-// Returns kBail when a walk is longer than its lanes or the vote has too many distinct vertices (table left empty).
+// per lane, all loads of a pass in flight at once; a walk longer than that goes on in further passes), votes in the
+// shared-memory table, closed-form resolution over the slots the vote used (see most_popular_vertex in lcb_traverse.cuh
+// for why the running arg-max has a closed form).
+// Returns kBail when the vote has too many distinct vertices for the table (left empty).
+#ifdef LCB_LEAN_MPV_V1 // A/B: the single-pass vote of the first version (walks deeper than 24 junctions are handed back)
 __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool try_used, Next &best)
 {
     LeanSmem *sm = c.sm;
@@ -730,6 +739,215 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
     return kOk;
 }
 
+#else
+__device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool try_used, Next &best)
+{
+    LeanSmem *sm = c.sm;
+    best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
+    const int start_vid = forward ? c.right_vertex : c.left_vertex;
+    const bool use_good = c.ngood >= 2;
+    const int n = use_good ? c.ngood : c.ninst;
+    int my_id = 0;
+    bool elig = false;
+    if (c.lane < n) {
+        my_id = use_good ? (int)sm->good[c.lane] : c.lane;
+        elig = (forward ? sm->inst[my_id].bv : sm->inst[my_id].fv) == start_vid;
+    }
+    const unsigned em = __ballot_sync(kFull, elig);
+    const int E = __popc(em);
+    if (E == 0) return kOk;
+    if (elig) sm->elist[__popc(em & lanemask_lt(c.lane))] = (unsigned char)c.lane;
+    __syncwarp();
+    const int k = c.lane >> 3, dd = c.lane & 7;
+    bool fail = false;
+    int nused = 0; // keys in the vote table (it is empty between two calls)
+    for (int gb = 0; gb < E && !fail; gb += 4) {
+        const bool lane_on = gb + k < E;
+        const int q = lane_on ? (int)sm->elist[gb + k] : 0; // list position of my walk's instance
+        const int id = use_good ? (int)sm->good[q] : q;
+        const LInst &I = sm->inst[id];
+        const bool pos = (I.flags & kPos) != 0;
+        const int og = forward ? I.bg : I.fg;
+        const unsigned obp = forward ? I.bbp : I.fbp;
+        const unsigned weight = (I.fbp > I.bbp ? I.fbp - I.bbp : I.bbp - I.fbp) + 1u;
+        const int clo = I.clo, chi = I.chi;
+        const int step = (forward == pos) ? 1 : -1;
+        const unsigned seg = 0xFFu << (k * 8);
+        int mylo = 0x7FFFFFFF, myhi = -1;
+        bool pending = lane_on; // my walk has not met its end yet
+        // a pass covers 8 * kLTiers junctions of every pending walk; nearly always one pass is all there is
+        for (int d0 = 0;; d0 += 8 * kLTiers) {
+            // a pass inserts at most 4 * 8 * kLTiers keys: go on only while its probing is certain to find empty slots
+            if (nused + 4 * 8 * kLTiers > kLVote - 1) {
+                fail = true;
+                c.why = kWhyVote;
+                break;
+            }
+            int vid[kLTiers], flag[kLTiers];
+            bool inr[kLTiers], ok[kLTiers], inpath[kLTiers];
+            {
+                int4 rc[kLTiers];
+                uint32_t ep[kLTiers];
+#if defined(LCB_TMA_WINDOWS) && defined(__CUDACC__)
+                // window of the walk: records [a, b) of [wa, wa + 24) inside the chromosome; its epochs: 32 entries from ea
+                const int wa = step > 0 ? og + d0 + 1 : og - d0 - 8 * kLTiers;
+                const int a = max(wa, clo), b = min(wa + 8 * kLTiers, chi);
+                const int ea = max(a - 1, 0) & ~3;
+                const bool leader = pending && dd == 0 && a < b;
+                const unsigned my_bytes = leader ? (unsigned)(b - a) * 16u + (try_used ? 0u : 128u) : 0u;
+                const unsigned all_bytes = __reduce_add_sync(kFull, my_bytes);
+                if (all_bytes) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of the buffers before the async writes
+                    if (c.lane == 0) mbar_expect(&sm->mbar, all_bytes);
+                    __syncwarp();
+                    if (leader) {
+                        bulk_g2s(&sm->w_rec[k][a - wa], c.rec + a, (unsigned)(b - a) * 16u, &sm->mbar);
+                        if (!try_used) bulk_g2s(&sm->w_E[k][0], c.E + ea, 128u, &sm->mbar);
+                    }
+                    mbar_wait(&sm->mbar, c.tma_phase);
+                    c.tma_phase ^= 1u;
+                }
+#pragma unroll
+                for (int t = 0; t < kLTiers; t++) {
+                    const int g = og + step * (d0 + t * 8 + dd + 1);
+                    inr[t] = pending && g >= clo && g < chi; // it.Valid()
+                    const bool has = pos || g > clo;
+                    flag[t] = (inr[t] && has) ? (pos ? g : g - 1) : -1;
+                    rc[t] = make_int4(0, 0, 0, 0);
+                    ep[t] = kFree;
+                    if (inr[t]) rc[t] = sm->w_rec[k][g - wa];
+                    if (flag[t] >= 0 && !try_used) ep[t] = sm->w_E[k][flag[t] - ea];
+                }
+#else
+#pragma unroll
+                for (int t = 0; t < kLTiers; t++) { // every load of every walk is in flight before the first one is used
+                    const int g = og + step * (d0 + t * 8 + dd + 1);
+                    inr[t] = pending && g >= clo && g < chi; // it.Valid()
+                    const bool has = pos || g > clo;
+                    flag[t] = (inr[t] && has) ? (pos ? g : g - 1) : -1;
+                    rc[t] = make_int4(0, 0, 0, 0);
+                    ep[t] = kFree;
+                    if (inr[t]) rc[t] = __ldg(c.rec + g);
+                    if (flag[t] >= 0 && !try_used) ep[t] = __ldg(c.E + flag[t]);
+                }
+#endif
+#pragma unroll
+                for (int t = 0; t < kLTiers; t++) {
+                    const int d = d0 + t * 8 + dd + 1;
+                    vid[t] = 0;
+                    inpath[t] = false;
+                    bool used = false;
+                    if (inr[t]) {
+                        if (t == 0 && d0 == 0) prefetch_l1(c.occ + rc[t].z); // the push of this vertex starts with its occurrence list
+                        vid[t] = pos ? rc[t].x : -rc[t].x;
+                        const unsigned bp = (unsigned)rc[t].y;
+                        const unsigned dp = bp > obp ? bp - obp : obp - bp;
+                        inr[t] = d < c.depth || dp <= (unsigned)c.b;
+                    }
+                    if (inr[t]) {
+                        used = flag[t] >= 0 && ep[t] < c.thresh; // ep stays kFree under try_used
+                        inpath[t] = hash_find(c, vid[t]) != kNotSet;
+                    } else {
+                        flag[t] = -1;
+                    }
+                    ok[t] = inr[t] && !inpath[t] && !used;
+                }
+            }
+            // first junction of this pass that ends the walk (8 * kLTiers: none, the walk goes on in the next pass)
+            int nok = 8 * kLTiers;
+#pragma unroll
+            for (int t = kLTiers - 1; t >= 0; t--) {
+                const unsigned f = __ballot_sync(kFull, pending && !ok[t]) & seg;
+                if (f) nok = t * 8 + ffs_lane(f) - k * 8;
+            }
+#pragma unroll
+            for (int t = 0; t < kLTiers; t++) {
+                const int di = t * 8 + dd; // 0-based depth inside the pass
+                const bool active = pending && di < nok;
+                const bool stop_in_body = pending && di == nok && inr[t];
+                const bool dep = flag[t] >= 0 && !try_used && (active || (stop_in_body && !inpath[t]));
+                if (dep) mylo = min(mylo, flag[t]), myhi = max(myhi, flag[t]);
+                bool fresh = false;
+                unsigned x = 0;
+                if (active) { // count[vid] += weight; remember the last (list position, depth) that touched it
+                    x = (hash_of(vid[t]) >> 12) & (unsigned)(kLVote - 1);
+                    while (true) {
+                        const int old = atomicCAS(&sm->vote[x].x, 0, vid[t]);
+                        fresh = old == 0;
+                        if (old == 0 || old == vid[t]) break;
+                        x = (x + 1) & (unsigned)(kLVote - 1);
+                    }
+                    atomicAdd((unsigned *)&sm->vote[x].y, weight);
+                    atomicMax(&sm->vlast[x], ((unsigned)q << 20) | (unsigned)(d0 + di + 1));
+                }
+                const unsigned fm = __ballot_sync(kFull, fresh); // new keys: remember their slots
+                if (fresh) sm->used[nused + __popc(fm & lanemask_lt(c.lane))] = (unsigned char)x;
+                nused += __popc(fm);
+            }
+            pending = pending && nok == 8 * kLTiers;
+            __syncwarp();
+            if (!__any_sync(kFull, pending)) break;
+        }
+        // the epochs each walk depended on (its leader lane owns the instance record; walks have distinct instances)
+        {
+            int lo = mylo, hi = myhi;
+#pragma unroll
+            for (int s = 1; s < 8; s <<= 1) {
+                lo = min(lo, __shfl_xor_sync(kFull, lo, s));
+                hi = max(hi, __shfl_xor_sync(kFull, hi, s));
+            }
+            if (lane_on && dd == 0 && lo <= hi) {
+                LInst &W = sm->inst[id];
+                if (lo < W.rlo) W.rlo = lo;
+                if (hi > W.rhi) W.rhi = hi;
+            }
+        }
+        __syncwarp();
+    }
+    // ---- resolve over the slots that were used (and leave the table empty): among the vertices with the maximal final
+    // count, the one whose LAST increment came from the smallest origin (- strand first, then (chr, idx)), earliest event
+    // on ties
+    __syncwarp();
+    unsigned M = 0;
+    for (int base = 0; base < nused; base += 32) {
+        unsigned cnt = 0;
+        if (base + c.lane < nused) cnt = (unsigned)sm->vote[sm->used[base + c.lane]].y;
+        M = max(M, __reduce_max_sync(kFull, cnt));
+    }
+    unsigned my_okey = 0xFFFFFFFFu, my_ev = 0xFFFFFFFFu;
+    int my_vid = 0;
+    for (int base = 0; base < nused; base += 32) {
+        if (base + c.lane < nused) {
+            const int x = sm->used[base + c.lane];
+            const int2 e = sm->vote[x];
+            const unsigned ev = sm->vlast[x];
+            sm->vote[x] = make_int2(0, 0);
+            sm->vlast[x] = 0u;
+            if (!fail && (unsigned)e.y == M) {
+                const int q = (int)(ev >> 20);
+                const LInst &I = sm->inst[use_good ? (int)sm->good[q] : q];
+                const unsigned okey = ((I.flags & kPos) ? 0x80000000u : 0u) | (unsigned)(forward ? I.bg : I.fg);
+                if (okey < my_okey || (okey == my_okey && ev < my_ev)) my_okey = okey, my_ev = ev, my_vid = e.x;
+            }
+        }
+    }
+    __syncwarp();
+    if (fail) return kBail;
+    if (M == 0) return kOk;
+    const unsigned kmin = __reduce_min_sync(kFull, my_okey);
+    const unsigned emin = __reduce_min_sync(kFull, my_okey == kmin ? my_ev : 0xFFFFFFFFu);
+    // (okey, event) names one (walk, depth) item, hence one vertex: at most one lane matches
+    const unsigned win = __ballot_sync(kFull, my_okey == kmin && my_ev == emin);
+    const int wl = ffs_lane(win);
+    best.vid = __shfl_sync(kFull, my_vid, wl);
+    best.og = (int)(kmin & 0x7FFFFFFFu);
+    best.opos = (kmin >> 31) != 0;
+    best.d = (int)(emin & 0xFFFFFu);
+    return kOk;
+}
+
+#endif
+
 // ExtendPathForward / ExtendPathBackward (blocksfinder.h:770-895).  Returns 0 failed, 1 success, 2 bail.
 __device__ __forceinline__ int extend_path(LCtx &c, const bool forward, int &best_size, long long &best_score, long long &now_score)
 {
@@ -741,16 +959,20 @@ __device__ __forceinline__ int extend_path(LCtx &c, const bool forward, int &bes
     bool success = false;
     const int step = (forward == nx.opos) ? 1 : -1;
     // `for (it = origin; it.GetVertexId() != next; ++it) push(it.Outgoing/IngoingEdge())`: stops at the FIRST junction of
-    // the walk that carries the chosen vertex (blocksfinder.h:789, :852); nx.d <= 24
+    // the walk that carries the chosen vertex (blocksfinder.h:789, :852); junctions og .. og + step * d, a warp's worth at a time
     int4 rc = make_int4(0, 0, 0, 0);
     if (c.lane <= nx.d) rc = __ldg(c.rec + (nx.og + step * c.lane));
     int prev_v = forward ? c.right_vertex : c.left_vertex; // vertex of the origin junction
     unsigned prev_bp = (unsigned)__shfl_sync(kFull, rc.y, 0);
     for (int j = 1; j <= nx.d; j++) {
-        const int idv = __shfl_sync(kFull, rc.x, j);
-        const unsigned bp = (unsigned)__shfl_sync(kFull, rc.y, j);
-        const unsigned o_first = (unsigned)__shfl_sync(kFull, rc.z, j);
-        const unsigned o_count = (unsigned)__shfl_sync(kFull, rc.w, j) >> 16;
+        if ((j & 31) == 0) { // next 32 junctions of a deep walk
+            rc = make_int4(0, 0, 0, 0);
+            if (j + c.lane <= nx.d) rc = __ldg(c.rec + (nx.og + step * (j + c.lane)));
+        }
+        const int idv = __shfl_sync(kFull, rc.x, j & 31);
+        const unsigned bp = (unsigned)__shfl_sync(kFull, rc.y, j & 31);
+        const unsigned o_first = (unsigned)__shfl_sync(kFull, rc.z, j & 31);
+        const unsigned o_count = (unsigned)__shfl_sync(kFull, rc.w, j & 31) >> 16;
         const int v = nx.opos ? idv : -idv;
         const int len = (int)(bp > prev_bp ? bp - prev_bp : prev_bp - bp);
         const int g_prev = nx.og + step * (j - 1), g_now = nx.og + step * j;

@@ -1,9 +1,12 @@
-"""World-size-2 (gloo, CPU) test of the multi-rank protocol of DESIGN.md section 7, the one lcb_device.cu runs over
-NCCL: the seeds of the rolling active set dealt round-robin over ranks, every rank evaluates / validates only its own
-seeds against a replicated epoch array, claims meet in an all-reduce(MIN), the first dirty seed in an all-reduce(MAX) of
-its complement, the clean prefix is committed with block ids from a prefix sum over all-reduced per-seed counts.  Seed evaluation itself is the oracle's epoch-threshold Process
-(oracle/liblcb_oracle_epoch.so), so the test checks the PROTOCOL -- sharding, reductions, termination, ordered emit --
-independently of CUDA.  The result must equal the sequential oracle's blocksInstance_ list."""
+"""World-size-2 (gloo, CPU) test of the multi-rank protocol of DESIGN.md section 7, the one lcb_device.cu runs over the peers'
+mailboxes: the seeds of the rolling active set are dealt round-robin over ranks; every rank evaluates only its own seeds
+and keeps their read-sets; the RESULTS of a round (speculative result + conflict flag, commit-time re-run) go to every rank
+(here: all_gather_object; on the device: stores into the peers' mailboxes from the traversal kernel); then every rank
+rebuilds the same epochs from all results, recomputes every seed's conflict status (replicated data only), validates its
+own seeds' read-sets, and one MIN over the ranks' first dirty seed fixes the commit frontier; the clean prefix is committed
+by every rank from its replica.  Seed evaluation itself is the oracle's epoch-threshold Process
+(oracle/liblcb_oracle_epoch.so), so the test checks the PROTOCOL -- sharding, exchange, replicated state, termination,
+ordered emit -- independently of CUDA.  Every rank's output must equal the sequential oracle's blocksInstance_ list."""
 import ctypes as C
 import os
 import sys
@@ -63,90 +66,101 @@ def _worker(rank, world, port, graph, fastas, k, W, out_queue):
                 return True
         return False
 
-    # rolling active set [c0, c1) as in lcb_find_blocks: admit `W` seeds per round (at most 4 W active), evaluate own
-    # dirty + new seeds (commit-time re-run right behind a conflicting speculative result), rebase + claim + all-reduce,
-    # validate own seeds, agree on the first dirty seed, commit the clean prefix
+    # rolling active set [c0, c1) as in find_blocks_device_loop: admit `W` seeds per round (at most 4 W active)
     Ecur = np.full(N, INF, np.uint32)
     out, blocks_before, rounds_total = [], 0, 0
     c0 = c1 = 0
-    r0, R0, r1, R1, conf = {}, {}, {}, {}, {}
+    r0, r1, conf = {}, {}, {}  # replicated: results and conflict flags of ALL active seeds
+    R0, R1, has1 = {}, {}, {}  # owner only: read-sets, "the commit-time re-run is up to date"
     need0, need1 = set(), set()
     while c0 < S:
         admit = min(W, S - c1, max(0, 4 * W - (c1 - c0)))
-        for i in range(c1, c1 + admit):
+        for i in range(c1, c1 + admit):  # k_admit: fresh state on every rank, the owner queues the evaluation
+            r0[i], conf[i] = np.zeros((0, 2), np.int64), False
+            r1.pop(i, None)
             if i % world == rank:
                 need0.add(i)
-                conf[i] = False
+                R0[i], has1[i] = np.zeros((0, 2), np.int64), False
         c1 += admit
         rounds_total += 1
+        # traversal of the own work items; every published result is also a message to the peers
+        msgs = []
         for i in sorted(need0):
             r0[i], R0[i] = process(i, i // PHASE * PHASE, Ecur)
-            r1.pop(i, None)
-            conf[i] = conflicts(r0[i], Ecur, i)
+            conf[i] = has1[i] = conflicts(r0[i], Ecur, i)
+            msgs.append((i, 0, conf[i], r0[i]))
             if conf[i]:
                 r1[i], R1[i] = process(i, i, Ecur)
+                msgs.append((i, 1, False, r1[i]))
         for i in sorted(need1):
             r1[i], R1[i] = process(i, i, Ecur)
+            msgs.append((i, 1, False, r1[i]))
         need0, need1 = set(), set()
-        own = [i for i in range(c0, c1) if i % world == rank]
+        everyone = [None] * world
+        dist.all_gather_object(everyone, msgs)  # <- the exchange step (peer mailboxes on the device)
+        for src, lst in enumerate(everyone):
+            if src == rank:
+                continue
+            for i, slot, cf, res in lst:  # k_xapply
+                if slot == 0:
+                    r0[i], conf[i] = res, cf
+                else:
+                    r1[i] = res
+
+        def final(i):
+            f = r1.get(i, np.zeros((0, 2), np.int64)) if conf[i] else r0[i]
+            return f if len(f) > 1 else f[:0]
+
         Enew = np.where(Ecur < c0, Ecur, INF).astype(np.int64)  # k_rebase: committed claims only
-        for i in own:
-            f = r1[i] if conf[i] else r0[i]
-            if len(f) > 1:
-                for e in edges(f):
-                    Enew[e] = np.minimum(Enew[e], i)
-        t = torch.from_numpy(Enew)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)  # <- the exchange step (ncclAllReduce(min) on the device)
-        Enew = t.numpy().astype(np.uint32)
+        for i in range(c0, c1):  # k_claim: every rank, every active seed
+            for e in edges(final(i)):
+                Enew[e] = np.minimum(Enew[e], i)
+        Enew = Enew.astype(np.uint32)
         first_dirty = INF
-        for i in own:
+        for i in range(c0, c1):  # k_validate
+            own = i % world == rank
+            rs0 = own and changed(R0[i], Ecur, Enew, i // PHASE * PHASE)
+            was = conf[i]
+            conf[i] = conflicts(r0[i], Enew, i)  # replicated data only: the same on every rank
+            if not own:
+                continue
             dirty = False
-            if changed(R0[i], Ecur, Enew, i // PHASE * PHASE):
+            if rs0:
                 need0.add(i)
+                has1[i] = False
                 dirty = True
             else:
-                c = conflicts(r0[i], Enew, i)
-                dirty = c != conf[i]
-                conf[i] = c
-                if c and (i not in r1 or changed(R1[i], Ecur, Enew, i)):
+                dirty = conf[i] != was
+                if conf[i] and (not has1[i] or changed(R1[i], Ecur, Enew, i)):
                     need1.add(i)
+                    has1[i] = True
                     dirty = True
-                if not c:
-                    r1.pop(i, None)
+                if not conf[i]:
+                    has1[i] = False
             if dirty:
                 first_dirty = min(first_dirty, i)
-        d = torch.tensor([INF - first_dirty])
-        dist.all_reduce(d, op=dist.ReduceOp.MAX)  # one max-reduction carries the round's decisions on the device
-        fd = min(INF - int(d.item()), c1)
-        if fd > c0:
-            counts = np.zeros(fd - c0, np.int64)
-            for i in own:
-                if i < fd:
-                    f = r1[i] if conf[i] else r0[i]
-                    counts[i - c0] = len(f) if len(f) > 1 else 0
-            t = torch.from_numpy(counts)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            ids = blocks_before + np.cumsum(counts > 0)
-            for i in own:
-                if i >= fd:
-                    continue
-                f = r1[i] if conf[i] else r0[i]
-                if len(f) > 1:
+        d = torch.tensor([first_dirty], dtype=torch.int64)
+        dist.all_reduce(d, op=dist.ReduceOp.MIN)  # the 16-word control exchange of the device
+        fd = min(int(d.item()), c1)
+        if fd > c0:  # every rank commits the prefix from its replica
+            for i in range(c0, fd):
+                f = final(i)
+                if len(f):
+                    blocks_before += 1
                     for fgs, bg in f:
                         pos, fg = bool(fgs >> 62), int(fgs & ((1 << 62) - 1))
                         if pos:
-                            out.append((i, int(ids[i - c0]), int(pos_bp[fg]), int(pos_bp[bg]) + k))
+                            out.append((i, blocks_before, int(pos_bp[fg]), int(pos_bp[bg]) + k))
                         else:
-                            out.append((i, -int(ids[i - c0]), int(pos_bp[bg]), int(pos_bp[fg]) + k))
-                for tab in (r0, R0, r1, R1, conf):
+                            out.append((i, -blocks_before, int(pos_bp[bg]), int(pos_bp[fg]) + k))
+                for tab in (r0, R0, r1, R1, conf, has1):
                     tab.pop(i, None)
-            blocks_before = int(ids[-1])
             c0 = fd
         Ecur = Enew
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:
-        out_queue.put((sum(gathered, []), rounds_total))
+        out_queue.put((gathered, rounds_total))
     dist.destroy_process_group()
 
 
@@ -160,15 +174,15 @@ def test_two_rank_protocol_matches_sequential_oracle(star_small, window):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, star_small.graph, star_small.fastas, star_small.k, window, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rows, rounds = q.get(timeout=600)
+    per_rank, rounds = q.get(timeout=600)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     ob = Oracle(star_small.graph, star_small.fastas, star_small.k, star_small.a).find_blocks(star_small.m, star_small.b)
-    # stable sort by seed index keeps each rank's instance order, i.e. the commit order
-    rows.sort(key=lambda r: r[0])
-    assert len(rows) == len(ob["id"]) > 1000
-    assert [r[1] for r in rows] == ob["id"].tolist()
-    assert [r[2] for r in rows] == ob["start"].tolist()
-    assert [r[3] for r in rows] == ob["end"].tolist()
+    assert len(per_rank) == 2
+    for rows in per_rank:  # every rank holds the whole commit-ordered list
+        assert len(rows) == len(ob["id"]) > 1000
+        assert [r[1] for r in rows] == ob["id"].tolist()
+        assert [r[2] for r in rows] == ob["start"].tolist()
+        assert [r[3] for r in rows] == ob["end"].tolist()
     assert rounds >= 2

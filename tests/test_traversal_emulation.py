@@ -118,6 +118,21 @@ def test_common_case_kernel_hands_back_what_it_cannot_do(examples, trav_emu, tmp
     assert n >= 12 and nonempty >= 10
 
 
+def test_common_case_kernel_deep_look_ahead(tmp_path_factory, trav_emu, tmp_path):
+    """8 x 80 kbp mammalian-like input (interspersed repeats, indels, inversions) at k=25: look-ahead walks longer than the
+    24 junctions of one pass and winners deeper than a warp's 32 lanes (the push loop then reloads), 8 walks per vote."""
+    from conftest import Case
+    from oracle_binding import run_twopaco
+    from tools.gen_synthetic import generate
+    d = str(tmp_path_factory.mktemp("mammal8x80k"))
+    fas = generate(d, "mammal", 8, 80000, 0.03, 3)
+    dbg = os.path.join(d, "g.dbg")
+    run_twopaco(fas, 25, dbg, threads=4)
+    n, nonempty = emulate_and_compare(Case("mammal", dbg, fas, 25), lambda S: list(range(0, S, max(1, S // 160))), trav_emu, str(tmp_path),
+                                      extra_args=["--lean"])
+    assert n >= 120 and nonempty >= 100
+
+
 def test_device_traversal_code_equals_oracle_repeat_rich(examples, trav_emu, tmp_path):
     """examples at k=15: repeat-rich, so the pushes meet vertices that occur several times on a chromosome (push_group), more
     than 32 instances (bisected order, spill arena) and the general vote.  Evaluations whose result has more than 32
