@@ -44,8 +44,12 @@ void SetErr(char *err, size_t errlen, const std::string &m)
 int Build(const uint8_t *const *seq, const uint64_t *len, int n, int k, uint64_t abundance, int device, double ms_parse, bool keep,
           lcg_graph **out, char *err, size_t errlen)
 {
-    if (k < 1 || k > 31 || k % 2 == 0) {
-        SetErr(err, errlen, "value of K must be odd and at most 31");
+    if (k < 1 || k % 2 == 0) {
+        SetErr(err, errlen, "value of K must be odd");
+        return LCG_ERR_ARG;
+    }
+    if (k > 31) { // (the reference's CAPACITY template goes to ~600, vertexenumerator.cpp:20-58)
+        SetErr(err, errlen, "k > 31 is not supported by the GPU junction finder (a k-mer is one 64-bit word): use the reference twopaco for this k");
         return LCG_ERR_ARG;
     }
     for (int r = 0; r < n; r++)

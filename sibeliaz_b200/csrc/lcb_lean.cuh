@@ -8,8 +8,9 @@
 //
 // This header is the same algorithm restricted to what nearly every seed of a few-genome input needs:
 //   * at most 32 path instances, kept in shared memory (13-word records: a conflict-free stride);
-//   * at most kLHash/2 path vertices (shared-memory hash with an insertion log, so that Path::Clear and the return to
-//     the best forward state undo insertions instead of copying or zeroing the table);
+//   * at most kLHash/2 + kLPath2 path vertices (the first 128 in a shared-memory hash, the rest of a long path in a
+//     per-warp table in HBM; both with an insertion log, so that Path::Clear and the return to the best forward state
+//     undo insertions instead of copying or zeroing a table);
 //   * every pushed vertex occurs at most 32 times, at most once per chromosome (the lanes evaluate all occurrences at
 //     once against the pre-push state, as push_parallel does);
 //   * look-ahead votes over at most ~160 distinct vertices (any number of walks, four at a time, 24 junctions of each
@@ -32,14 +33,14 @@ constexpr int kLInst = 32;   // instances (one lane each in the searches)
 #define LCB_LEAN_HASH 256
 #endif
 constexpr int kLHash = LCB_LEAN_HASH; // path hash slots (half of them usable)
-#ifdef LCB_LEAN_MPV_V1
-constexpr int kLVote = 128;
-#else
-constexpr int kLVote = 256;  // vote table slots
-#endif
-constexpr int kLTiers = 3;   // look-ahead depth = 8 * kLTiers junctions per walk
+constexpr int kLVote = 256;     // vote table slots (multi-pass votes)
+constexpr int kLVoteFast = 128; // ... of which the single-pass vote uses the first 128 and resolves by scanning them
+constexpr int kLTiers = 3;     // multi-pass vote: 8 * kLTiers junctions of every walk per pass
+constexpr int kLFastTiers = 2; // single-pass vote: walks of at most 16 junctions (the others take the multi-pass body)
 constexpr int kLChr = 64;    // chr_off entries cached per CTA (C + 1 <= kLChr)
-constexpr int kOk = 0, kBail = 1;
+constexpr int kLHash2 = 8192; // second-level path hash in HBM (per warp): the vertices beyond the first kLHash / 2
+constexpr int kLPath2 = kLHash2 / 2;
+constexpr int kOk = 0, kBail = 1, kRetry = 3;
 // reasons for handing an evaluation back (diagnostics: lcb_stats.lean_bail_why)
 constexpr int kWhyOccurrences = 0, kWhyPathLength = 1, kWhySameChromosome = 2, kWhyInstances = 3, kWhyReadSet = 4, kWhyWalkDepth = 5,
               kWhyVote = 6, kWhyDistance = 7, kWhyCount = 8;
@@ -64,6 +65,7 @@ struct LeanSmem {
     unsigned short hslot[kLHash / 2]; // slot of the i-th inserted vertex (undo log)
     unsigned char good[kLInst], s_good[kLInst];
     unsigned char elist[kLInst]; // list positions of the instances that sit on the path end (one look-ahead walk each)
+    int best_scratch[8];         // result of the out-of-line multi-pass vote (DeepOut)
     unsigned char used[kLVote];  // slots of the vote table that hold a key (so that resolving and emptying it costs what the
                                  // vote had, not what the table could hold)
 #ifdef LCB_TMA_WINDOWS
@@ -87,6 +89,8 @@ struct LCtx { // warp-uniform unless noted
     int lane;
     LeanSmem *sm;
     int2 *rs;   // read-set log of this warp (HBM)
+    int2 *hash2;           // second-level path hash (HBM, all-empty between evaluations), kLHash2 slots
+    unsigned short *hslot2; // its insertion log, kLPath2 entries
     LInst *shadow; // instances at the best forward point (HBM, written at every improvement and read once: restored
                    // instead of Clear + Init + re-push, blocksfinder.h:271-284)
     int rs_cap; // its capacity in intervals
@@ -119,27 +123,51 @@ __device__ __forceinline__ void chr_bounds_s(const LCtx &c, int g, int &lo, int 
     hi = (int)c.chr_off_s[a + 1];
 }
 
+// second level (long paths only): a real function, so that its probe loop is not repeated at every call site
+__device__ __noinline__ int hash_find2(const int2 *hash2, int key)
+{
+    unsigned s = (hash_of(key) >> 10) & (unsigned)(kLHash2 - 1);
+    while (true) {
+        const int2 kv = hash2[s];
+        if (kv.x == key) return kv.y;
+        if (kv.x == 0) return kNotSet;
+        s = (s + 1) & (unsigned)(kLHash2 - 1);
+    }
+}
+
+// The first kLHash / 2 vertices of a path live in shared memory, the rest (long paths only) in the warp's table in HBM.
 __device__ __forceinline__ int hash_find(const LCtx &c, int key) // per-lane key
 {
     unsigned s = (hash_of(key) >> 12) & (unsigned)(kLHash - 1);
     while (true) {
         const int2 kv = c.sm->hash[s];
         if (kv.x == key) return kv.y;
-        if (kv.x == 0) return kNotSet;
+        if (kv.x == 0) break;
         s = (s + 1) & (unsigned)(kLHash - 1);
     }
+    if (c.hcount <= kLHash / 2) return kNotSet;
+    return hash_find2(c.hash2, key);
 }
 
 // uniform key, known to be absent; false: the path outgrew the table
 __device__ __forceinline__ bool hash_insert(LCtx &c, int key, int val)
 {
-    if ((c.hcount + 1) * 2 > kLHash) return false;
     __syncwarp(); // every lane has finished probing before lane 0 changes the table
-    unsigned s = (hash_of(key) >> 12) & (unsigned)(kLHash - 1);
-    while (c.sm->hash[s].x != 0) s = (s + 1) & (unsigned)(kLHash - 1);
-    if (c.lane == 0) {
-        c.sm->hash[s] = make_int2(key, val);
-        c.sm->hslot[c.hcount] = (unsigned short)s;
+    if (c.hcount < kLHash / 2) {
+        unsigned s = (hash_of(key) >> 12) & (unsigned)(kLHash - 1);
+        while (c.sm->hash[s].x != 0) s = (s + 1) & (unsigned)(kLHash - 1);
+        if (c.lane == 0) {
+            c.sm->hash[s] = make_int2(key, val);
+            c.sm->hslot[c.hcount] = (unsigned short)s;
+        }
+    } else {
+        if (c.hcount - kLHash / 2 >= kLPath2) return false;
+        unsigned s = (hash_of(key) >> 10) & (unsigned)(kLHash2 - 1);
+        while (c.hash2[s].x != 0) s = (s + 1) & (unsigned)(kLHash2 - 1);
+        if (c.lane == 0) {
+            c.hash2[s] = make_int2(key, val);
+            c.hslot2[c.hcount - kLHash / 2] = (unsigned short)s;
+        }
     }
     c.hcount++;
     __syncwarp();
@@ -148,11 +176,18 @@ __device__ __forceinline__ bool hash_insert(LCtx &c, int key, int val)
 
 // forget the vertices inserted after the first `keep`: newest first is not needed, the slots simply become empty again
 // (they were empty before their insertion and nothing was inserted behind them that is kept)
+__device__ __noinline__ void hash_erase(LeanSmem *sm, int2 *hash2, const unsigned short *hslot2, int from, int to, int lane)
+{
+    for (int i = from + lane; i < to; i += 32) {
+        if (i < kLHash / 2) sm->hash[sm->hslot[i]].x = 0;
+        else hash2[hslot2[i - kLHash / 2]].x = 0;
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ void hash_truncate(LCtx &c, int keep)
 {
-    for (int i = keep + c.lane; i < c.hcount; i += 32) c.sm->hash[c.sm->hslot[i]].x = 0;
+    if (keep < c.hcount) hash_erase(c.sm, c.hash2, c.hslot2, keep, c.hcount, c.lane);
     c.hcount = keep;
-    __syncwarp();
 }
 
 __device__ __forceinline__ bool rs_add(LCtx &c, int lo, int hi) // uniform
@@ -538,8 +573,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // shared-memory table, closed-form resolution over the slots the vote used (see most_popular_vertex in lcb_traverse.cuh
 // for why the running arg-max has a closed form).
 // Returns kBail when the vote has too many distinct vertices for the table (left empty).
-#ifdef LCB_LEAN_MPV_V1 // A/B: the single-pass vote of the first version (walks deeper than 24 junctions are handed back)
-__device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool try_used, Next &best)
+__device__ __forceinline__ int most_popular_vertex_fast(LCtx &c, bool forward, bool try_used, Next &best)
 {
     LeanSmem *sm = c.sm;
     best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
@@ -572,15 +606,15 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
         const int clo = I.clo, chi = I.chi;
         const int step = (forward == pos) ? 1 : -1;
         const unsigned seg = 0xFFu << (k * 8);
-        int vid[kLTiers], flag[kLTiers];
-        bool inr[kLTiers], ok[kLTiers], inpath[kLTiers];
+        int vid[kLFastTiers], flag[kLFastTiers];
+        bool inr[kLFastTiers], ok[kLFastTiers], inpath[kLFastTiers];
         {
-            int4 rc[kLTiers];
-            uint32_t ep[kLTiers];
+            int4 rc[kLFastTiers];
+            uint32_t ep[kLFastTiers];
 #if defined(LCB_TMA_WINDOWS) && defined(__CUDACC__)
             // window of the walk: records [a, b) of [wa, wa + 24) inside the chromosome; its epochs: 32 entries from ea
-            const int wa = step > 0 ? og + 1 : og - 8 * kLTiers;
-            const int a = max(wa, clo), b = min(wa + 8 * kLTiers, chi);
+            const int wa = step > 0 ? og + 1 : og - 8 * kLFastTiers;
+            const int a = max(wa, clo), b = min(wa + 8 * kLFastTiers, chi);
             const int ea = max(a - 1, 0) & ~3;
             const bool leader = lane_on && dd == 0 && a < b;
             const unsigned my_bytes = leader ? (unsigned)(b - a) * 16u + (try_used ? 0u : 128u) : 0u;
@@ -597,7 +631,7 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
                 c.tma_phase ^= 1u;
             }
 #pragma unroll
-            for (int t = 0; t < kLTiers; t++) {
+            for (int t = 0; t < kLFastTiers; t++) {
                 const int g = og + step * (t * 8 + dd + 1);
                 inr[t] = lane_on && g >= clo && g < chi; // it.Valid()
                 const bool has = pos || g > clo;
@@ -609,7 +643,7 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
             }
 #else
 #pragma unroll
-            for (int t = 0; t < kLTiers; t++) { // every load of every walk is in flight before the first one is used
+            for (int t = 0; t < kLFastTiers; t++) { // every load of every walk is in flight before the first one is used
                 const int g = og + step * (t * 8 + dd + 1);
                 inr[t] = lane_on && g >= clo && g < chi; // it.Valid()
                 const bool has = pos || g > clo;
@@ -621,7 +655,7 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
             }
 #endif
 #pragma unroll
-            for (int t = 0; t < kLTiers; t++) {
+            for (int t = 0; t < kLFastTiers; t++) {
                 const int d = t * 8 + dd + 1;
                 vid[t] = 0;
                 inpath[t] = false;
@@ -643,34 +677,33 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
             }
         }
         // first junction of every walk that ends it
-        int nok = 8 * kLTiers;
+        int nok = 8 * kLFastTiers;
 #pragma unroll
-        for (int t = kLTiers - 1; t >= 0; t--) {
+        for (int t = kLFastTiers - 1; t >= 0; t--) {
             const unsigned f = __ballot_sync(kFull, lane_on && !ok[t]) & seg;
             if (f) nok = t * 8 + ffs_lane(f) - k * 8;
         }
-        if (__any_sync(kFull, lane_on && nok == 8 * kLTiers)) { // a walk needs more depth than its lanes offer
+        if (__any_sync(kFull, lane_on && nok == 8 * kLFastTiers)) { // a walk needs more depth than its lanes offer
             fail = true;
-            c.why = kWhyWalkDepth;
             break;
         }
         int mylo = 0x7FFFFFFF, myhi = -1;
 #pragma unroll
-        for (int t = 0; t < kLTiers; t++) {
+        for (int t = 0; t < kLFastTiers; t++) {
             const int di = t * 8 + dd; // 0-based depth
             const bool active = lane_on && di < nok;
             const bool stop_in_body = lane_on && di == nok && inr[t];
             const bool dep = flag[t] >= 0 && !try_used && (active || (stop_in_body && !inpath[t]));
             if (dep) mylo = min(mylo, flag[t]), myhi = max(myhi, flag[t]);
             if (active) { // count[vid] += weight; remember the last (list position, depth) that touched it
-                unsigned x = (hash_of(vid[t]) >> 12) & (unsigned)(kLVote - 1);
+                unsigned x = (hash_of(vid[t]) >> 12) & (unsigned)(kLVoteFast - 1);
                 while (true) {
                     const int old = atomicCAS(&sm->vote[x].x, 0, vid[t]);
                     if (old == 0 || old == vid[t]) {
                         if (old == 0) distinct++; // per-lane count, summed below
                         break;
                     }
-                    x = (x + 1) & (unsigned)(kLVote - 1);
+                    x = (x + 1) & (unsigned)(kLVoteFast - 1);
                 }
                 atomicAdd((unsigned *)&sm->vote[x].y, weight);
                 atomicMax(&sm->vlast[x], ((unsigned)q << 20) | (unsigned)(di + 1));
@@ -690,20 +723,20 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
                 if (hi > W.rhi) W.rhi = hi;
             }
         }
-        // the next group inserts up to 4 * 8 * kLTiers keys: go on only while its probing is certain to find empty slots
+        // the next group inserts up to 4 * 8 * kLFastTiers keys: go on only while its probing is certain to find empty slots
         if (gb + 4 < E) {
             const int total_distinct = (int)__reduce_add_sync(kFull, (unsigned)distinct);
-            if (total_distinct + 4 * 8 * kLTiers > kLVote - 1) fail = true, c.why = kWhyVote;
+            if (total_distinct + 4 * 8 * kLFastTiers > kLVoteFast - 1) fail = true;
         }
         __syncwarp();
     }
     // ---- resolve (and leave the table empty): among the vertices with the maximal final count, the one whose LAST
     // increment came from the smallest origin (- strand first, then (chr, idx)), earliest event on ties
-    int2 e[kLVote / 32];
-    unsigned ev[kLVote / 32];
+    int2 e[kLVoteFast / 32];
+    unsigned ev[kLVoteFast / 32];
     unsigned mymax = 0;
 #pragma unroll
-    for (int r = 0; r < kLVote / 32; r++) {
+    for (int r = 0; r < kLVoteFast / 32; r++) {
         e[r] = sm->vote[r * 32 + c.lane];
         ev[r] = sm->vlast[r * 32 + c.lane];
         if (e[r].x != 0) {
@@ -713,13 +746,13 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
         }
     }
     __syncwarp();
-    if (fail) return kBail;
+    if (fail) return kRetry;
     const unsigned M = __reduce_max_sync(kFull, mymax);
     if (M == 0) return kOk;
     unsigned my_okey = 0xFFFFFFFFu, my_ev = 0xFFFFFFFFu;
     int my_vid = 0;
 #pragma unroll
-    for (int r = 0; r < kLVote / 32; r++) {
+    for (int r = 0; r < kLVoteFast / 32; r++) {
         if (e[r].x != 0 && (unsigned)e[r].y == M) {
             const int q = (int)(ev[r] >> 20);
             const LInst &I = sm->inst[use_good ? (int)sm->good[q] : q];
@@ -739,8 +772,7 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
     return kOk;
 }
 
-#else
-__device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool try_used, Next &best)
+__device__ __forceinline__ int most_popular_vertex_deep(LCtx &c, bool forward, bool try_used, Next &best)
 {
     LeanSmem *sm = c.sm;
     best.vid = 0, best.og = 0, best.d = 0, best.opos = false;
@@ -946,15 +978,54 @@ __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool t
     return kOk;
 }
 
+// The vote: the single-pass body first (every walk ends within 24 junctions, a table scan resolves it); the rare vote that
+// does not fit is done again by the multi-pass body (deeper walks, bigger table).  Two bodies instead of one general one
+// because the general one costs the common case 16 % (profiles/ab_tma_graph_r2.md).
+// The multi-pass body as a real function (a cold one): it gets the few fields of the context it reads by value and
+// hands its result back through memory, so that neither its instructions nor its registers sit in the hot path.
+struct DeepOut {
+    Next best;
+    int status, why;
+};
+__device__ __noinline__ void most_popular_vertex_cold(LeanSmem *sm, const int4 *rec, const int2 *occ, const uint32_t *E, const int2 *hash2,
+                                                      int hcount, uint32_t thresh, int b, int depth, int lane, int right_vertex,
+                                                      int left_vertex, int ngood, int ninst, bool forward, bool try_used, DeepOut *out)
+{
+    LCtx c;
+    c.sm = sm, c.rec = rec, c.occ = occ, c.E = E, c.hash2 = const_cast<int2 *>(hash2), c.hcount = hcount, c.thresh = thresh;
+    c.b = b, c.depth = depth, c.lane = lane, c.right_vertex = right_vertex, c.left_vertex = left_vertex;
+    c.ngood = ngood, c.ninst = ninst, c.why = 0;
+#if defined(LCB_TMA_WINDOWS) && defined(__CUDACC__)
+    c.tma_phase = 0; // (the bulk-copy variant is only measured on inputs that never come here)
 #endif
+    Next best;
+    const int status = most_popular_vertex_deep(c, forward, try_used, best);
+    if (lane == 0) out->best = best, out->status = status, out->why = c.why;
+}
+
+__device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool try_used, Next &best)
+{
+    const int r = most_popular_vertex_fast(c, forward, try_used, best);
+    if (r != kRetry) return r;
+    DeepOut *out = (DeepOut *)c.sm->best_scratch; // (shared memory: visible to the whole warp after the call)
+    most_popular_vertex_cold(c.sm, c.rec, c.occ, c.E, c.hash2, c.hcount, c.thresh, c.b, c.depth, c.lane, c.right_vertex, c.left_vertex,
+                             c.ngood, c.ninst, forward, try_used, out);
+    __syncwarp();
+    best = out->best;
+    c.why = out->why;
+    const int status = out->status;
+    __syncwarp();
+    return status;
+}
 
 // ExtendPathForward / ExtendPathBackward (blocksfinder.h:770-895).  Returns 0 failed, 1 success, 2 bail.
 __device__ __forceinline__ int extend_path(LCtx &c, const bool forward, int &best_size, long long &best_score, long long &now_score)
 {
     Next nx;
     nx.vid = 0;
-    if (most_popular_vertex(c, forward, false, nx) != kOk) return 2;
-    if (nx.vid == 0 && forward && most_popular_vertex(c, forward, true, nx) != kOk) return 2; // tryUsed retry (:782-785)
+#pragma unroll 1
+    for (int attempt = 0; attempt < (forward ? 2 : 1) && nx.vid == 0; attempt++) // forward retries with tryUsed (:782-785)
+        if (most_popular_vertex(c, forward, attempt == 1, nx) != kOk) return 2;
     if (nx.vid == 0) return 0;
     bool success = false;
     const int step = (forward == nx.opos) ? 1 : -1;

@@ -214,7 +214,8 @@ void align_impl(const uint8_t *seq, const uint64_t *copy_off, uint64_t n_copies,
         uint64_t m = 0;
         for (uint32_t c = block_off[b]; c < block_off[b + 1]; c++) m = std::max<uint64_t>(m, copy_off[c + 1] - copy_off[c]);
         mx[b] = m, sum[b] = copy_off[block_off[b + 1]] - copy_off[block_off[b]];
-        if (sum[b] >= 0x7FFFFFF0ull) throw Fail{LCA_ERR_CAPACITY, "block " + std::to_string(b) + " has more than 2^31 characters"};
+        // the worst-case arena (level 2) counts 2 * 31 * characters + ... entries in 32 bits (poa_caps_for): 66 M characters per block
+        if (sum[b] >= 66000000ull) throw Fail{LCA_ERR_CAPACITY, "block " + std::to_string(b) + " has more than 66 M characters in its copies"};
         pool_guess += (uint64_t)(block_off[b + 1] - block_off[b]) * std::min<uint64_t>(sum[b], m + m / 4 + 64);
     }
     auto need = [&](uint32_t b, int level) { return poa::poa_arena_bytes(poa::poa_caps_for(sum[b], mx[b], level), block_off[b + 1] - block_off[b]) + 256; };

@@ -62,6 +62,8 @@ int main(int argc, char **argv)
     memset(lsm.get(), 0, sizeof(lcb::lean::LeanSmem)); // k_traverse_lean zeroes the hash and the vote table once per warp
     std::vector<int2> lean_rs((size_t)lcb::kReadSetMax);
     std::vector<lcb::lean::LInst> lean_shadow((size_t)lcb::lean::kLInst);
+    std::vector<int2> lean_hash2((size_t)lcb::lean::kLHash2, int2{0, 0});
+    std::vector<unsigned short> lean_hslot2((size_t)lcb::lean::kLPath2);
     long long bails = 0;
     std::vector<unsigned char> arena(lcb::arena_stride_of(false) + 256, 0); // spill arena: the hash part must start all-empty
     unsigned char *abase = (unsigned char *)(((uintptr_t)arena.data() + 255) & ~(uintptr_t)255);
@@ -86,6 +88,7 @@ int main(int argc, char **argv)
             lc.lane = l, lc.sm = lsm.get(), lc.rs = lean_rs.data(), lc.rs_cap = (int)lean_rs.size();
             lc.last_clo = lc.last_chi = 0, lc.why = 0;
             lc.shadow = lean_shadow.data();
+            lc.hash2 = lean_hash2.data(), lc.hslot2 = lean_hslot2.data();
             for (int64_t s = 0; s < S; s++) {
                 c.thresh = jobs[(size_t)s].thresh;
                 c.err = 0;

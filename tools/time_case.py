@@ -92,7 +92,7 @@ def main():
         # whole-binary wall clock of the drop-in CLI on the same input, and byte comparison of the GFF
         mine = os.path.join(d, "myout")
         t = time.time()
-        r = subprocess.run([sb.CLI_PATH, "--graph", dbg] + fas + ["-k", str(a.k), "-b", "200", "-o", mine, "-m", "50", "-t", "1",
+        r = subprocess.run([sb.CLI_PATH, "--graph", dbg] + fas + ["-k", str(a.k), "-b", "200", "-o", mine, "-m", "50", "-t", str(min(32, os.cpu_count() or 1)),
                             "--abundance", "150", "--noseq", "--stats"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         print("sibeliaz-lcb (B200) whole binary %.2fs rc=%d" % (time.time() - t, r.returncode))
         print(r.stdout.strip().splitlines()[-2:], r.stderr.strip()[-900:])

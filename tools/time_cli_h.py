@@ -16,7 +16,7 @@ dbg = sys.argv[1]
 d = "/tmp/h"
 os.makedirs(d, exist_ok=True)
 fas = generate(d, "star", 4, 100000000, 0.05, 1)
-args = ["--graph", dbg] + fas + ["-k", "25", "-b", "200", "-m", "50", "-t", "1", "--abundance", "150", "--noseq"]
+args = ["--graph", dbg] + fas + ["-k", "25", "-b", "200", "-m", "50", "-t", str(min(32, os.cpu_count() or 1)), "--abundance", "150", "--noseq"]
 extra = [a for a in sys.argv[2:] if a.startswith("--") and a != "--ref"]
 for rep in range(3):
     t = time.time()

@@ -53,7 +53,7 @@ def main():
     threads = min(32, os.cpu_count() or 1)
     common = ["-k", str(a.k), "-b", "200", "-m", "50", "--abundance", "150", "--noseq"]
     for rep in range(2):
-        dt, rc, r = run([sb.CLI_PATH, "--construct"] + fas + common + ["-t", "1", "-o", d + "/fused", "--stats"], 600,
+        dt, rc, r = run([sb.CLI_PATH, "--construct"] + fas + common + ["-t", str(threads), "-o", d + "/fused", "--stats"], 600,
                         env=dict(os.environ, LCB_LOAD_TRACE="1"))
         print("B200 fused binary (FASTA -> blocks_coords.gff): %.2fs rc=%d" % (dt, rc), flush=True)
         if r is not None:
@@ -61,7 +61,7 @@ def main():
             print(r.stdout.strip().splitlines()[-2:], flush=True)
     dt, rc, r = run([sb.GRAPH_CLI_PATH, "--tmpdir", d, "-t", str(threads), "-k", str(a.k), "--filtermemory", "8", "-o", d + "/b200.dbg"] + fas, 600)
     print("B200 twopaco: %.2fs rc=%d" % (dt, rc), flush=True)
-    dt, rc, r = run([sb.CLI_PATH, "--graph", d + "/b200.dbg"] + fas + common + ["-t", "1", "-o", d + "/two"], 600)
+    dt, rc, r = run([sb.CLI_PATH, "--graph", d + "/b200.dbg"] + fas + common + ["-t", str(threads), "-o", d + "/two"], 600)
     print("B200 sibeliaz-lcb on that junction file: %.2fs rc=%d" % (dt, rc), flush=True)
     print("fused GFF == two-step GFF:", same(d + "/fused/blocks_coords.gff", d + "/two/blocks_coords.gff"), flush=True)
     if a.no_ref:

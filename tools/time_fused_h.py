@@ -16,7 +16,7 @@ k = sys.argv[2] if len(sys.argv) > 2 else "25"
 d = "/tmp/hf"
 os.makedirs(d, exist_ok=True)
 fas = generate(d, "star", 4, length, 0.05, 1)
-common = ["-k", k, "-b", "200", "-m", "50", "-t", "1", "--abundance", "150", "--noseq", "--stats"]
+common = ["-k", k, "-b", "200", "-m", "50", "-t", str(min(32, os.cpu_count() or 1)), "--abundance", "150", "--noseq", "--stats"]
 for rep in range(3):
     t = time.time()
     r = subprocess.run([sb.CLI_PATH, "--construct"] + fas + common + ["-o", d + "/fused"], capture_output=True, text=True, env=dict(os.environ, LCB_LOAD_TRACE="1"))
