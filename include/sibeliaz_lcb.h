@@ -125,6 +125,8 @@ typedef struct lcb_stats {
     uint64_t lean_bail_why[8];             /* ... by reason: > 32 occurrences of a vertex, > 128 path vertices, two occurrences on one
                                               chromosome, > 32 instances, read-set log full, look-ahead walk > 24 junctions, vote table
                                               full, |path distance| >= 2^30 */
+    double ms_tail[6];                     /* the rest of the rounds on the device (%globaltimer, summed): gap after the traversal,
+                                              epochs of committed seeds, claims, change map, validation (+ peer control), commit */
 } lcb_stats;
 
 void lcb_default_params(lcb_params *p);

@@ -62,11 +62,11 @@ class Stats(C.Structure):
                [("ms_enumerate", C.c_double), ("ms_find", C.c_double), ("ms_traverse_kernels", C.c_double),
                 ("traverse_launches", C.c_uint64), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("ms_step_device", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("pool_restarts", C.c_uint64),
-                ("big_arena_runs", C.c_uint64), ("lean_runs", C.c_uint64), ("lean_bails", C.c_uint64), ("lean_bail_why", C.c_uint64 * 8)]
+                ("big_arena_runs", C.c_uint64), ("lean_runs", C.c_uint64), ("lean_bails", C.c_uint64), ("lean_bail_why", C.c_uint64 * 8), ("ms_tail", C.c_double * 6)]
     # keep in sync with lcb_stats in include/sibeliaz_lcb.h (ms_step_device sits right after ms_d2h)
 
     def as_dict(self):
-        return {n: (list(getattr(self, n)) if n == "lean_bail_why" else getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n in ("lean_bail_why", "ms_tail") else getattr(self, n)) for n, _ in self._fields_}
 
 
 class GraphStats(C.Structure):
@@ -76,7 +76,7 @@ class GraphStats(C.Structure):
                [(n, C.c_double) for n in ("ms_parse", "ms_h2d", "ms_device", "ms_edges", "ms_d2h", "ms_total")]
 
     def as_dict(self):
-        return {n: (list(getattr(self, n)) if n == "lean_bail_why" else getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n in ("lean_bail_why", "ms_tail") else getattr(self, n)) for n, _ in self._fields_}
 
 
 _lib = None

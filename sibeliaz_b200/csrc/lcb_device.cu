@@ -94,6 +94,9 @@ struct Control { // device-resident round state, mirrored to pinned host memory 
     unsigned rounds, windows;
     unsigned commit_first, commit_n; // prefix committed by this round's emit kernels
     unsigned long long t_first, t_last; // %globaltimer bracket of this round's traversal kernels
+    // where the rest of a round goes (diagnostics, lcb_stats.ms_tail): %globaltimer at the start of k_rebase, k_claim, k_diff,
+    // k_validate, k_round_end, and sums of the differences (gap after the traversal, rebase, claim, diff, validation, commit)
+    unsigned long long t_mark[5], tail_ns[6];
     unsigned x_entries, x_inst;         // results / instances this rank has stored into its peers' mailboxes this round
     unsigned x_tag_base;                // run number << 22: tags of different runs never compare equal
     unsigned big_runs;            // evaluations that outgrew the per-warp arena and ran in a big slot
@@ -738,6 +741,7 @@ __global__ void k_rebase(uint32_t *dst, const uint32_t *src, size_t n, uint32_t 
         if (sched->done | sched->halt) return;
         c0 = sched->c0;
         if (blockIdx.x == 0 && threadIdx.x == 0) {
+            sched->t_mark[0] = global_ns();
             sched->n0 = 0, sched->n1 = 0, sched->dirty = 0, sched->first_dirty = 0xFFFFFFFFu;
             sched->heavy_done = sched->n_heavy;        // what the general kernel had to do in this round
             sched->head_heavy = 0, sched->n_heavy = 0; // the validation queues the known-heavy seeds of the next round
@@ -755,15 +759,25 @@ __global__ void k_claim(uint32_t *__restrict__ Enew, unsigned lo_seed, unsigned 
     if (sched) {
         if (sched->done | sched->halt) return;
         lo_seed = sched->c0, hi_seed = sched->c1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<Control *>(sched)->t_mark[1] = global_ns();
     }
     const int lane = threadIdx.x & 31;
-    for (unsigned i = lo_seed + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < hi_seed; i += gridDim.x * (blockDim.x >> 5)) {
-        unsigned off, cnt;
-        final_result(win, i & win.mask, off, cnt);
-        for (unsigned t = 0; t < cnt; t++) {
-            int lo, hi;
-            inst_edges(win.inst_pool[off + t], lo, hi);
-            for (int f = lo + lane; f <= hi; f += 32) atomicMin(&Enew[f], i);
+    const unsigned warps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // most seeds have no block to claim: one lane per seed finds the few that do, then the warp writes their edges
+    for (unsigned base = lo_seed + warp * 32u; base < hi_seed; base += warps * 32u) {
+        const unsigned i = base + (unsigned)lane;
+        unsigned off = 0, cnt = 0;
+        if (i < hi_seed) final_result(win, i & win.mask, off, cnt);
+        unsigned m = __ballot_sync(kFull, cnt != 0);
+        while (m) {
+            const int src = ffs_lane(m);
+            m &= m - 1;
+            const unsigned o = __shfl_sync(kFull, off, src), c = __shfl_sync(kFull, cnt, src), seed = base + (unsigned)src;
+            for (unsigned t = 0; t < c; t++) {
+                int lo, hi;
+                inst_edges(win.inst_pool[o + t], lo, hi);
+                for (int f = lo + lane; f <= hi; f += 32) atomicMin(&Enew[f], seed);
+            }
         }
     }
 }
@@ -790,6 +804,7 @@ __global__ void k_diff(const uint4 *__restrict__ Ecur, const uint4 *__restrict__
                        const Control *sched)
 {
     if (sched && (sched->done | sched->halt)) return;
+    if (sched && blockIdx.x == 0 && threadIdx.x == 0) const_cast<Control *>(sched)->t_mark[2] = global_ns();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) { // n4 is a multiple of 32: whole warps
         const uint4 a = Ecur[t], b = Enew[t];
@@ -855,6 +870,7 @@ __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__
     if (sched) {
         if (ctl->done | ctl->halt) return;
         lo_seed = ctl->c0, hi_seed = ctl->c1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->t_mark[3] = global_ns();
     }
     const int lane = threadIdx.x & 31;
     const unsigned warps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -938,6 +954,11 @@ struct SchedParams { // admission thresholds of the round loop (developer knobs,
 // start of a round: admission decision (what the host loop of lcb_find_blocks decides between two rounds)
 __global__ void k_round_begin(Control *ctl, unsigned R, unsigned me)
 {
+    if (ctl->t_mark[4]) { // commit kernels of the round before (also after the last round)
+        const unsigned long long now = global_ns();
+        if (now > ctl->t_mark[4]) ctl->tail_ns[5] += now - ctl->t_mark[4];
+        ctl->t_mark[4] = 0;
+    }
     if (ctl->done | ctl->halt) return;
     if (ctl->c0 == ctl->c1) { // nothing active: no pool entry is referenced any more
         ctl->inst_used = 0, ctl->rs_used = 0;
@@ -974,6 +995,14 @@ __global__ void k_round_end(Control *ctl, SchedParams sp, Mirror *mirror, XchDev
         return;
     }
     if (ctl->inst_used * 2 > sp.inst_cap || ctl->rs_used * 2 > sp.rs_cap) ctl->drain = 1;
+    {
+        const unsigned long long now = global_ns();
+        ctl->t_mark[4] = now;
+        if (ctl->t_last && ctl->t_mark[0] > ctl->t_last) ctl->tail_ns[0] += ctl->t_mark[0] - ctl->t_last;
+        for (int q = 0; q < 3; q++)
+            if (ctl->t_mark[q + 1] > ctl->t_mark[q]) ctl->tail_ns[q + 1] += ctl->t_mark[q + 1] - ctl->t_mark[q];
+        if (now > ctl->t_mark[3]) ctl->tail_ns[4] += now - ctl->t_mark[3];
+    }
     float ms = ctl->t_last > ctl->t_first ? (float)(ctl->t_last - ctl->t_first) * 1e-6f : 0.f;
     unsigned n0_all = ctl->n0;
     if (x.R > 1) { // every rank combines the same R outcomes: same decisions everywhere
@@ -2725,6 +2754,7 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     ctx->st.big_arena_runs = ctx->h_ctl->big_runs;
     ctx->st.lean_runs = ctx->h_ctl->lean_runs;
     ctx->st.lean_bails = ctx->h_ctl->lean_bails;
+    for (int q = 0; q < 6; q++) ctx->st.ms_tail[q] = (double)ctx->h_ctl->tail_ns[q] * 1e-6;
     for (int w = 0; w < 8; w++) ctx->st.lean_bail_why[w] = ctx->h_ctl->lean_why[w];
     ctx->st.traversals_rerun = ctx->h_ctl->runs1;
     ctx->st.t_walk = ctx->h_ctl->ct_walk;
