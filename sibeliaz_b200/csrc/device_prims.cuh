@@ -119,9 +119,18 @@ __global__ void k_gather(const unsigned *perm, const T *in, T *out, unsigned n)
 }
 __global__ void k_is_uniform_digit(const unsigned *hist, unsigned blocks, unsigned n, unsigned *flag)
 {
-    // one thread per digit: if a single digit holds all n keys the pass is the identity
-    unsigned d = threadIdx.x, tot = 0;
-    for (unsigned b = 0; b < blocks; b++) tot += hist[(size_t)d * blocks + b];
-    if (tot == n) *flag = 1;
+    // one CTA per digit (launch with 256 CTAs of 256 threads): if a single digit holds all n keys the pass is the identity
+    __shared__ unsigned part[8];
+    const unsigned d = blockIdx.x;
+    unsigned tot = 0;
+    for (unsigned b = threadIdx.x; b < blocks; b += blockDim.x) tot += hist[(size_t)d * blocks + b];
+    tot = __reduce_add_sync(0xFFFFFFFFu, tot);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned all = 0;
+        for (unsigned w = 0; w < (blockDim.x >> 5); w++) all += part[w];
+        if (all == n) *flag = 1;
+    }
 }
 

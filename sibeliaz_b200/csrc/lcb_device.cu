@@ -685,21 +685,23 @@ __global__ void __launch_bounds__(kThreads, LCB_LEAN_CTAS_PER_SM) k_traverse_lea
     }
 }
 
-// One byte per 64 epoch entries: did any of them change between the current and the new epochs of this round (k_diff)?
-// A seed's validation can only come out differently where something changed, so the validation reads its intervals'
-// bytes (a few hundred KB in all, cache-resident) instead of both epoch arrays.
+// Change map of a round (k_diff): per 64 epoch entries, the smallest seed index that appears in an entry that differs between
+// the current and the new epochs (min over the old and the new value; 0xFFFFFFFF: nothing changed).  A seed sees an edge as
+// used iff its epoch is below the seed's limit, so a change matters to it only if one of the two values is below that limit:
+// changes made by LATER seeds -- nearly all of a round's, the new claims come from the newly admitted seeds -- are invisible.
+// The validation reads these words (under 1 MB in all, cache-resident) instead of both epoch arrays.
 constexpr int kDiffShift = 6;
-__device__ __forceinline__ bool range_dirty(const unsigned char *__restrict__ diff, int lo, int hi)
+__device__ __forceinline__ bool range_dirty(const uint32_t *__restrict__ diff, int lo, int hi, uint32_t limit)
 {
     if (!diff) return true;
     for (int b = lo >> kDiffShift; b <= (hi >> kDiffShift); b++)
-        if (diff[b]) return true;
+        if (diff[b] < limit) return true;
     return false;
 }
 
 // does any edge of result `slot 0` of seed j carry an epoch < limit?   (warp-wide); `was`: the answer against the current epochs
 __device__ __forceinline__ bool result_conflicts(const Window &win, unsigned j, const uint32_t *E, uint32_t limit,
-                                                 int lane, const unsigned char *__restrict__ diff, bool was)
+                                                 int lane, const uint32_t *__restrict__ diff, bool was)
 {
     const unsigned cnt = win.res_cnt[0][j], off = win.res_off[0][j];
     if (diff) { // unchanged epochs under every edge of the result: unchanged answer
@@ -707,7 +709,7 @@ __device__ __forceinline__ bool result_conflicts(const Window &win, unsigned j, 
         for (unsigned t = 0; t < cnt && !any; t++) {
             int lo, hi;
             inst_edges(win.inst_pool[off + t], lo, hi);
-            for (int base = (lo >> kDiffShift) + lane; base <= (hi >> kDiffShift) && !any; base += 32) any = diff[base] != 0;
+            for (int base = (lo >> kDiffShift) + lane; base <= (hi >> kDiffShift) && !any; base += 32) any = diff[base] < limit;
             any = __any_sync(kFull, any);
         }
         if (!any) return was;
@@ -784,14 +786,14 @@ __global__ void k_claim(uint32_t *__restrict__ Enew, unsigned lo_seed, unsigned 
 
 // did any epoch in the read-set change its meaning (< limit) between Ecur and Enew?
 __device__ __forceinline__ bool readset_changed(const int2 *rs, unsigned cnt, const uint32_t *Ecur,
-                                                const uint32_t *Enew, uint32_t limit, int lane, const unsigned char *__restrict__ diff)
+                                                const uint32_t *Enew, uint32_t limit, int lane, const uint32_t *__restrict__ diff)
 {
     bool changed = false;
     for (unsigned base = 0; base < cnt && !changed; base += 32) {
         bool ch = false;
         if (base + lane < cnt) {
             int2 iv = rs[base + lane];
-            if (range_dirty(diff, iv.x, iv.y))
+            if (range_dirty(diff, iv.x, iv.y, limit))
                 for (int f = iv.x; f <= iv.y && !ch; f++) ch = (Ecur[f] < limit) != (Enew[f] < limit);
         }
         changed = __any_sync(kFull, ch);
@@ -799,8 +801,9 @@ __device__ __forceinline__ bool readset_changed(const int2 *rs, unsigned cnt, co
     return changed;
 }
 
-// diff[b] = do the current and the new epochs differ anywhere in entries [64 b, 64 b + 64)?  (n is padded to a multiple of 128)
-__global__ void k_diff(const uint4 *__restrict__ Ecur, const uint4 *__restrict__ Enew, size_t n4, unsigned char *__restrict__ diff,
+// diff[b] = min over the entries of [64 b, 64 b + 64) that differ between the two arrays of min(old, new)   (n is padded to
+// a multiple of 128: whole warps of uint4, two blocks per warp)
+__global__ void k_diff(const uint4 *__restrict__ Ecur, const uint4 *__restrict__ Enew, size_t n4, uint32_t *__restrict__ diff,
                        const Control *sched)
 {
     if (sched && (sched->done | sched->halt)) return;
@@ -808,8 +811,14 @@ __global__ void k_diff(const uint4 *__restrict__ Ecur, const uint4 *__restrict__
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) { // n4 is a multiple of 32: whole warps
         const uint4 a = Ecur[t], b = Enew[t];
-        const unsigned m = __ballot_sync(kFull, a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w);
-        if ((threadIdx.x & 31) == 0) *(unsigned short *)(diff + (t >> 4)) = (unsigned short)(((m & 0xFFFFu) ? 1u : 0u) | ((m >> 16) ? 0x100u : 0u));
+        uint32_t m = kFree;
+        if (a.x != b.x) m = min(m, min(a.x, b.x));
+        if (a.y != b.y) m = min(m, min(a.y, b.y));
+        if (a.z != b.z) m = min(m, min(a.z, b.z));
+        if (a.w != b.w) m = min(m, min(a.w, b.w));
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) m = min(m, __shfl_xor_sync(kFull, m, d)); // the 16 lanes of a block
+        if ((threadIdx.x & 15) == 0) diff[t >> 4] = m;
     }
 }
 
@@ -817,7 +826,7 @@ __global__ void k_diff(const uint4 *__restrict__ Ecur, const uint4 *__restrict__
 // The conflict status of the speculative result depends on replicated data only (results + epochs) and is recomputed by
 // every rank for every seed; the read-sets live with the seed's owner (i % R == me), who alone decides about re-evaluations.
 __device__ __forceinline__ void validate_seed(unsigned i, const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned phase,
-                                              const Window &win, Control *ctl, const unsigned char *__restrict__ diff, int lane, bool own)
+                                              const Window &win, Control *ctl, const uint32_t *__restrict__ diff, int lane, bool own)
 {
     const unsigned j = i & win.mask;
     const uint32_t T = (i / phase) * phase;
@@ -864,7 +873,7 @@ __device__ __forceinline__ void validate_seed(unsigned i, const uint32_t *__rest
 // edges of its result (conflict status), the read-set of its commit-time re-run; almost always nothing did, and the seed costs
 // a few cached byte loads.  The others get the full check by the whole warp.
 __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__restrict__ Enew, unsigned lo_seed,
-                           unsigned hi_seed, unsigned phase, Window win, Control *ctl, int sched, const unsigned char *__restrict__ diff,
+                           unsigned hi_seed, unsigned phase, Window win, Control *ctl, int sched, const uint32_t *__restrict__ diff,
                            unsigned R, unsigned me)
 {
     if (sched) {
@@ -878,7 +887,7 @@ __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__
         for (unsigned i = lo_seed + warp; i < hi_seed; i += warps) validate_seed(i, Ecur, Enew, phase, win, ctl, diff, lane, i % R == me);
         return;
     }
-    constexpr unsigned kLaneIntervals = 16; // a lane looks at read-sets up to this size by itself (all loads in flight at once)
+    constexpr unsigned kBatch = 16, kLaneIntervals = 64; // a lane looks at read-sets up to this size by itself, 16 loads in flight
     for (unsigned base = lo_seed + warp * 32u; base < hi_seed; base += warps * 32u) {
         const unsigned i = base + (unsigned)lane;
         bool need = false;
@@ -891,28 +900,27 @@ __global__ void k_validate(const uint32_t *__restrict__ Ecur, const uint32_t *__
             if (cnt0 > kLaneIntervals || cnt1 > kLaneIntervals || rc > 8u || (c1 && !win.has1[j])) {
                 need = true; // big read-sets go to the whole warp right away (32 intervals at a time)
             } else {
-                const int2 *rs = win.rs_pool + win.rs_off[0][j];
-                int2 iv[kLaneIntervals];
+                for (int slot = 0; slot < 2 && !need; slot++) {
+                    const unsigned cnt = slot ? cnt1 : cnt0;
+                    const uint32_t limit = slot ? i : (i / phase) * phase; // commit-time re-run / speculative evaluation
+                    if (!cnt) continue;
+                    const int2 *rs = win.rs_pool + win.rs_off[slot][j];
+                    for (unsigned b0 = 0; b0 < cnt && !need; b0 += kBatch) {
+                        int2 iv[kBatch];
 #pragma unroll
-                for (unsigned t = 0; t < kLaneIntervals; t++) iv[t] = t < cnt0 ? rs[t] : make_int2(0, -1);
+                        for (unsigned t = 0; t < kBatch; t++) iv[t] = b0 + t < cnt ? rs[b0 + t] : make_int2(0, -1);
 #pragma unroll
-                for (unsigned t = 0; t < kLaneIntervals; t++)
-                    if (iv[t].x <= iv[t].y) need = need || range_dirty(diff, iv[t].x, iv[t].y);
+                        for (unsigned t = 0; t < kBatch; t++)
+                            if (iv[t].x <= iv[t].y) need = need || range_dirty(diff, iv[t].x, iv[t].y, limit);
+                    }
+                }
                 if (!need && rc > 1) {
                     const unsigned ro = win.res_off[0][j];
                     for (unsigned t = 0; t < rc && !need; t++) {
                         int lo, hi;
                         inst_edges(win.inst_pool[ro + t], lo, hi);
-                        need = range_dirty(diff, lo, hi);
+                        need = range_dirty(diff, lo, hi, i); // conflict test: edges claimed by a seed < i
                     }
-                }
-                if (!need && cnt1) {
-                    const int2 *rs1 = win.rs_pool + win.rs_off[1][j];
-#pragma unroll
-                    for (unsigned t = 0; t < kLaneIntervals; t++) iv[t] = t < cnt1 ? rs1[t] : make_int2(0, -1);
-#pragma unroll
-                    for (unsigned t = 0; t < kLaneIntervals; t++)
-                        if (iv[t].x <= iv[t].y) need = need || range_dirty(diff, iv[t].x, iv[t].y);
                 }
             }
         }
@@ -1078,38 +1086,58 @@ __global__ void k_final_counts(unsigned lo, unsigned n, Window win, unsigned *cn
 __global__ void __launch_bounds__(1024) k_emit_scan(unsigned first, unsigned n, Window win, Control *ctl,
                                                      const unsigned *__restrict__ counts, int sched)
 {
-    __shared__ unsigned sb[1024], so[1024];
+    // one CTA; warp w owns the contiguous segment [w * seg, (w + 1) * seg) and walks it 32 seeds at a time (coalesced loads,
+    // shuffle scans): pass 1 totals per warp, a scan of the 32 totals, pass 2 the offsets
+    __shared__ unsigned wb[32], wo[32];
     if (sched) {
         first = ctl->commit_first, n = (ctl->halt ? 0u : ctl->commit_n);
         if (n == 0) return;
     }
-    const unsigned blocks_before = ctl->blocks_done, out_before = ctl->out_done; // updated after the scan's barriers
-    const unsigned per = (n + 1023) / 1024;
-    const unsigned lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+    const unsigned blocks_before = ctl->blocks_done, out_before = ctl->out_done; // updated after the barriers
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned seg = ((n + 31) / 32 + 31) / 32 * 32; // seeds per warp, a multiple of 32
+    const unsigned lo = min(n, w * seg), hi = min(n, lo + seg);
     unsigned nb = 0, no = 0;
-    for (unsigned j = lo; j < hi; j++) {
-        const unsigned cnt = counts[j];
-        nb += cnt ? 1 : 0;
+    for (unsigned t = lo + lane; t < hi; t += 32) {
+        const unsigned cnt = counts[t];
+        nb += cnt ? 1u : 0u;
         no += cnt;
     }
-    sb[threadIdx.x] = nb, so[threadIdx.x] = no;
+    nb = __reduce_add_sync(kFull, nb), no = __reduce_add_sync(kFull, no);
+    if (lane == 0) wb[w] = nb, wo[w] = no;
     __syncthreads();
-    for (unsigned d = 1; d < 1024; d <<= 1) {
-        unsigned vb = threadIdx.x >= d ? sb[threadIdx.x - d] : 0, vo = threadIdx.x >= d ? so[threadIdx.x - d] : 0;
-        __syncthreads();
-        sb[threadIdx.x] += vb, so[threadIdx.x] += vo;
-        __syncthreads();
+    if (w == 0) { // exclusive scan of the warp totals
+        const unsigned vb = wb[lane], vo = wo[lane];
+        unsigned ib = vb, io = vo;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned tb = __shfl_up_sync(kFull, ib, d), to = __shfl_up_sync(kFull, io, d);
+            if ((int)lane >= d) ib += tb, io += to;
+        }
+        wb[lane] = ib - vb, wo[lane] = io - vo;
+        if (lane == 31) {
+            ctl->blocks_done = blocks_before + ib;
+            ctl->out_done = out_before + io;
+        }
     }
-    unsigned b = blocks_before + sb[threadIdx.x] - nb, o = out_before + so[threadIdx.x] - no;
-    for (unsigned t = lo; t < hi; t++) {
-        const unsigned cnt = counts[t], j = (first + t) & win.mask;
-        win.out_off[j] = o;
-        win.blk[j] = cnt ? ++b : 0;
-        o += cnt;
-    }
-    if (threadIdx.x == 1023) {
-        ctl->blocks_done = blocks_before + sb[1023];
-        ctl->out_done = out_before + so[1023];
+    __syncthreads();
+    unsigned b = blocks_before + wb[w], o = out_before + wo[w]; // blocks / instances before this warp's segment
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned t = base + lane;
+        const unsigned cnt = t < hi ? counts[t] : 0u;
+        const unsigned has = cnt ? 1u : 0u;
+        unsigned ib = has, io = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned tb = __shfl_up_sync(kFull, ib, d), to = __shfl_up_sync(kFull, io, d);
+            if ((int)lane >= d) ib += tb, io += to;
+        }
+        if (t < hi) {
+            const unsigned j = (first + t) & win.mask;
+            win.out_off[j] = o + io - cnt;
+            win.blk[j] = cnt ? b + ib : 0u;
+        }
+        b += __shfl_sync(kFull, ib, 31), o += __shfl_sync(kFull, io, 31);
     }
 }
 
@@ -1342,7 +1370,7 @@ struct lcb_ctx {
     lean::LInst *d_lean_shadow = nullptr; // ... and shadow copies of the instance table
     int2 *d_lean_hash2 = nullptr;         // ... and second-level path hashes (all-empty between evaluations)
     unsigned short *d_lean_hslot2 = nullptr;
-    unsigned char *d_diff = nullptr; // one byte per 64 epoch entries: changed in this round? (k_diff; null: LCB_NO_DIFF=1)
+    uint32_t *d_diff = nullptr; // change map of a round: one word per 64 epoch entries (k_diff; null: LCB_NO_DIFF=1)
     lcb_block_instance *d_out = nullptr;
     lcb_stats st{};
     int rank = 0, n_ranks = 1;
@@ -1378,6 +1406,7 @@ struct CachedBlock {
 };
 std::mutex g_cache_mu;
 std::vector<CachedBlock> g_cache;
+std::vector<std::pair<void *, size_t>> g_results; // page-locked result buffers handed out by lcb_find_blocks
 #ifdef LCB_WITH_NCCL
 ncclComm_t g_comm = nullptr; // reused by every context of this process (lcb_comm_init), freed by lcb_trim_cache
 int g_comm_dev = -1, g_comm_rank = -1, g_comm_size = 0;
@@ -1510,7 +1539,7 @@ int radix_sort_word(lcb_ctx *ctx, unsigned **perm, unsigned **tmp, const K *key,
     for (int shift = 0; shift < bits; shift += 8) {
         CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(unsigned), ctx->stream));
         k_radix_hist<K><<<blocks, 256, 0, ctx->stream>>>(*perm, key, shift, n, d_hist, descending ? 1 : 0);
-        k_is_uniform_digit<<<1, 256, 0, ctx->stream>>>(d_hist, blocks, n, d_flag);
+        k_is_uniform_digit<<<256, 256, 0, ctx->stream>>>(d_hist, blocks, n, d_flag);
         unsigned flag = 0;
         CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -2729,10 +2758,18 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     const unsigned out_done = ctx->h_ctl->out_done, blocks_done = ctx->h_ctl->blocks_done;
     // ---- results ----
     auto t_d2h = std::chrono::steady_clock::now();
-    lcb_block_instance *host = (lcb_block_instance *)malloc(sizeof(lcb_block_instance) * std::max<size_t>(out_done, 1));
-    if (!host) {
+    // the result goes to page-locked memory from the block cache (no first-touch page faults, a true DMA copy);
+    // lcb_free_blocks hands it back
+    lcb_block_instance *host = nullptr;
+    const size_t host_bytes = sizeof(lcb_block_instance) * std::max<size_t>(out_done, 1);
+    if (cached_alloc((void **)&host, host_bytes, -1, nullptr) != cudaSuccess || !host) {
+        cudaGetLastError();
         ctx->error = "out of host memory";
         return LCB_ERR_ARG;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_results.emplace_back((void *)host, host_bytes);
     }
     CUDA_TRY(cudaEventRecord(ctx->ev_step1, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(host, ctx->d_out, sizeof(lcb_block_instance) * out_done, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2767,7 +2804,22 @@ extern "C" int lcb_find_blocks(lcb_ctx *ctx, lcb_block_instance **out, uint64_t 
     return LCB_OK;
 }
 
-extern "C" void lcb_free_blocks(lcb_block_instance *p) { free(p); }
+extern "C" void lcb_free_blocks(lcb_block_instance *p)
+{
+    if (!p) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_results.size(); i++)
+            if (g_results[i].first == (void *)p) {
+                bytes = g_results[i].second;
+                g_results.erase(g_results.begin() + (long)i);
+                break;
+            }
+    }
+    if (bytes) cached_free(p, bytes, -1); // page-locked result buffer: back to the block cache
+    else free(p);
+}
 
 extern "C" void lcb_trim_cache(void)
 {
