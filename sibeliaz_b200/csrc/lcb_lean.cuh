@@ -95,6 +95,7 @@ struct LCtx { // warp-uniform unless noted
                    // instead of Clear + Init + re-push, blocksfinder.h:271-284)
     int rs_cap; // its capacity in intervals
     int why;    // why the last evaluation was handed back (kWhy*)
+    int deep_bias; // 0..8: how often the recent look-ahead votes needed the multi-pass body
 #ifdef LCB_TMA_WINDOWS
     unsigned tma_phase; // parity of the mbarrier's current phase
 #endif
@@ -1005,8 +1006,19 @@ __device__ __noinline__ void most_popular_vertex_cold(LeanSmem *sm, const int4 *
 
 __device__ __forceinline__ int most_popular_vertex(LCtx &c, bool forward, bool try_used, Next &best)
 {
-    const int r = most_popular_vertex_fast(c, forward, try_used, best);
-    if (r != kRetry) return r;
+    // On inputs whose walks are usually deeper than the single-pass body covers (many genomes, dense junctions) trying it
+    // first only doubles the work: the warp remembers how its last votes went and goes straight to the multi-pass body
+    // while most of them needed it.
+    if (c.deep_bias < 4) {
+        const int r = most_popular_vertex_fast(c, forward, try_used, best);
+        if (r != kRetry) {
+            c.deep_bias = max(c.deep_bias - 1, 0);
+            return r;
+        }
+        c.deep_bias = min(c.deep_bias + 2, 8);
+    } else {
+        c.deep_bias--; // (an attempt with the fast body every now and then)
+    }
     DeepOut *out = (DeepOut *)c.sm->best_scratch; // (shared memory: visible to the whole warp after the call)
     most_popular_vertex_cold(c.sm, c.rec, c.occ, c.E, c.hash2, c.hcount, c.thresh, c.b, c.depth, c.lane, c.right_vertex, c.left_vertex,
                              c.ngood, c.ninst, forward, try_used, out);

@@ -86,7 +86,7 @@ int main(int argc, char **argv)
             lc.rec = ix.rec, lc.occ = ix.occ, lc.vtx_off = ix.vtx_off, lc.E = E.data(), lc.chr_off_s = ix.chr_off, lc.C = ix.C;
             lc.b = pr.b, lc.m = pr.m, lc.flank = pr.flank, lc.depth = pr.depth;
             lc.lane = l, lc.sm = lsm.get(), lc.rs = lean_rs.data(), lc.rs_cap = (int)lean_rs.size();
-            lc.last_clo = lc.last_chi = 0, lc.why = 0;
+            lc.last_clo = lc.last_chi = 0, lc.why = 0, lc.deep_bias = 0;
             lc.shadow = lean_shadow.data();
             lc.hash2 = lean_hash2.data(), lc.hslot2 = lean_hslot2.data();
             for (int64_t s = 0; s < S; s++) {
