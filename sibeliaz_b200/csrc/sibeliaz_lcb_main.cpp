@@ -179,11 +179,16 @@ int Run(const Options &o, Done done)
     int load_rc = o.construct ? lcb_index_load_fasta(files.data(), (int)files.size(), (int)o.k, &index, err, sizeof err)
                               : lcb_index_load(o.graph.c_str(), files.data(), (int)files.size(), (int)o.k, (int)o.a, &index, err, sizeof err);
     auto t_parsed = std::chrono::steady_clock::now();
-    if (!load_rc && !o.construct) lcb_index_pack(index); // device record layout, built while the context is still coming up (optional step)
+    int pack_rc = 0;
+    if (!load_rc && !o.construct) pack_rc = lcb_index_pack(index); // device record layout, built while the context is still coming up
     auto t_packed = std::chrono::steady_clock::now();
     warm.join();
     if (load_rc) {
         fprintf(stderr, "error: %s\n", err);
+        return done(1);
+    }
+    if (pack_rc) { // (the reference accepts any -a; here a vertex may occur at most 65535 times after the abundance filter)
+        fprintf(stderr, "error: a junction occurs more than 65535 times: lower the abundance threshold (-a)\n");
         return done(1);
     }
     auto t1 = std::chrono::steady_clock::now();

@@ -149,3 +149,21 @@ def test_align_cli_error_contract(tmp_path):
         chunk.write_text("> a;0;4;+;9@ACGT@> b;0;4;+;9@ACGA@\n")
         r = subprocess.run([sb.ALIGN_CLI_PATH, "--cmd", "x", "-o", str(tmp_path / "a.maf"), str(chunk)], capture_output=True, text=True)
         assert r.returncode == 1 and "no CUDA device" in r.stderr and not (tmp_path / "a.maf").exists()
+
+
+def test_cli_rejects_malformed_numbers(tmp_path):
+    """TCLAP (the reference's parser) refuses values that are not entirely a number of the argument's type
+    (sibeliaz.cpp:37-111): so do the three drop-in binaries, before any CUDA call."""
+    import subprocess
+    import sibeliaz_b200 as sb
+    fa = tmp_path / "a.fa"
+    fa.write_text(">a\nACGT\n")
+    for args in (["-k", "abc"], ["-k", " 25"], ["-k", "+25"], ["-k", "4294967297"], ["-b", "-3"], ["-t", "1x"]):
+        r = subprocess.run([sb.CLI_PATH, "--graph", str(tmp_path / "g.dbg"), str(fa)] + args, capture_output=True, text=True)
+        assert r.returncode == 1 and "Couldn't read argument value" in r.stderr, (args, r.stderr)
+    r = subprocess.run([sb.CLI_PATH, "--graph", "x", str(fa), "-k", "24"], capture_output=True, text=True)
+    assert r.returncode == 1 and "must be odd" in r.stderr
+    r = subprocess.run([sb.GRAPH_CLI_PATH, "-k", "abc", "-f", "3", str(fa)], capture_output=True, text=True)
+    assert r.returncode == 1 and "Couldn't read argument value" in r.stderr
+    r = subprocess.run([sb.ALIGN_CLI_PATH, "--gpu", "x", "-o", str(tmp_path / "o.maf")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Couldn't read argument value" in r.stderr
