@@ -2,8 +2,11 @@
 //
 // What runs here replaces BlocksFinder::FindBlocks (SibeliaZ-LCB/blocksfinder.h:453-530):
 //   * seed (bundle) enumeration + sort                         blocksfinder.h:461-503, :517
-//   * the carving-path traversal per seed (lcb_traverse.cuh)   blocksfinder.h:228-310, path.h
+//   * the carving-path traversal per seed                      blocksfinder.h:228-310, path.h
+//       k_traverse_lean (lcb_lean.cuh): the common case in a small body; k_traverse (lcb_traverse.cuh): everything
 //   * the 256-seed phase / ordered-commit protocol             blocksfinder.h:334-433
+//       rounds driven from the device (k_round_begin / k_round_end, tail of a round as a CUDA graph), change map +
+//       lane-per-seed validation, peer-mailbox exchange between GPUs
 //
 // The commit protocol is sequential in the reference.  Here it is evaluated as a FIXPOINT over a window
 // of W seeds (W a multiple of the phase size; all earlier seeds are final):
@@ -138,7 +141,6 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -160,11 +162,10 @@ NcclApi *nccl_api()
         a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
         a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
         a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
-        a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
         a.Broadcast = (decltype(a.Broadcast))dlsym(h, "ncclBroadcast");
         a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
         a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
-        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.AllGather && a.GetErrorString;
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Broadcast && a.AllGather && a.GetErrorString;
         return a;
     }();
     return &api;
@@ -172,7 +173,6 @@ NcclApi *nccl_api()
 #define ncclGetUniqueId nccl_api()->GetUniqueId
 #define ncclCommInitRank nccl_api()->CommInitRank
 #define ncclCommDestroy nccl_api()->CommDestroy
-#define ncclAllReduce nccl_api()->AllReduce
 #define ncclBroadcast nccl_api()->Broadcast
 #define ncclAllGather nccl_api()->AllGather
 #define ncclGetErrorString nccl_api()->GetErrorString
@@ -1401,7 +1401,7 @@ struct lcb_ctx {
 #ifdef LCB_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
-    unsigned *d_counts = nullptr, *d_wnext = nullptr;
+    unsigned *d_counts = nullptr;
     std::vector<void *> allocs, seed_allocs;
     std::vector<size_t> alloc_bytes, seed_alloc_bytes;
     bool arena_dirty = false;
@@ -1783,7 +1783,6 @@ int create_end(lcb_ctx *ctx, const CreateTrace &lap)
     if ((rc = dev_alloc(ctx, &ctx->win.list_heavy, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->win.heavy, W))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_counts, W))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->d_wnext, 8))) return rc;
     ctx->win.inst_cap = kInstPoolCap;
     ctx->win.rs_cap = kRsPoolCap;
     if (const char *e = getenv("LCB_TEST_POOL_ENTRIES")) { // testing aid: tiny result pools force the window-halving retry
