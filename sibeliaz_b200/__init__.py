@@ -311,8 +311,8 @@ class BlocksFinder:
         st = Stats()
         self._check(self._lib.lcb_find_blocks(self._ctx, C.byref(ptr), C.byref(n), C.byref(st)))
         if n.value:
-            buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value * C.sizeof(BlockInstance),))
-            self.blocks = np.frombuffer(bytes(buf), dtype=BLOCK_DTYPE).copy()
+            self.blocks = np.empty(n.value, BLOCK_DTYPE)  # one copy out of the library's (page-locked) buffer
+            C.memmove(self.blocks.ctypes.data, ptr, n.value * C.sizeof(BlockInstance))
         else:
             self.blocks = np.zeros(0, BLOCK_DTYPE)
         self._lib.lcb_free_blocks(ptr)
