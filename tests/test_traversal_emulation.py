@@ -110,6 +110,15 @@ def test_common_case_kernel_code_equals_oracle_star(star_small, trav_emu, tmp_pa
     assert n >= 80 and nonempty >= 60
 
 
+def test_common_case_kernel_long_paths(examples, trav_emu, tmp_path):
+    """examples at k=25 (duplicate-rich, paths of up to 1180 edges): paths beyond the 128 vertices of the shared-memory hash
+    go on in the per-warp second-level table (undo log across both levels), multi-pass votes, up to 32 instances; what
+    does not fit is handed back in the middle of a path."""
+    n, nonempty = emulate_and_compare(examples["k25"], lambda S: list(range(3, S, max(1, S // 70))), trav_emu, str(tmp_path), max_instances=40,
+                                      extra_args=["--lean"])
+    assert n >= 50 and nonempty >= 45
+
+
 def test_common_case_kernel_hands_back_what_it_cannot_do(examples, trav_emu, tmp_path):
     """examples at k=15: nearly every evaluation meets a vertex that occurs several times on one chromosome, i.e. leaves the
     common case in the middle of a path; the shared state must be left clean for the general code every time."""
