@@ -2632,7 +2632,23 @@ int find_blocks_device_loop(lcb_ctx *ctx, float &trav_ms)
         }
         // queue full: wait for the device to finish a round (pinned-memory poll, no stream synchronisation)
         const unsigned seen = mir->rounds_done;
-        while (mir->rounds_done == seen && !mir->done && !mir->halt) std::this_thread::yield();
+        for (unsigned spins = 1; mir->rounds_done == seen && !mir->done && !mir->halt; spins++) {
+            std::this_thread::yield();
+            if ((spins & 0x3FFu) == 0) { // now and then: is the device still alive?  (a faulting kernel never reports a round)
+                const cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) {
+                    ctx->arena_dirty = true;
+                    ctx->error = std::string("the traversal rounds stopped on the device: ") + cudaGetErrorString(q);
+                    return LCB_ERR_CUDA;
+                }
+                if (q == cudaSuccess && mir->rounds_done == seen && !mir->done && !mir->halt) {
+                    // everything queued has run, yet no round was reported: cannot happen (k_round_end reports every round)
+                    ctx->arena_dirty = true;
+                    ctx->error = "the traversal rounds ended without a report from the device";
+                    return LCB_ERR_CUDA;
+                }
+            }
+        }
     }
     ctx->st.rounds = ctx->h_ctl->rounds;
     ctx->st.windows = ctx->h_ctl->windows;
