@@ -48,7 +48,8 @@ typedef struct lcg_stats {
     double ms_total;
 } lcg_stats;
 
-/* FASTA files -> junction list.  k odd, 1 <= k <= 31.  abundance: vertices with more candidate occurrences are dropped
+/* FASTA files -> junction list.  k odd, 1 <= k <= 255 (a k-mer is one 64-bit word up to k = 31, two to eight words
+ * beyond; TwoPaCo's CAPACITY template, vertexenumerator.cpp:20-58).  abundance: vertices with more candidate occurrences are dropped
  * (twopaco -a; pass UINT64_MAX for the wrapper's behaviour). */
 int lcg_build_from_fasta(const char *const *fasta_files, int n_files, int k, uint64_t abundance, int device,
                          lcg_graph **out, char *err, size_t errlen);

@@ -29,11 +29,12 @@
  * (vertices renumbered by first appearance, first appearance positive) in which two files can be compared byte for
  * byte.  tests/test_graph_oracle.py pins this restatement against the compiled reference twopaco in that normal form.
  *
- * Limits: k odd, k <= 31 (one 64-bit word per k-mer).
+ * Limits: k odd.  k <= 31: one 64-bit word per k-mer; larger k: the k-mer as a string (same order: 'A' < 'C' < 'G' < 'T').
  */
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -89,11 +90,13 @@ struct Junction {
     int64_t id;
 };
 
+// Key = uint64_t: 2 bits per base, first base most significant (k <= 31).  Key = std::string: the bases themselves.
+template <class Key>
 struct Builder {
     int k;
     uint64_t mask;
     std::vector<std::string> rec;
-    std::unordered_map<uint64_t, VertexInfo> vtx;
+    std::unordered_map<Key, VertexInfo> vtx;
     std::vector<Junction> out;
 
     // calls f(pos in S', forward k-mer, reverse-complement k-mer, prev code, next code) for every definite k-mer of S'
@@ -109,7 +112,7 @@ struct Builder {
             const int c = at(i);
             if (c < 4) {
                 fw = ((fw << 2) | (uint64_t)c) & mask;
-                rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
+                rc = (rc >> 2) | ((uint64_t)(3 - c) << ((2 * (k - 1)) & 63));
                 definite++;
             } else {
                 fw = rc = 0;
@@ -117,17 +120,30 @@ struct Builder {
             }
             if (i >= (size_t)k && definite >= k) {
                 const size_t pos = i - k + 1; // window S'[pos, pos + k)
-                f(pos, fw, rc, at(pos - 1), at(pos + k));
+                Emit(s, pos, fw, rc, at(pos - 1), at(pos + k), f, (Key *)nullptr);
             }
         }
+    }
+    template <class F>
+    static void Emit(const std::string &, size_t pos, uint64_t fw, uint64_t rc, int prev, int next, F &f, uint64_t *)
+    {
+        f(pos, fw, rc, prev, next);
+    }
+    template <class F>
+    void Emit(const std::string &s, size_t pos, uint64_t, uint64_t, int prev, int next, F &f, std::string *) const
+    {
+        const std::string fw = s.substr(pos - 1, (size_t)k); // S'[pos, pos + k) = s[pos - 1, pos - 1 + k)
+        std::string rc(fw.rbegin(), fw.rend());
+        for (char &c : rc) c = "TGCA"[Code(c)];
+        f(pos, fw, rc, prev, next);
     }
 
     void Run(uint64_t abundance)
     {
-        mask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+        mask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1); // (unused by the string keys)
         // ---- E as per-vertex neighbour masks in canonical orientation
         for (const std::string &s : rec)
-            ForEachKmer(s, [&](size_t, uint64_t fw, uint64_t rc, int prev, int next) {
+            ForEachKmer(s, [&](size_t, const Key &fw, const Key &rc, int prev, int next) {
                 const bool fwd = fw < rc;
                 VertexInfo &v = vtx[fwd ? fw : rc];
                 const uint8_t dummy = (1u << 0) | (1u << 3); // A and T: closed under complement
@@ -146,7 +162,7 @@ struct Builder {
             return in > 1 || outc > 1;
         };
         for (const std::string &s : rec)
-            ForEachKmer(s, [&](size_t, uint64_t fw, uint64_t rc, int prev, int next) {
+            ForEachKmer(s, [&](size_t, const Key &fw, const Key &rc, int prev, int next) {
                 const bool fwd = fw < rc;
                 VertexInfo &v = vtx[fwd ? fw : rc];
                 if (!candidate(v, fwd, prev, next)) return;
@@ -155,7 +171,7 @@ struct Builder {
                 if (v.cand < 0xFFFFFFFFu) v.cand++;
             });
         // ---- bifurcations, ids = 1 + rank of the canonical k-mer
-        std::vector<uint64_t> keys;
+        std::vector<Key> keys;
         for (auto &kv : vtx) {
             VertexInfo &v = kv.second;
             bool bif = false;
@@ -178,7 +194,7 @@ struct Builder {
             const size_t L = s.size();
             if (L < (size_t)k) continue;
             std::vector<Junction> here;
-            ForEachKmer(s, [&](size_t pos, uint64_t fw, uint64_t rc, int prev, int next) {
+            ForEachKmer(s, [&](size_t pos, const Key &fw, const Key &rc, int prev, int next) {
                 const bool fwd = fw < rc;
                 const VertexInfo &v = vtx[fwd ? fw : rc];
                 if (v.id && candidate(v, fwd, prev, next)) here.push_back(Junction{(uint32_t)c, (uint32_t)(pos - 1), fwd ? v.id : -v.id});
@@ -231,30 +247,43 @@ extern "C" {
 /* Builds the junction file of the given FASTA files at vertex size k.  Returns the number of junction records, -1 on error. */
 int64_t gro_build(const char *const *fastas, int n, int k, uint64_t abundance, const char *out_path, char *err, int errlen)
 {
-    if (k < 1 || k > 31 || k % 2 == 0) {
-        snprintf(err, errlen, "k must be odd and <= 31");
+    if (k < 1 || k % 2 == 0) {
+        snprintf(err, errlen, "k must be odd");
         return -1;
     }
-    Builder b;
-    b.k = k;
+    std::vector<std::string> rec;
     std::string e;
     for (int i = 0; i < n; i++)
-        if (!ReadFasta(fastas[i], b.rec, e)) {
+        if (!ReadFasta(fastas[i], rec, e)) {
             snprintf(err, errlen, "%s", e.c_str());
             return -1;
         }
-    for (std::string &s : b.rec)
+    for (std::string &s : rec)
         for (char &c : s)
             if (Code(c) == 4) c = 'N';
-    b.Run(abundance);
+    std::vector<Junction> js;
+    // GRO_STRING_KEYS: the string-keyed restatement for a small k too (a test compares the two)
+    if (k <= 31 && !getenv("GRO_STRING_KEYS")) {
+        Builder<uint64_t> b;
+        b.k = k;
+        b.rec.swap(rec);
+        b.Run(abundance);
+        js.swap(b.out);
+    } else {
+        Builder<std::string> b;
+        b.k = k;
+        b.rec.swap(rec);
+        b.Run(abundance);
+        js.swap(b.out);
+    }
     FILE *f = fopen(out_path, "wb");
     if (!f) {
         snprintf(err, errlen, "Can't create the output file");
         return -1;
     }
-    WriteFile(b.out, f);
+    WriteFile(js, f);
     fclose(f);
-    return (int64_t)b.out.size();
+    return (int64_t)js.size();
 }
 
 /* Label-free normal form of a junction file: vertices renumbered 1, 2, ... by first appearance, the first appearance of

@@ -18,7 +18,7 @@ CLI = os.path.join(BINDIR, "sibeliaz-lcb")
 CLI_GRAPH = os.path.join(BINDIR, "twopaco")
 CLI_ALIGN = os.path.join(BINDIR, "sibeliaz-align")
 SOURCES = ("lcb_device.cu", "lcb_host.cpp", "graph_device.cu", "graph_host.cpp", "poa_device.cu")
-HEADERS = ("lcb_traverse.cuh", "lcb_lean.cuh", "device_prims.cuh", "host_common.h", "graph_internal.h", "poa_core.cuh", "lcb_internal.h", "cli_common.h")
+HEADERS = ("lcb_traverse.cuh", "lcb_lean.cuh", "device_prims.cuh", "graph_kmer.cuh", "host_common.h", "graph_internal.h", "poa_core.cuh", "lcb_internal.h", "cli_common.h")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-pthread"]

@@ -3,7 +3,8 @@
 // (TwoPaCo/src/graphconstructor/vertexenumerator.h:122-466), done exactly with ONE open-addressing k-mer table in HBM.
 //
 // Text layout: G = 'N' rec0 'N' rec1 'N' ... 'N', packed to 2 bits per base + 1 "not definite" bit per base, so that the
-// k-mer starting at any position is two 64-bit loads and a funnel shift (k <= 31).  One thread per position:
+// k-mer starting at any position is two 64-bit loads and a funnel shift (k <= 31; a wider k-mer, up to k = 255, is up to
+// eight words and its table slot names it by the position of one occurrence: graph_kmer.cuh).  One thread per position:
 //
 //   k_pack        bytes -> 2-bit codes + N mask                                         streaming, 1.4 B per base
 //   k_edges       every definite k-mer: canonical key, find-or-insert, OR the neighbour characters it shows (with the
@@ -34,94 +35,7 @@ namespace {
 
 #include "device_prims.cuh"
 
-constexpr uint64_t kEmpty = ~0ULL;
-constexpr int kIdShift = 34;               // info: 0-3 in chars, 4-7 out chars, 8-32 pairs, 33 "a pair seen twice", 34.. id
-constexpr uint64_t kMultiBit = 1ULL << 33;
-
-struct Text {
-    const uint64_t *bits; // 32 bases per word, base i of a word at bits 2i
-    const uint32_t *nm;   // 32 bases per word, bit i set: not definite
-    uint64_t n;           // positions in G
-    int k;
-};
-
-struct Slot { // key and vertex word side by side: one 32-byte sector per probe
-    unsigned long long key, info;
-};
-struct Table {
-    Slot *slot;
-    uint64_t mask;
-};
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x)
-{
-    x ^= x >> 33;
-    x *= 0xff51afd7ed558ccdULL;
-    x ^= x >> 33;
-    x *= 0xc4ceb9fe1a85ec53ULL;
-    x ^= x >> 33;
-    return x;
-}
-
-__device__ __forceinline__ unsigned comp4(unsigned m) // neighbour-character set under complement: bit c -> bit 3 - c
-{
-    return ((m & 1u) << 3) | ((m & 2u) << 1) | ((m & 4u) >> 1) | ((m & 8u) >> 3);
-}
-
-struct Kmer {
-    uint64_t key; // canonical: the smaller of the k-mer and its reverse complement, first base most significant
-    bool fwd;     // the k-mer itself is the canonical one
-    int prev, next; // 0-3, 4 = not definite
-};
-
-// k-mer at position p (1 <= p, p + k < n).  Returns false when it holds a non-definite character.
-__device__ __forceinline__ bool load_kmer(const Text &t, uint64_t p, Kmer &out)
-{
-    const int k = t.k;
-    const uint64_t q = p - 1; // window [p - 1, p + k]: prev, k-mer, next  (k + 2 <= 33 bits of the N mask)
-    const uint64_t w = q >> 5;
-    const unsigned off = (unsigned)(q & 31);
-    const uint64_t nmw = ((uint64_t)t.nm[w] | ((uint64_t)t.nm[w + 1] << 32)) >> off;
-    if ((nmw >> 1) & ((1ULL << k) - 1)) return false;
-    const bool prev_n = nmw & 1, next_n = (nmw >> (k + 1)) & 1;
-    // 2-bit codes of [p - 1, p + k]: up to 66 bits -> the k-mer from two words, prev and next on their own
-    const uint64_t pw = p >> 5;
-    const unsigned po = 2u * (unsigned)(p & 31);
-    uint64_t x = t.bits[pw] >> po;
-    if (po) x |= t.bits[pw + 1] << (64 - po);
-    const uint64_t kmask = (1ULL << (2 * k)) - 1;
-    x &= kmask; // base i of the k-mer at bits 2i
-    const uint64_t r = __brevll(x);
-    const uint64_t fw = (((r & 0x5555555555555555ULL) << 1) | ((r >> 1) & 0x5555555555555555ULL)) >> (64 - 2 * k);
-    const uint64_t rc = ~x & kmask; // reverse complement with ITS first base most significant
-    out.fwd = fw < rc;
-    out.key = out.fwd ? fw : rc;
-    out.prev = prev_n ? 4 : (int)((t.bits[q >> 5] >> (2 * (q & 31))) & 3);
-    const uint64_t e = p + (uint64_t)k;
-    out.next = next_n ? 4 : (int)((t.bits[e >> 5] >> (2 * (e & 31))) & 3);
-    return true;
-}
-
-__device__ __forceinline__ uint64_t find_or_insert(const Table &tb, uint64_t key)
-{
-    uint64_t s = mix64(key) & tb.mask;
-    while (true) {
-        const uint64_t cur = tb.slot[s].key;
-        if (cur == key) return s;
-        if (cur == kEmpty) {
-            const unsigned long long old = atomicCAS(&tb.slot[s].key, (unsigned long long)kEmpty, (unsigned long long)key);
-            if (old == kEmpty || old == key) return s;
-        }
-        s = (s + 1) & tb.mask;
-    }
-}
-
-__device__ __forceinline__ uint64_t find(const Table &tb, uint64_t key) // the key is present
-{
-    uint64_t s = mix64(key) & tb.mask;
-    while (tb.slot[s].key != key) s = (s + 1) & tb.mask;
-    return s;
-}
+#include "graph_kmer.cuh"
 
 __global__ void k_table_init(Slot *slot, uint64_t n)
 {
@@ -159,54 +73,20 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ text, 
     nm[w] = m;
 }
 
-// ---- the table-building pass ---------------------------------------------------------------------------------------
+// ---- the table-building pass and the candidate pass: one thread per position (bodies in graph_kmer.cuh) ----------------
+template <int W>
 __global__ void __launch_bounds__(256) k_edges(Text t, Table tb, unsigned long long *n_kmers)
 {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
-    bool live = false;
-    if (p + (uint64_t)t.k < t.n) {
-        Kmer km;
-        if (load_kmer(t, p, km)) {
-            live = true;
-            // the neighbour characters this occurrence shows; next to a non-definite character the two dummies A and T
-            const unsigned in = km.prev < 4 ? 1u << km.prev : 9u, out = km.next < 4 ? 1u << km.next : 9u;
-            const unsigned long long add = km.fwd ? (in | (out << 4)) : (comp4(out) | (comp4(in) << 4));
-            const uint64_t s = find_or_insert(tb, km.key);
-            if ((tb.slot[s].info & add) != add) atomicOr(&tb.slot[s].info, add);
-        }
-    }
+    const bool live = edges_at<W>(t, tb, p);
     const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_kmers, (unsigned long long)__popc(m));
 }
 
+template <int W>
 __global__ void __launch_bounds__(256) k_candidates(Text t, Table tb, uint8_t *__restrict__ flag, unsigned *__restrict__ count)
 {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (p + (uint64_t)t.k >= t.n) return;
-    Kmer km;
-    if (!load_kmer(t, p, km)) return;
-    const uint64_t s = find(tb, km.key);
-    const unsigned long long info = tb.slot[s].info;
-    const unsigned vin = (unsigned)info & 15u, vout = ((unsigned)info >> 4) & 15u;
-    const int in = km.prev < 4 ? __popc(km.fwd ? vin : vout) : 2;
-    const int out = km.next < 4 ? __popc(km.fwd ? vout : vin) : 2;
-    if (in <= 1 && out <= 1) return;
-    flag[p] = 1;
-    const int cp = km.fwd ? km.prev : (km.next < 4 ? 3 - km.next : 4), cn = km.fwd ? km.next : (km.prev < 4 ? 3 - km.prev : 4);
-    const unsigned long long bit = 1ULL << (8 + cp * 5 + cn);
-    const unsigned long long old = atomicOr(&tb.slot[s].info, bit);
-    if ((old & bit) && !(old & kMultiBit)) atomicOr(&tb.slot[s].info, kMultiBit);
-    if (count) atomicAdd(&count[s], 1u); // only with a finite abundance threshold (twopaco -a)
-}
-
-__device__ __forceinline__ bool is_bifurcation(unsigned long long info)
-{
-    const unsigned pairs = (unsigned)(info >> 8) & 0x1FFFFFFu;
-    if (!pairs) return false;
-    if (pairs & (pairs - 1)) return true; // two different (prev, next) pairs
-    if (!(info & kMultiBit)) return false; // a single candidate occurrence
-    const int p = __ffs((int)pairs) - 1;
-    return p / 5 == 4 || p % 5 == 4; // the shared prev (or next) is 'N': unknown twice
+    candidate_at<W>(t, tb, flag, count, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1);
 }
 
 template <bool FILL>
@@ -319,8 +199,6 @@ __global__ void __launch_bounds__(256) k_flag_write(const uint8_t *__restrict__ 
     for (unsigned mm = m; mm; mm &= mm - 1) out[w++] = base + (uint64_t)(__ffs((int)mm) - 1);
 }
 
-constexpr int32_t kStub = INT32_MIN; // a first / last k-mer of a record that is not a junction: gets a unique id
-
 // first and last k-mer of every record that yields a task (vertexenumerator.h:913-920); bit 1 of the position's flag
 __global__ void k_mark_stubs(const uint64_t *__restrict__ goff, int n_records, int k, uint8_t *__restrict__ flag)
 {
@@ -332,21 +210,28 @@ __global__ void k_mark_stubs(const uint64_t *__restrict__ goff, int n_records, i
     flag[goff[r] + len - (uint64_t)k] |= 2; // the same byte when len == k; no other thread touches these two
 }
 
+template <int W>
 __global__ void k_emit_ids(Text t, Table tb, const uint8_t *__restrict__ flag, const uint64_t *__restrict__ pos, unsigned n,
                            int32_t *__restrict__ id)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t p = pos[i];
-    const unsigned f = flag[p];
-    int32_t out = 0;
-    Kmer km;
-    if ((f & 1u) && load_kmer(t, p, km)) {
-        const long long v = (long long)(tb.slot[find(tb, km.key)].info >> kIdShift);
-        out = (int32_t)(km.fwd ? v : -v);
-    }
-    if (out == 0 && (f & 2u)) out = kStub;
-    id[i] = out;
+    id[i] = id_at<W>(t, tb, flag[p], p);
+}
+
+// ---- k > 31: the bifurcation k-mers' words for the ranking sort, and the ids from the sorted order ------------------
+template <int W>
+__global__ void k_canon_words(Text t, const uint64_t *__restrict__ bif_keys, unsigned n, uint64_t *__restrict__ words)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) canon_words_at<W>(t, bif_keys, n, i, words);
+}
+template <int W>
+__global__ void k_assign_ids_wide(Text t, Table tb, const uint64_t *__restrict__ bif_keys, const unsigned *__restrict__ perm, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) assign_id_at<W>(t, tb, bif_keys[perm[i]], i);
 }
 
 // ---- final list: entries with id != 0 in order, stubs numbered in order, position -> (record, offset) ----------------
@@ -420,8 +305,10 @@ struct Scope { // frees everything on every exit path
     std::vector<void *> dev;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t l2_fetch_before = 0; // != 0: the device's L2 fetch granularity was changed for this stage (LCG_L2_FETCH)
     ~Scope()
     {
+        if (l2_fetch_before) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, l2_fetch_before);
         for (void *p : dev) cudaFree(p);
         for (cudaEvent_t e : ev)
             if (e) cudaEventDestroy(e);
@@ -460,6 +347,23 @@ int exclusive_scan_u32(Scope &sc, const unsigned *in, unsigned *out, size_t n, u
     return LCG_OK;
 }
 
+// k-mer width in 64-bit words -> the matching instantiation (W = 1: k <= 31)
+#define LCG_FOR_WIDTH(width, ...)                         \
+    switch (width) {                                      \
+    case 1: { constexpr int W = 1; __VA_ARGS__; } break;  \
+    default: LCG_FOR_WIDE(width, __VA_ARGS__)             \
+    }
+#define LCG_FOR_WIDE(width, ...)                          \
+    switch (width) {                                      \
+    case 2: { constexpr int W = 2; __VA_ARGS__; } break;  \
+    case 3: { constexpr int W = 3; __VA_ARGS__; } break;  \
+    case 4: { constexpr int W = 4; __VA_ARGS__; } break;  \
+    case 5: { constexpr int W = 5; __VA_ARGS__; } break;  \
+    case 6: { constexpr int W = 6; __VA_ARGS__; } break;  \
+    case 7: { constexpr int W = 7; __VA_ARGS__; } break;  \
+    default: { constexpr int W = 8; __VA_ARGS__; } break; \
+    }
+
 } // namespace
 
 namespace lcg {
@@ -471,6 +375,11 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
     };
     const int k = in.k;
+    if (k < 1 || k > kMaxK) {
+        err = "k must be between 1 and " + std::to_string(kMaxK);
+        return LCG_ERR_ARG;
+    }
+    const int width = (2 * k + 63) / 64; // words of a k-mer
     const bool trace = getenv("LCG_TRACE") != nullptr;
     cudaStream_t trace_stream = nullptr;
     auto lap = [&](const char *what) { // developer aid: synchronising stage timer
@@ -496,6 +405,21 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     CU(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
     for (auto &e : sc.ev) CU(cudaEventCreate(&e));
     trace_stream = sc.stream;
+    if (const char *e = getenv("LCG_L2_FETCH")) {
+        // A/B switch: the table passes read one 16-byte slot per position at a random address; the granularity at which L2
+        // fetches a missing line from HBM (32 / 64 / 128 bytes, a hint) decides how many bytes each of them costs.  Restored
+        // on exit: the stages after this one walk consecutive records.
+        size_t before = 0;
+        if (cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity) == cudaSuccess && before &&
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)) == cudaSuccess) {
+            sc.l2_fetch_before = before;
+            size_t now = 0;
+            cudaDeviceGetLimit(&now, cudaLimitMaxL2FetchGranularity);
+            if (trace) fprintf(stderr, "[graph] L2 fetch granularity %zu -> %zu bytes\n", before, now);
+        } else {
+            cudaGetLastError();
+        }
+    }
     lap("context + stream");
     lcg_stats &st = out.st;
     st.n_records = (uint64_t)in.n_records;
@@ -509,6 +433,10 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     }
     goff[(size_t)in.n_records] = g;
     const uint64_t G = g;                                // positions; G[0] and G[G-1] are 'N'
+    if (width > 1 && G >= kRepMask) { // a wide slot names its k-mer by a 40-bit text position
+        err = "more than 2^40 characters with k > 31";
+        return LCG_ERR_ARG;
+    }
     const uint64_t words = (G + 31) / 32 + 2;            // + padding words read by windows near the end
     const uint64_t padded = words * 32;
     // ---- k-mer table: a power of two >= 2 x positions
@@ -570,10 +498,10 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     const unsigned pos_blocks = (unsigned)((G + 255) / 256);
     lap("init + pack");
     CU(cudaEventRecord(sc.ev[1], sc.stream));
-    k_edges<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_ctr + 2);
+    LCG_FOR_WIDTH(width, k_edges<W><<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_ctr + 2));
     CU(cudaEventRecord(sc.ev[2], sc.stream));
     lap("k_edges");
-    k_candidates<<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_flag, d_cnt);
+    LCG_FOR_WIDTH(width, k_candidates<W><<<pos_blocks, 256, 0, sc.stream>>>(text, tb, d_flag, d_cnt));
     if (in.n_records) k_mark_stubs<<<(in.n_records + 255) / 256, 256, 0, sc.stream>>>(d_goff, in.n_records, k, d_flag);
     lap("k_candidates + stubs");
     int sms = 148;
@@ -610,16 +538,33 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
         if ((rc = dalloc(sc, &d_small, 8, err))) return rc;
         k_iota<<<(nb + 255) / 256, 256, 0, sc.stream>>>(perm, nb);
         st.kernel_launches += 2;
-        for (int shift = 0; shift < 2 * k; shift += 8) { // stable LSD passes over the 2k key bits
-            k_radix_hist<uint64_t><<<sblocks, 256, 0, sc.stream>>>(perm, d_bif, shift, nb, d_hist, 0);
-            if ((rc = exclusive_scan_u32(sc, d_hist, d_hist, hn, d_small, d_hist + hn, st.kernel_launches, err))) return rc;
-            k_radix_scatter<uint64_t><<<sblocks, 256, 0, sc.stream>>>(perm, tmp, d_bif, shift, nb, d_hist, 0);
-            std::swap(perm, tmp);
-            st.kernel_launches += 2;
+        // stable LSD passes over the 2k key bits; a wide k-mer's words are written out first (d_bif then holds slot keys:
+        // fingerprint | position of the representative) and sorted word by word, least significant first
+        uint64_t *d_words = nullptr;
+        if (width > 1) {
+            if ((rc = dalloc(sc, &d_words, (size_t)width * nb, err))) return rc;
+            LCG_FOR_WIDE(width, k_canon_words<W><<<(nb + 255) / 256, 256, 0, sc.stream>>>(text, d_bif, nb, d_words));
+            st.kernel_launches += 1;
         }
-        k_gather<<<(nb + 255) / 256, 256, 0, sc.stream>>>(perm, d_bif, d_sorted, nb);
-        k_assign_ids<<<(nb + 255) / 256, 256, 0, sc.stream>>>(tb, d_sorted, nb);
-        st.kernel_launches += 2;
+        for (int w = 0; w < width; w++) {
+            const uint64_t *keys = width > 1 ? d_words + (size_t)w * nb : d_bif;
+            const int bits = std::min(64, 2 * k - 64 * w);
+            for (int shift = 0; shift < bits; shift += 8) {
+                k_radix_hist<uint64_t><<<sblocks, 256, 0, sc.stream>>>(perm, keys, shift, nb, d_hist, 0);
+                if ((rc = exclusive_scan_u32(sc, d_hist, d_hist, hn, d_small, d_hist + hn, st.kernel_launches, err))) return rc;
+                k_radix_scatter<uint64_t><<<sblocks, 256, 0, sc.stream>>>(perm, tmp, keys, shift, nb, d_hist, 0);
+                std::swap(perm, tmp);
+                st.kernel_launches += 2;
+            }
+        }
+        if (width == 1) {
+            k_gather<<<(nb + 255) / 256, 256, 0, sc.stream>>>(perm, d_bif, d_sorted, nb);
+            k_assign_ids<<<(nb + 255) / 256, 256, 0, sc.stream>>>(tb, d_sorted, nb);
+            st.kernel_launches += 2;
+        } else {
+            LCG_FOR_WIDE(width, k_assign_ids_wide<W><<<(nb + 255) / 256, 256, 0, sc.stream>>>(text, tb, d_bif, perm, nb));
+            st.kernel_launches += 1;
+        }
     }
     lap("collect + sort + ids");
     // ---- flagged positions in genome order
@@ -647,7 +592,7 @@ int run_device(const DeviceInput &in, DeviceOutput &out, std::string &err)
     int32_t *d_jid = nullptr;
     if (nc) {
         k_flag_write<<<fblocks, 256, 0, sc.stream>>>(d_flag, G, d_bo, d_pos);
-        k_emit_ids<<<(nc + 255) / 256, 256, 0, sc.stream>>>(text, tb, d_flag, d_pos, nc, d_id);
+        LCG_FOR_WIDTH(width, k_emit_ids<W><<<(nc + 255) / 256, 256, 0, sc.stream>>>(text, tb, d_flag, d_pos, nc, d_id));
         const unsigned qblocks = (nc + kFinalTile - 1) / kFinalTile;
         unsigned *d_kc = nullptr, *d_sc = nullptr, *d_ko = nullptr, *d_so = nullptr, *d_tile2 = nullptr, *d_tot2 = nullptr;
         if ((rc = dalloc(sc, &d_kc, qblocks, err))) return rc;
@@ -737,15 +682,15 @@ void preload_kernels()
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, k_table_init);
     cudaFuncGetAttributes(&fa, k_pack);
-    cudaFuncGetAttributes(&fa, k_edges);
-    cudaFuncGetAttributes(&fa, k_candidates);
+    cudaFuncGetAttributes(&fa, k_edges<1>); // the one-word instantiations: what the wrapper's defaults (k = 15, 25) use
+    cudaFuncGetAttributes(&fa, k_candidates<1>);
     cudaFuncGetAttributes(&fa, k_mark_stubs);
     cudaFuncGetAttributes(&fa, k_decide<false>);
     cudaFuncGetAttributes(&fa, k_decide<true>);
     cudaFuncGetAttributes(&fa, k_assign_ids);
     cudaFuncGetAttributes(&fa, k_flag_count);
     cudaFuncGetAttributes(&fa, k_flag_write);
-    cudaFuncGetAttributes(&fa, k_emit_ids);
+    cudaFuncGetAttributes(&fa, k_emit_ids<1>);
     cudaFuncGetAttributes(&fa, k_final_count);
     cudaFuncGetAttributes(&fa, k_final_write);
     cudaFuncGetAttributes(&fa, k_iota);

@@ -48,8 +48,8 @@ int Build(const uint8_t *const *seq, const uint64_t *len, int n, int k, uint64_t
         SetErr(err, errlen, "value of K must be odd");
         return LCG_ERR_ARG;
     }
-    if (k > 31) { // (the reference's CAPACITY template goes to ~600, vertexenumerator.cpp:20-58)
-        SetErr(err, errlen, "k > 31 is not supported by the GPU junction finder (a k-mer is one 64-bit word): use the reference twopaco for this k");
+    if (k > 255) { // (the reference's CAPACITY template stops at its build's MAX_CAPACITY, vertexenumerator.cpp:20-58)
+        SetErr(err, errlen, "k > 255 is not supported by the GPU junction finder (a k-mer is at most eight 64-bit words)");
         return LCG_ERR_ARG;
     }
     for (int r = 0; r < n; r++)

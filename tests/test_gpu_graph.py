@@ -56,7 +56,7 @@ def test_in_memory_records_and_edge_cases(tmp_path):
     with pytest.raises(sb.LcbError):
         sb.JunctionGraph(sequences=recs, k=6)     # even k
     with pytest.raises(sb.LcbError):
-        sb.JunctionGraph(sequences=recs, k=33)    # beyond one 64-bit word
+        sb.JunctionGraph(sequences=recs, k=257)   # beyond eight 64-bit words (wider k-mers: tests/test_zz_gpu_wide_k.py)
 
 
 def test_finite_abundance_threshold(star_small, tmp_path):

@@ -3,11 +3,13 @@ made by the reference itself: the committed fixtures (examples k=15 / k=25, star
 compiled reference twopaco) and, where oracle/_ref/twopaco is present, fresh runs on an N-rich multi-record input.
 Comparison is in the label-free normal form (the reference's vertex ids and orientations are seeded from /dev/urandom
 and differ from run to run, see the header of graph_oracle.cpp)."""
+import lzma
 import os
 import subprocess
 
 import pytest
 
+from conftest import GOLDEN
 from graph_cases import write_nrich
 from oracle_binding import REF_TWOPACO, canonical_junctions, graph_oracle_build, run_twopaco
 
@@ -30,6 +32,51 @@ def test_graph_oracle_matches_reference_fixture_star(star_small, tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF_TWOPACO), reason="compiled reference twopaco not present")
 @pytest.mark.parametrize("k", [15, 21])
 def test_graph_oracle_matches_compiled_reference_on_nrich_input(tmp_path, k):
+    fas = write_nrich(str(tmp_path))
+    ref = run_twopaco(fas, k, str(tmp_path / "ref.dbg"), threads=4)
+    mine = str(tmp_path / "mine.dbg")
+    graph_oracle_build(fas, k, mine)
+    assert canonical_junctions(mine) == canonical_junctions(ref)
+
+
+def test_string_keyed_restatement_equals_word_keyed(tmp_path, monkeypatch):
+    """k > 31 uses the k-mer strings themselves as keys; at a small k both variants must write the same file."""
+    fas = write_nrich(str(tmp_path))
+    a, b = str(tmp_path / "words.dbg"), str(tmp_path / "strings.dbg")
+    graph_oracle_build(fas, 21, a)
+    monkeypatch.setenv("GRO_STRING_KEYS", "1")
+    graph_oracle_build(fas, 21, b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+@pytest.mark.parametrize("k", [33, 63, 127])
+def test_graph_oracle_wide_k_matches_reference_fixture_nrich(tmp_path, k):
+    """Vertex sizes beyond one 64-bit word against the compiled reference's junction files (tests/golden/wide_k,
+    made by tests/golden/make_wide_fixtures.py)."""
+    mine = str(tmp_path / "mine.dbg")
+    graph_oracle_build(write_nrich(str(tmp_path)), k, mine)
+    with lzma.open(os.path.join(GOLDEN, "wide_k", "nrich_k%d.canon.xz" % k)) as f:
+        assert canonical_junctions(mine) == f.read()
+
+
+def test_wide_k_pipeline_matches_reference_fixture_star(star_small, tmp_path):
+    """k = 33 end to end on the CPU checkers: restated junction file == the reference twopaco's (normal form), and the
+    LCB restatement on it writes the reference sibeliaz-lcb's blocks_coords.gff byte for byte."""
+    from oracle_binding import Oracle
+    mine = str(tmp_path / "mine.dbg")
+    graph_oracle_build(star_small.fastas, 33, mine)
+    with lzma.open(os.path.join(GOLDEN, "wide_k", "star4x200k_k33.canon.xz")) as f:
+        assert canonical_junctions(mine) == f.read()
+    o = Oracle(mine, star_small.fastas, 33, star_small.a)
+    o.find_blocks(star_small.m, star_small.b)
+    o.generate_output(str(tmp_path / "out"), False, 0, star_small.m)
+    with lzma.open(os.path.join(GOLDEN, "wide_k", "star4x200k_k33.gff.xz")) as f:
+        assert open(tmp_path / "out" / "blocks_coords.gff", "rb").read() == f.read()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TWOPACO), reason="compiled reference twopaco not present")
+@pytest.mark.parametrize("k", [45, 65, 201])
+def test_graph_oracle_wide_k_matches_compiled_reference(tmp_path, k):
     fas = write_nrich(str(tmp_path))
     ref = run_twopaco(fas, k, str(tmp_path / "ref.dbg"), threads=4)
     mine = str(tmp_path / "mine.dbg")
