@@ -1,8 +1,8 @@
 """GPU parity of the junction finder for vertex sizes beyond one 64-bit word (31 < k <= 255; graph_kmer.cuh, Kmer<W> with
 W = 2 .. 8) and of the LCB path behind it at k = 33, through the drop-in binaries (which call the C ABI), each run in its
 own process with a time limit.  Checkers: the CPU restatement (byte for byte) and fixtures made by the compiled reference
-(tests/golden/wide_k).  The same device code runs on the CPU in tests/test_graph_emulation.py.  The file name sorts last:
-this path was written after the last GPU session of round 2 and first runs under the driver."""
+(tests/golden/wide_k).  The same device code runs on the CPU in tests/test_graph_emulation.py.  Green on a B200 in round-2
+session 25 (profiles/gpu_suite_widek_r2.log); the file name sorts last because every case starts its own process."""
 import lzma
 import os
 import subprocess
