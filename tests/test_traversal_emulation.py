@@ -34,8 +34,9 @@ def _epoch_oracle():
     return L
 
 
-def emulate_and_compare(case, sample_of, exe, workdir, thresh=1000, max_instances=10 ** 9, extra_args=()):
-    """Returns (evaluations, non-empty results); asserts that the emulated device code and the oracle agree on every one."""
+def emulate_and_compare(case, sample_of, exe, workdir, thresh=1000, max_instances=10 ** 9, extra_args=(), used_period=150, used_run=40):
+    """Returns (evaluations, non-empty results); asserts that the emulated device code and the oracle agree on every one.
+    Every `used_period` records a run of `used_run` edges counts as used (claimed by seed 0)."""
     st = sb.JunctionStorage(case.graph, case.fastas, case.k, case.a)
     lib = sb.load_library()
     lib.lcb_index_pack.argtypes = [C.c_void_p]
@@ -49,8 +50,8 @@ def emulate_and_compare(case, sample_of, exe, workdir, thresh=1000, max_instance
     vo = np.concatenate([vo, vo[-1:]])
     co = np.ctypeslib.as_array(v.chr_off, shape=(Cn + 1,)).astype(np.uint32)
     E = np.full(N + 32, 0xFFFFFFFF, np.uint32)
-    for g in range(0, N, 150):  # runs of used edges
-        E[g:g + 40] = 0
+    for g in range(0, N, used_period):  # runs of used edges
+        E[g:g + used_run] = 0
     L = _epoch_oracle()
     err = C.create_string_buffer(512)
     files = (C.c_char_p * len(case.fastas))(*[f.encode() for f in case.fastas])
