@@ -2,7 +2,8 @@
 stage's checkers, in the mode spoa's `Global` test and the sibeliaz wrapper share (kNW, 5 / -4 / -8 linear gaps,
 spoa_test.cpp:245-259; sibeliaz:66).  Fixture tests/golden/spoa_sample (made by tests/golden/make_spoa_fixture.py from the
 unmodified reference library): the restatement and the product's core compiled for the host must print the same MSA byte
-for byte, and the MSA must have the properties spoa's Check() asserts (spoa_test.cpp:58-80).  The consensus that test also
+for byte, and the MSA must have the properties spoa's Check() asserts (spoa_test.cpp:58-80); the GPU path does the same in
+tests/test_zzz_gpu_first_run.py.  The consensus that test also
 compares is not part of this path: the wrapper only uses the MSA rows (sibeliaz:64-100)."""
 import lzma
 import os
@@ -57,13 +58,3 @@ def test_product_core_on_host_reproduces_the_reference_msa(sample, tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(HERE, "poa_core_host.cpp")], check=True)
     for level in (0, 2):
         assert subprocess.run([exe, "--chunk", chunk, "--level", str(level)], check=True, stdout=subprocess.PIPE, text=True).stdout == want
-
-
-@pytest.mark.gpu
-def test_gpu_reproduces_the_reference_msa(sample, tmp_path):
-    import sibeliaz_b200 as sb
-    chunk, want = sample
-    out = str(tmp_path / "sample.maf")
-    st = sb.global_alignment([chunk], "sample", out)
-    assert open(out).read() == "##maf version=1\n# sibeliaz v1.2.7 \n# cmd=sample\n" + want
-    assert st["n_blocks"] == 1 and st["kernel_launches"] >= 1

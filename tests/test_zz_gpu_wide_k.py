@@ -56,16 +56,3 @@ def test_k33_star_graph_then_blocks_equal_reference(star_small, tmp_path):
                             "--abundance", "150", "--noseq"], capture_output=True, text=True, timeout=180)
         assert r.returncode == 0, r.stderr[-2000:]
         assert open(os.path.join(out, "blocks_coords.gff"), "rb").read() == want, mode
-
-
-def test_reference_selftest_on_the_gpu(tmp_path):
-    """`twopaco --test` restated (tests/graph_selftest.py, tests/test_graph_selftest.py) against the GPU junction finder:
-    the positions in its junction file are the naively computed ones, for the self-test's k = 3 .. 9 and two wider ones."""
-    import random
-    from graph_selftest import check, make_case, write_fasta
-    chrs = make_case(random.Random(4))
-    fa = write_fasta(str(tmp_path / "test.fa"), chrs)
-    for k in (3, 5, 7, 9, 15, 33):
-        g = sb.JunctionGraph([fa], k)
-        assert check(g.write(str(tmp_path / ("gpu%d.dbg" % k))), chrs, k) > 12
-        g.close()
