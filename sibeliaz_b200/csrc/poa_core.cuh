@@ -546,6 +546,7 @@ POA_HD void run_block(Work &w, const Params &pr, const uint8_t *seq, const uint6
         const uint32_t nodes = w.n_nodes;
         if (nodes != 0 && len != 0) { // sisd_alignment_engine.cpp:268-270: otherwise the alignment is empty
             if ((uint64_t)(nodes + 1) * ((uint64_t)len + 1) > w.cap.max_cells || nodes + len + 2 > w.cap.max_align) {
+                poa_sync(); // every lane has read w.err (end of the previous copy), w.n_nodes and w.cap before the flag is written
                 if (lane == 0) w.err = 1;
                 poa_sync();
                 return;

@@ -49,10 +49,11 @@ int main(int argc, char **argv)
 {
     std::string chunk;
     poa::Params pr{5, -4, -8};
-    int cta_warps = 0;
+    int cta_warps = 0, first_level = 2; // --level 0|1: start at an optimistic arena level and climb the driver's retry ladder
     for (int i = 1; i < argc; i++) {
         if (std::string(argv[i]) == "--chunk" && i + 1 < argc) chunk = argv[++i];
         else if (std::string(argv[i]) == "--cta" && i + 1 < argc) cta_warps = atoi(argv[++i]);
+        else if (std::string(argv[i]) == "--level" && i + 1 < argc) first_level = atoi(argv[++i]);
     }
     std::ifstream in(chunk);
     if (chunk.empty() || !in || cta_warps < 0 || cta_warps > emu::kMaxWarps) return 1;
@@ -93,10 +94,11 @@ int main(int argc, char **argv)
         uint64_t sum = seq.size(), mx = 0;
         for (uint32_t c = 0; c < copies; c++) mx = std::max<uint64_t>(mx, off[c + 1] - off[c]);
         poa::Work w; // shared by the 32 lanes, like the kernel's shared-memory copy
-        poa::Caps caps = poa::poa_caps_for(sum, mx, 2);
+        std::vector<std::string> rows(copies);
+        for (int level = first_level;; level++) { // a block that outgrows its arena reports err = 1 and runs again one level up
+        poa::Caps caps = poa::poa_caps_for(sum, mx, level);
         std::vector<uint8_t> arena(poa::poa_arena_bytes(caps, copies) + 64, 0xCD);
         poa::poa_bind(w, arena.data(), caps, copies);
-        std::vector<std::string> rows(copies);
         std::vector<std::thread> lanes;
         for (int t = 0; t < nthreads; t++)
             lanes.emplace_back([&, t]() {
@@ -120,9 +122,15 @@ int main(int argc, char **argv)
                 }
             });
         for (auto &t : lanes) t.join();
+        if (w.err == 1 && level < 2) {
+            fprintf(stderr, "block retried at level %d\n", level + 1);
+            continue;
+        }
         if (w.err) {
             fprintf(stderr, "poa core failed: err %d\n", w.err);
             return 2;
+        }
+        break;
         }
         std::cout << "\na\n";
         for (uint32_t k = 0; k < copies; k++) std::cout << header[k] << ' ' << rows[k] << "\n";

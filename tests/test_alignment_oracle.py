@@ -136,3 +136,11 @@ def test_warp_row_kernel_under_emulation(tmp_path):
     emulate("cta4", blocks[:4], 4)
     emulate("cta1", [blocks[5]], 1)
     emulate("cta2", [[(h, s2[:300]) for h, s2 in blocks[5]]], 2)
+    # a block that outgrows the optimistic arena level 0 (30 noisy copies of a 60-character ancestor: more graph nodes than
+    # 2 x the longest copy): every lane must leave the block together with err = 1, and the run one level up -- the device
+    # driver's retry ladder -- must give the restatement's rows
+    noisy = [[("n%d;0;9;+;99" % i, mutate(blocks[4][0][1][:60], 0.3)) for i in range(30)]]
+    f = write_chunk(str(tmp_path / "level0.tmp"), noisy)
+    for cta in (0, 2):
+        r = subprocess.run([exe, "--chunk", f, "--cta", str(cta), "--level", "0"], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert "block retried at level 1" in r.stderr and r.stdout == poa_oracle_text(f), cta
